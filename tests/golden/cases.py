@@ -1,0 +1,85 @@
+"""Registry of golden cases: name -> (workload factory, compute_modes kwargs, store_fields)."""
+import numpy as np
+
+from tidy3d_b200 import workloads as W
+
+
+def _nonuniform(n=56):
+    """Strip on a graded (non-uniform) grid with PML and a PMC/PEC symmetry pair."""
+    wl = W.si_strip(n, 3)
+    g = np.linspace(-1, 1, n + 1)
+    c = 1.5 * (0.55 * g + 0.45 * g**3)
+    wl.coords = [c.copy(), c.copy()]
+    ctr = 0.5 * (c[:-1] + c[1:])
+    core = (np.abs(ctr)[:, None] <= 0.225) & (np.abs(ctr)[None, :] <= 0.11)
+    e = np.where(core, 3.48**2, 1.44**2).astype(complex)
+    z = np.zeros_like(e)
+    wl.eps_cross = [e, z, z, z, e.copy(), z, z, z, e.copy()]
+    wl.mode_spec.num_pml = (6, 6)
+    wl.mode_spec.target_neff = 2.2
+    wl.name = f"nonuniform_{n}"
+    return wl
+
+
+def _lossy(n=48):
+    wl = W.si_strip(n, 3)
+    wl.eps_cross = [e * (1 + 0.01j) if i in (0, 4, 8) else e for i, e in enumerate(wl.eps_cross)]
+    wl.name = f"lossy_{n}"
+    return wl
+
+
+def _slab1d(axis):
+    n = 200
+    c = np.linspace(-1.5, 1.5, n + 1)
+    ctr = 0.5 * (c[:-1] + c[1:])
+    prof = np.where(np.abs(ctr) <= 0.11, 3.48**2, 1.44**2).astype(complex)
+    e = prof[None, :] if axis == 0 else prof[:, None]
+    z = np.zeros_like(e)
+    one = np.array([-0.5, 0.5])
+    coords = [one, c] if axis == 0 else [c, one]
+    pml = (0, 10) if axis == 0 else (10, 0)
+    return W.Workload(
+        name=f"slab1d_axis{axis}", eps_cross=[e, z, z, z, e.copy(), z, z, z, e.copy()], coords=coords,
+        freqs=np.array([W.C_0 / 1.55]), mode_spec=W.ModeSpecLike(num_modes=3, num_pml=pml, target_neff=2.5),
+    )  # fmt: skip
+
+
+def _offdiag(n=48):
+    wl = W.si_strip(n, 3)
+    e = wl.eps_cross[0]
+    wl.eps_cross[1] = 0.05 * e
+    wl.eps_cross[3] = 0.05 * e
+    wl.name = f"offdiag_{n}"
+    return wl
+
+
+# name: (factory, kwargs for compute_modes, store full fields?)
+CASES = {
+    "c1_64": (W.c1, {}, True),
+    "c1_64_minus": (W.c1, {"direction": "-"}, True),
+    "c1_64_sym_pmc_pec": (W.c1, {"symmetry": (1, -1)}, True),
+    "strip_128_m4": (lambda: W.si_strip(128, 4), {}, False),
+    "c3_96": (lambda: W.c3(96), {}, False),
+    "c3_128": (lambda: W.c3(128), {}, False),
+    "c4_96": (lambda: W.c4(96), {}, False),
+    "c4_128": (lambda: W.c4(128), {}, False),
+    "c4_96_axis0": (lambda: _axis0(W.c4(96)), {}, False),
+    "nonuniform_56": (_nonuniform, {"symmetry": (0, 1)}, True),
+    "lossy_48": (_lossy, {}, True),
+    "slab1d_x1": (lambda: _slab1d(0), {}, True),
+    "slab1d_y1": (lambda: _slab1d(1), {}, True),
+    "angled_64": (lambda: W.angled(64), {}, True),
+    "angled_48_minus": (lambda: W.angled(48), {"direction": "-"}, True),
+    "angled_phi_48": (lambda: W.angled(48, theta=0.3, phi=0.7), {}, True),
+    "offdiag_48": (_offdiag, {}, True),
+    "c2_256_f0": (lambda: W.c2(1), {}, False),
+    "headline_512_f0": (lambda: W.headline(1), {}, False),
+    "c3_512": (W.c3, {}, False),
+    "c4_512": (W.c4, {}, False),
+}
+
+
+def _axis0(wl):
+    wl.mode_spec.bend_axis = 0
+    wl.name += "_axis0"
+    return wl

@@ -1,0 +1,57 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (oracle/ref_shim.py).
+
+Build-container only (needs /root/reference).  Usage:
+    python tests/golden/make_golden.py [case ...]        # default: all cases not yet on disk
+Each fixture ``<case>.npz`` holds n_complex at the reference tolerance (TOL_EIGS = fp_eps) and at
+TOL_EIGS = 1e-12 ("tight"), eps_spec, the tight mode fields when the grid is small, and always a
+per-mode field signature (|E|,|H| component norms) that is phase independent.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_shim  # noqa: E402
+from tests.golden.cases import CASES  # noqa: E402
+
+
+def signature(fields):
+    """(M, 6) array of component 2-norms per mode after unit-normalising the in-plane E part."""
+    f = fields.reshape(6, -1, fields.shape[-1])
+    scale = np.sqrt((np.abs(f[:2]) ** 2).sum(axis=(0, 1)))
+    return (np.sqrt((np.abs(f) ** 2).sum(axis=1)) / scale).T
+
+
+def run(name):
+    factory, kw, store = CASES[name]
+    wl = factory()
+    ref = ref_shim.load()
+    out = {}
+    for tag, tol in (("ref", None), ("tight", 1e-12)):
+        old = ref.TOL_EIGS
+        if tol is not None:
+            ref.TOL_EIGS = tol
+        t0 = time.time()
+        try:
+            fields, n_complex, spec = ref_shim.compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, **kw)
+        finally:
+            ref.TOL_EIGS = old
+        out[f"n_{tag}"] = n_complex
+        out[f"sig_{tag}"] = signature(fields)
+        out[f"sec_{tag}"] = time.time() - t0
+        out["spec"] = spec
+        if store and tag == "tight":
+            out["fields_tight"] = fields
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, out["spec"], out["n_ref"], "max|n_ref-n_tight|=%.2e" % np.abs(out["n_ref"] - out["n_tight"]).max(),
+          "%.1fs/%.1fs" % (out["sec_ref"], out["sec_tight"]), flush=True)  # fmt: skip
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or [n for n in CASES if not os.path.exists(os.path.join(HERE, n + ".npz"))]
+    for n in names:
+        run(n)
