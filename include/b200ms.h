@@ -1,0 +1,147 @@
+/*
+ * b200ms.h -- C ABI of the B200-native waveguide mode solver (libb200ms.so).
+ *
+ * Drop-in boundary for the hot path of flexcompute/tidy3d's local mode solver.  Every entry point
+ * names the reference interface it replaces (paths relative to the tidy3d tree):
+ *
+ *   b200ms_solve_batch   <->  tidy3d/plugins/mode/solver.py:941 `compute_modes(eps_cross, coords,
+ *                             freq, mode_spec, mu_cross, split_curl_scaling, symmetry, direction,
+ *                             solver_basis_fields)` == EigSolver.compute_modes (solver.py:33-269),
+ *                             called once per frequency by ModeSolver._solve_single_freq
+ *                             (tidy3d/plugins/mode/mode_solver.py:725); a batch corresponds to the
+ *                             frequency loop ModeSolver._solve_all_freqs (mode_solver.py:655-672).
+ *   b200ms_problem       <->  the argument list above; mode_spec fields as read at
+ *                             solver.py:86-90,198,204,247 (tidy3d/components/mode.py:18-209).
+ *   b200ms_result        <->  the returned tuple (fields[2,3,Nx,Ny,1,M], n_complex[M], eps_spec)
+ *                             (solver.py:257-269).
+ *   error codes          <->  ValueError / RuntimeError raised at solver.py:107, 876, 901.
+ *
+ * Plain C types only (no torch, no C++).  Host pointers in and out; the library owns all device
+ * memory and one CUDA stream per handle.  One handle per GPU; calls on one handle must not overlap.
+ * There is no CPU fallback: without a usable CUDA device b200ms_create fails with B200MS_ERR_CUDA.
+ */
+#ifndef B200MS_H
+#define B200MS_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MS_VERSION 100
+
+/* return codes */
+enum {
+  B200MS_OK = 0,
+  B200MS_ERR_SHAPE = 1,       /* ValueError: "Mismatch between 'coords' and 'esp_cross' shapes." (solver.py:107) */
+  B200MS_ERR_NO_MODES = 2,    /* RuntimeError: "Could not find any eigenmodes for this waveguide." (solver.py:876) */
+  B200MS_ERR_UNSUPPORTED = 3, /* option outside the built scope (tensorial eps / mu_cross / split-curl / basis fields) */
+  B200MS_ERR_CUDA = 4,        /* CUDA runtime failure or no device -- never falls back to the CPU */
+  B200MS_ERR_NOCONV = 5,      /* eigen-iteration did not converge (scipy ArpackNoConvergence analogue) */
+  B200MS_ERR_ARG = 6          /* bad argument (null pointer, num_modes < 1, ...) */
+};
+
+/* eps_spec values, solver.py:364,376,383 */
+enum { B200MS_SPEC_DIAGONAL = 0, B200MS_SPEC_TENSORIAL_REAL = 1, B200MS_SPEC_TENSORIAL_COMPLEX = 2 };
+
+typedef struct b200ms_handle b200ms_handle;
+
+/* One eigenproblem == one compute_modes call (one plane, one frequency). */
+typedef struct {
+  int nx, ny;            /* eps_cross[i].shape */
+  int num_modes;         /* mode_spec.num_modes */
+  int num_pml[2];        /* mode_spec.num_pml */
+  int symmetry[2];       /* 0 none, +1 PMC, -1 PEC at the min wall (solver.py:184,197) */
+  int bend_axis;         /* mode_spec.bend_axis, ignored when bend_radius is NaN */
+  int direction;         /* +1 "+", -1 "-" */
+  int precision;         /* 0 double, 1 single (single: fields are rounded to complex64 precision) */
+  double freq;           /* Hz */
+  double target_neff;    /* NaN == None */
+  double bend_radius;    /* NaN == None */
+  double angle_theta, angle_phi;
+  const double *eps;     /* 9*nx*ny complex128 as interleaved (re,im), component-major xx,xy,...,zz,
+                            each component C-order with y fastest (solver.py:890-901) */
+  const double *coords_x; /* nx+1 */
+  const double *coords_y; /* ny+1 */
+} b200ms_problem;
+
+typedef struct {
+  double *fields;        /* caller-allocated 2*3*nx*ny*1*num_modes complex128 (re,im), reference layout
+                            [E/H][comp][ix][iy][0][mode]; may be NULL to skip fields */
+  double *n_complex;     /* caller-allocated num_modes complex128 (re,im): n_eff + i k_eff */
+  int eps_spec;          /* out: B200MS_SPEC_* */
+  int status;            /* out: per-problem B200MS_* code */
+  int converged;         /* out: number of converged modes */
+  int outer_iters;       /* out: Krylov-Schur restarts */
+  int op_applies;        /* out: shift-invert (OP^-1) applications */
+  int inner_iters;       /* out: total preconditioned GMRES iterations */
+  int stencil_applies;   /* out: fine-grid operator applications (all kinds) */
+  int is_complex;        /* out: 1 if the eigenproblem was solved in complex arithmetic (solver.py:389-411) */
+  double solve_ms;       /* out: device time of the batch this problem was solved in */
+  double max_residual;   /* out: max_i ||A v_i - lambda_i v_i|| / (|lambda_i| ||v_i||) */
+} b200ms_result;
+
+/* Tunables (all have defaults). */
+typedef struct {
+  double eig_tol;        /* relative Ritz residual tolerance (default 1e-9; reference ARPACK tol is 1.19e-7) */
+  double inner_tol;      /* relative residual of the shift-invert solves (default 1e-10) */
+  int ncv;               /* Krylov subspace size, 0 = max(2k+1, 20) like scipy (solver.py:744) */
+  int max_restarts;      /* default 100 */
+  int gmres_restart;     /* default 40 */
+  int gmres_maxit;       /* default 400 */
+  int mg_nu;             /* Jacobi pre/post sweeps (default 2) */
+  int mg_min_size;       /* stop coarsening below this many cells per axis (default 12) */
+  int mg_coarse_iters;   /* Krylov iterations on the coarsest level (default 16) */
+  int max_batch;         /* problems solved concurrently on the device (default 32) */
+  double mg_omega;       /* Jacobi damping (default 0.8) */
+  double mg_ppw;         /* indefinite problems: keep >= this many cells per local wavelength (default 4) */
+  int verbose;
+} b200ms_options;
+
+int b200ms_version(void);
+void b200ms_default_options(b200ms_options *opt);
+/* device < 0: use cudaGetDevice() */
+int b200ms_create(int device, b200ms_handle **out);
+int b200ms_destroy(b200ms_handle *h);
+int b200ms_set_options(b200ms_handle *h, const b200ms_options *opt);
+const char *b200ms_last_error(b200ms_handle *h);
+
+/* Solve nprob independent eigenproblems.  Problems with identical (nx, ny, arithmetic) are batched on
+ * the device.  Returns B200MS_OK if every problem succeeded, else the first failing status (each
+ * result carries its own status). */
+int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_problem *prob, b200ms_result *res);
+
+/* Benchmark / roofline hook: run the fused curl-curl stencil y = (A - sigma) x `nrep` times on
+ * `nbatch` device-resident copies of the operator of `prob` and return the mean kernel time (CUDA
+ * events on the library stream).  mode 0: operator apply, 1: fused Jacobi sweep.  x (2*nx*ny values,
+ * complex128 (re,im)) may be NULL (random); y may be NULL.  bytes_per_apply returns the algorithmic
+ * bytes of one launch (N*(4*s_v + n_coef*s_c) per problem). */
+int b200ms_bench_stencil(b200ms_handle *h, const b200ms_problem *prob, int nbatch, int mode, int nrep,
+                         int flush_l2, const double *x, double *y, double *ms_per_launch,
+                         double *bytes_per_apply);
+
+/* ---- host-only debug hooks (no GPU needed; used by the CPU test-suite) ---------------------- */
+/* complex Schur decomposition A = Q T Q^H of an n x n row-major complex matrix (re,im) */
+int b200ms_debug_schur(int n, const double *a, double *t, double *q);
+/* problem set-up as the solver sees it: writes sigma (re,im), flags[4] = {is_complex, tensorial,
+ * has_mu, eps_is_complex}, target, knorm, 1-D coefficient vectors coef_x[8*nx] / coef_y[8*ny]
+ * (f0,f1,b0,bm complex) and fields[6*nx*ny] complex (exx,eyy,ezz,mxx,myy,mzz). NULL outputs skipped. */
+int b200ms_debug_setup(const b200ms_problem *prob, double *sigma, int *flags, double *target,
+                       double *knorm, double *coef_x, double *coef_y, double *fields);
+/* multigrid hierarchy shapes for a problem: writes up to max_levels (nx,ny) pairs, returns count */
+int b200ms_debug_hierarchy(const b200ms_problem *prob, const b200ms_options *opt, int max_levels,
+                           int *shapes);
+
+/* ---- device debug hooks (GPU tests compare these against the numpy model) ------------------- */
+/* y = (A - sigma) x on level `level` of the hierarchy of `prob`; x,y complex128 2*nxl*nyl */
+int b200ms_debug_apply(b200ms_handle *h, const b200ms_problem *prob, int level, int mode,
+                       const double *x, const double *rhs, double *y);
+/* one multigrid V-cycle z = M^-1 r on the fine level */
+int b200ms_debug_vcycle(b200ms_handle *h, const b200ms_problem *prob, const double *r, double *z);
+/* x = (A - sigma)^-1 b by preconditioned FGMRES; returns iterations and relative residual */
+int b200ms_debug_solve(b200ms_handle *h, const b200ms_problem *prob, const double *b, double *x,
+                       int *iters, double *relres);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MS_H */

@@ -1,0 +1,198 @@
+"""ctypes binding of ``libb200ms.so`` (C ABI declared in ``include/b200ms.h``).
+
+This is the only way the Python layer reaches the solver; there is no Python/NumPy compute path.  If the
+shared library is missing the import of this module raises (build it with ``python -c "import
+__graft_entry__ as g; g.build()"``), and if no CUDA device is usable ``Handle()`` raises -- the product
+never falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200ms.so")
+
+OK, ERR_SHAPE, ERR_NO_MODES, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOCONV, ERR_ARG = range(7)
+SPEC_NAMES = {0: "diagonal", 1: "tensorial_real", 2: "tensorial_complex"}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int), ("ny", C.c_int), ("num_modes", C.c_int), ("num_pml", C.c_int * 2),
+        ("symmetry", C.c_int * 2), ("bend_axis", C.c_int), ("direction", C.c_int), ("precision", C.c_int),
+        ("freq", C.c_double), ("target_neff", C.c_double), ("bend_radius", C.c_double),
+        ("angle_theta", C.c_double), ("angle_phi", C.c_double),
+        ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp),
+    ]  # fmt: skip
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("fields", _dp), ("n_complex", _dp), ("eps_spec", C.c_int), ("status", C.c_int), ("converged", C.c_int),
+        ("outer_iters", C.c_int), ("op_applies", C.c_int), ("inner_iters", C.c_int), ("stencil_applies", C.c_int),
+        ("is_complex", C.c_int), ("solve_ms", C.c_double), ("max_residual", C.c_double),
+    ]  # fmt: skip
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("eig_tol", C.c_double), ("inner_tol", C.c_double), ("ncv", C.c_int), ("max_restarts", C.c_int),
+        ("gmres_restart", C.c_int), ("gmres_maxit", C.c_int), ("mg_nu", C.c_int), ("mg_min_size", C.c_int),
+        ("mg_coarse_iters", C.c_int), ("max_batch", C.c_int), ("mg_omega", C.c_double), ("mg_ppw", C.c_double),
+        ("verbose", C.c_int),
+    ]  # fmt: skip
+
+
+EXPORTS = [
+    "b200ms_version", "b200ms_default_options", "b200ms_create", "b200ms_destroy", "b200ms_set_options",
+    "b200ms_last_error", "b200ms_solve_batch", "b200ms_bench_stencil", "b200ms_debug_schur", "b200ms_debug_setup",
+    "b200ms_debug_hierarchy", "b200ms_debug_apply", "b200ms_debug_vcycle", "b200ms_debug_solve",
+]  # fmt: skip
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load the shared library (raises OSError with a build hint if it is missing)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise OSError(
+                    f"{LIB_PATH} not found: the CUDA library is not built. Run `python -c \"import __graft_entry__ "
+                    'as g; g.build()"` at the repo root. tidy3d_b200 has no CPU fallback.'
+                )
+            L = C.CDLL(LIB_PATH)
+            L.b200ms_version.restype = C.c_int
+            L.b200ms_default_options.argtypes = [C.POINTER(Options)]
+            L.b200ms_default_options.restype = None
+            L.b200ms_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+            L.b200ms_destroy.argtypes = [C.c_void_p]
+            L.b200ms_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+            L.b200ms_last_error.argtypes = [C.c_void_p]
+            L.b200ms_last_error.restype = C.c_char_p
+            L.b200ms_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Problem), C.POINTER(Result)]
+            L.b200ms_bench_stencil.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
+            L.b200ms_debug_schur.argtypes = [C.c_int, _dp, _dp, _dp]
+            L.b200ms_debug_setup.argtypes = [C.POINTER(Problem), _dp, _ip, _dp, _dp, _dp, _dp, _dp]
+            L.b200ms_debug_hierarchy.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.c_int, _ip]
+            L.b200ms_debug_apply.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, C.c_int, _dp, _dp, _dp]
+            L.b200ms_debug_vcycle.argtypes = [C.c_void_p, C.POINTER(Problem), _dp, _dp]
+            L.b200ms_debug_solve.argtypes = [C.c_void_p, C.POINTER(Problem), _dp, _dp, _ip, _dp]
+            _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+class PackedProblem:
+    """Owns the contiguous arrays a ``Problem`` struct points to."""
+
+    def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None):
+        if eps_packed is not None:
+            eps = eps_packed
+        else:
+            if isinstance(eps_cross, np.ndarray):
+                if eps_cross.shape[0] != 9:
+                    raise ValueError("Wrong input to mode solver pemittivity/permeability!")
+                comps = [eps_cross[i] for i in range(9)]
+            else:
+                if len(eps_cross) != 9:
+                    raise ValueError("Wrong input to mode solver pemittivity/permeability!")
+                comps = list(eps_cross)
+            eps = np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.complex128) for c in comps]))
+        if eps.ndim != 3:
+            raise ValueError("Wrong input to mode solver pemittivity/permeability!")
+        self.eps = eps
+        self.nx, self.ny = eps.shape[1], eps.shape[2]
+        self.cx = np.ascontiguousarray(coords[0], dtype=np.float64)
+        self.cy = np.ascontiguousarray(coords[1], dtype=np.float64)
+        if self.cx.size != self.nx + 1 or self.cy.size != self.ny + 1:
+            raise ValueError("Mismatch between 'coords' and 'esp_cross' shapes.")
+        p = Problem()
+        p.nx, p.ny = self.nx, self.ny
+        p.num_modes = int(mode_spec.num_modes)
+        npml = getattr(mode_spec, "num_pml", (0, 0))
+        p.num_pml[0], p.num_pml[1] = int(npml[0]), int(npml[1])
+        p.symmetry[0], p.symmetry[1] = int(symmetry[0]), int(symmetry[1])
+        br = getattr(mode_spec, "bend_radius", None)
+        p.bend_radius = math.nan if br is None else float(br)
+        ba = getattr(mode_spec, "bend_axis", None)
+        p.bend_axis = -1 if ba is None else int(ba)
+        p.direction = -1 if direction == "-" else 1
+        p.precision = 1 if getattr(mode_spec, "precision", "single") == "single" else 0
+        p.freq = float(freq)
+        tn = getattr(mode_spec, "target_neff", None)
+        p.target_neff = math.nan if tn is None else float(tn)
+        p.angle_theta = float(getattr(mode_spec, "angle_theta", 0.0))
+        p.angle_phi = float(getattr(mode_spec, "angle_phi", 0.0))
+        p.eps, p.coords_x, p.coords_y = _ptr(self.eps.view(np.float64)), _ptr(self.cx), _ptr(self.cy)
+        self.struct = p
+        self.num_modes = p.num_modes
+
+
+class Handle:
+    """One solver handle == one GPU (``b200ms_create`` / ``b200ms_destroy``)."""
+
+    def __init__(self, device: int = -1, **options):
+        self._h = C.c_void_p()
+        rc = lib().b200ms_create(device, C.byref(self._h))
+        if rc != OK:
+            raise RuntimeError(
+                "b200ms_create failed: no usable CUDA device (tidy3d_b200 is GPU-only, there is no CPU fallback)"
+            )
+        self.options = Options()
+        lib().b200ms_default_options(C.byref(self.options))
+        if options:
+            self.set_options(**options)
+
+    def set_options(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.options, k):
+                raise AttributeError(f"unknown solver option {k!r}")
+            setattr(self.options, k, v)
+        lib().b200ms_set_options(self._h, C.byref(self.options))
+
+    def last_error(self) -> str:
+        return lib().b200ms_last_error(self._h).decode()
+
+    def close(self):
+        if self._h:
+            lib().b200ms_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve_batch(self, packed, want_fields=True):
+        """packed: list of PackedProblem.  Returns (fields list | None, n_complex list, Result structs)."""
+        n = len(packed)
+        probs = (Problem * n)(*[p.struct for p in packed])
+        results = (Result * n)()
+        fields, ncs = [], []
+        for i, p in enumerate(packed):
+            nc = np.zeros(p.num_modes, dtype=np.complex128)
+            ncs.append(nc)
+            results[i].n_complex = _ptr(nc.view(np.float64))
+            if want_fields:
+                f = np.empty((2, 3, p.nx, p.ny, 1, p.num_modes), dtype=np.complex128)
+                fields.append(f)
+                results[i].fields = _ptr(f.view(np.float64))
+            else:
+                results[i].fields = None
+        rc = lib().b200ms_solve_batch(self._h, n, probs, results)
+        return rc, (fields if want_fields else None), ncs, results

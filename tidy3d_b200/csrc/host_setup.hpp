@@ -1,0 +1,455 @@
+// Host-side problem set-up: everything EigSolver.compute_modes does before the eigen-solve
+// (tidy3d/plugins/mode/solver.py:86-217, 327-339, 389-411) reduced to what the matrix-free device
+// operator needs, plus the construction of the multigrid hierarchy (ours; no reference analogue).
+#pragma once
+#include <cmath>
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200ms.h"
+
+namespace b200ms {
+
+using cd = std::complex<double>;
+
+// tidy3d/constants.py:16-64
+constexpr double kC0 = 2.99792458e14;
+constexpr double kMu0 = 1.25663706212e-12;
+constexpr double kEps0 = 1.0 / (kMu0 * kC0 * kC0);
+constexpr double kFpEps = 1.1920928955078125e-07;  // np.finfo(np.float32).eps
+constexpr double kPecVal = -1e8;
+constexpr double kTolTensorial = 1e-6;  // solver.py:22
+inline double eta0() { return std::sqrt(kMu0 / kEps0); }
+
+// One axis of one grid level.  Lengths are complex-stretched (PML) and multiplied by k0.
+struct Axis {
+  int n = 0;
+  bool pmc = false;             // PMC instead of PEC at the min wall (solver.py:184)
+  std::vector<cd> lf, lb;       // primal (forward / H-site) and dual (backward / E-site) lengths
+  std::vector<double> pos;      // n+1 real node coordinates (interpolation weights only)
+  // rows of the bidiagonal difference operators, derivatives.py:9-62 with S.D/k0 folded in
+  // (solver.py:201):  (Df v)[i] = f0[i] v[i] + f1[i] v[i+1],  (Db v)[i] = b0[i] v[i] + bm[i] v[i-1]
+  void coefficients(std::vector<cd> &c) const {
+    c.assign((size_t)4 * n, cd(0, 0));
+    if (n <= 1) return;  // derivatives.py:12-13: a 1-cell axis has zero derivative matrices
+    for (int i = 0; i < n; ++i) {
+      c[i] = -1.0 / lf[i];
+      c[n + i] = (i + 1 < n) ? 1.0 / lf[i] : cd(0, 0);
+      c[2 * n + i] = 1.0 / lb[i];
+      c[3 * n + i] = (i > 0) ? -1.0 / lb[i] : cd(0, 0);
+    }
+    if (!pmc) c[0] = 0.0;                      // derivatives.py:15-16
+    c[2 * n] = pmc ? 2.0 / lb[0] : cd(0, 0);   // derivatives.py:28-31
+  }
+};
+
+struct ProblemSetup {
+  int nx = 0, ny = 0, num_modes = 0;
+  int status = B200MS_OK;
+  std::string error;
+  bool is_complex = false;   // eigenproblem arithmetic (solver.py:389-411)
+  bool coef_complex = false; // eps/mu fields have an imaginary part
+  bool tensorial = false, has_mu = false;
+  int eps_spec = B200MS_SPEC_DIAGONAL;
+  double k0 = 0, target = 0, knorm = 1;
+  cd sigma;                  // eigenvalue shift -(target^2) (solver.py:504)
+  int direction = 1;
+  Axis ax[2];
+  std::vector<cd> f[6];      // exx, eyy, ezz, mxx, myy, mzz after Jacobian + PEC model, N each
+  std::vector<double> jz_e, jz_h;  // bend back-transform E_z *= jz_e[ix or iy], H_z *= jz_h (solver.py:254-259)
+  int jz_axis = -1;          // axis along which jz varies (-1: none)
+  double max_k2 = 0;         // max over cells of Re(eps) - target^2 (positive => indefinite region)
+};
+
+inline cd s_value(double dl, double step, double omega, cd avg_speed) {
+  // derivatives.py:200-232 (sigma_max = 2, kappa 1..3, order 3)
+  double p = step * step * step;
+  cd sig = 2.0 * avg_speed / (eta0() * dl) * p;
+  return cd(1.0 + 2.0 * p, 0.0) + cd(0, 1) * sig / (omega * kEps0);
+}
+
+// derivatives.py:174-196
+inline void sfactors(double omega, const std::vector<double> &dlf, const std::vector<double> &dlb, int n,
+                     int npml, bool pml_at_min, cd sp_min, cd sp_max, std::vector<cd> &sf, std::vector<cd> &sb) {
+  sf.assign(n, cd(1, 0));
+  sb.assign(n, cd(1, 0));
+  if (npml == 0) return;
+  for (int i = 0; i < n; ++i) {
+    if (i <= npml - 1 && pml_at_min)
+      sf[i] = s_value(dlf[0], (npml - i - 0.5) / npml, omega, sp_min);
+    else if (i >= n - npml)
+      sf[i] = s_value(dlf[n - 1], (i - (n - npml) + 0.5) / npml, omega, sp_max);
+    if (i < npml && pml_at_min)
+      sb[i] = s_value(dlb[0], double(npml - i) / npml, omega, sp_min);
+    else if (i > n - npml)
+      sb[i] = s_value(dlb[n - 1], double(i - (n - npml)) / npml, omega, sp_max);
+  }
+}
+
+inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
+  const int nx = p.nx, ny = p.ny;
+  s.nx = nx;
+  s.ny = ny;
+  s.num_modes = p.num_modes;
+  s.direction = p.direction < 0 ? -1 : 1;
+  if (nx < 1 || ny < 1 || !p.eps || !p.coords_x || !p.coords_y || p.num_modes < 1) {
+    s.status = B200MS_ERR_ARG;
+    s.error = "bad problem description";
+    return;
+  }
+  const size_t n = (size_t)nx * ny;
+  const cd *eps = reinterpret_cast<const cd *>(p.eps);
+  const double omega = 2.0 * M_PI * p.freq;
+  s.k0 = omega / kC0;
+  const bool bend = !std::isnan(p.bend_radius);
+  const bool angled = std::abs(p.angle_theta) > 0.0;
+
+  // k-vector transformation, solver.py:160-162
+  {
+    double c = std::cos(p.angle_theta), sn = std::sin(p.angle_theta);
+    double kxy = c * c, kz = c * sn;
+    double a = kxy * std::sin(p.angle_phi), b = kxy * std::cos(p.angle_phi);
+    s.knorm = std::sqrt(a * a + b * b + kz * kz);
+  }
+  // target, solver.py:204-217
+  if (std::isnan(p.target_neff)) {
+    double mx = 0.0;
+    for (size_t i = 0; i < 9 * n; ++i) {
+      double a = std::abs(eps[i]);
+      if (a < std::abs(kPecVal) && a > mx) mx = a;
+    }
+    s.target = std::sqrt(mx);
+  } else {
+    s.target = p.target_neff;
+  }
+  s.target /= s.knorm;
+  const double shift = 10 * kFpEps;
+  if (std::abs(shift) > std::abs(s.target * shift))
+    s.target += shift;
+  else
+    s.target *= 1 + shift;
+  s.sigma = cd(-(s.target * s.target), 0.0);
+
+  // coordinates and Jacobian (transforms.py:14-71); only dwdz != 1 for a bend
+  std::vector<double> coords[2] = {std::vector<double>(p.coords_x, p.coords_x + nx + 1),
+                                   std::vector<double>(p.coords_y, p.coords_y + ny + 1)};
+  std::vector<double> de, dh;  // dwdz at E / H sites along the normal axis
+  int norm_axis = -1;
+  if (bend) {
+    norm_axis = (p.bend_axis == 1) ? 0 : 1;
+    std::vector<double> &c = coords[norm_axis];
+    const int nn = (int)c.size() - 1;
+    const double off = p.bend_radius - c[nn / 2];
+    for (double &v : c) v += off;
+    de.resize(nn);
+    dh.resize(nn);
+    for (int i = 0; i < nn; ++i) {
+      de[i] = p.bend_radius / c[i];
+      dh[i] = 2.0 * p.bend_radius / (c[i] + c[i + 1]);
+    }
+    s.jz_axis = norm_axis;
+    s.jz_e = de;
+    s.jz_h = dh;
+    s.has_mu = true;
+  }
+  if (angled) {
+    s.tensorial = true;  // J has off-diagonals (transforms.py:74-111) -> solver.py:594
+  }
+
+  // eps' = J eps J^T / det J with J = diag(1,1,d) (solver.py:165-172); mu' likewise from identity
+  for (int k = 0; k < 6; ++k) s.f[k].assign(n, cd(1, 0));
+  double off_max = 0.0, im2 = 0.0, all2 = 0.0;
+  for (int ix = 0; ix < nx; ++ix)
+    for (int iy = 0; iy < ny; ++iy) {
+      const size_t c = (size_t)ix * ny + iy;
+      double d_e = 1.0, d_h = 1.0;
+      if (bend) {
+        int t = norm_axis == 0 ? ix : iy;
+        d_e = de[t];
+        d_h = dh[t];
+      }
+      cd e[9];
+      for (int k = 0; k < 9; ++k) e[k] = eps[(size_t)k * n + c];
+      // J e J^T / det: rows/cols 2 scaled by d, everything / d
+      const double sc[3] = {1.0, 1.0, d_e};
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) e[3 * a + b] *= sc[a] * sc[b] / d_e;
+      s.f[0][c] = e[0];
+      s.f[1][c] = e[4];
+      s.f[2][c] = e[8];
+      s.f[3][c] = 1.0 / d_h;
+      s.f[4][c] = 1.0 / d_h;
+      s.f[5][c] = d_h;
+    }
+
+  // grid steps, solver.py:187-190
+  std::vector<double> dlf[2], dlb[2];
+  for (int a = 0; a < 2; ++a) {
+    const int nn = a == 0 ? nx : ny;
+    dlf[a].resize(nn);
+    dlb[a].resize(nn);
+    for (int i = 0; i < nn; ++i) dlf[a][i] = coords[a][i + 1] - coords[a][i];
+    dlb[a][0] = dlf[a][0];
+    for (int i = 1; i < nn; ++i) dlb[a][i] = 0.5 * (dlf[a][i - 1] + dlf[a][i]);
+  }
+  // average relative speed in the four PML strips (derivatives.py:129-155), BEFORE the PEC model
+  cd speed[4];
+  {
+    const int npx = p.num_pml[0], npy = p.num_pml[1];
+    cd esum[4] = {0, 0, 0, 0}, msum[4] = {0, 0, 0, 0};
+    size_t cnt[4] = {0, 0, 0, 0};
+    for (int ix = 0; ix < nx; ++ix)
+      for (int iy = 0; iy < ny; ++iy) {
+        const size_t c = (size_t)ix * ny + iy;
+        bool in[4] = {ix < npx, ix >= nx - npx + 1, iy < npy, iy >= ny - npy + 1};
+        cd es = s.f[0][c] + s.f[1][c] + s.f[2][c], ms = s.f[3][c] + s.f[4][c] + s.f[5][c];
+        for (int r = 0; r < 4; ++r)
+          if (in[r]) {
+            esum[r] += es;
+            msum[r] += ms;
+            cnt[r] += 3;
+          }
+      }
+    for (int r = 0; r < 4; ++r) {
+      cd ea = cnt[r] ? esum[r] / double(cnt[r]) : cd(1, 0);
+      cd ma = cnt[r] ? msum[r] / double(cnt[r]) : cd(1, 0);
+      speed[r] = 1.0 / std::sqrt(ea * ma);
+    }
+  }
+  bool der_complex = false;
+  for (int a = 0; a < 2; ++a) {
+    const int nn = a == 0 ? nx : ny;
+    Axis &A = s.ax[a];
+    A.n = nn;
+    A.pmc = p.symmetry[a] == 1;
+    A.pos = coords[a];
+    std::vector<cd> sf, sb;
+    sfactors(omega, dlf[a], dlb[a], nn, p.num_pml[a], p.symmetry[a] == 0, speed[2 * a], speed[2 * a + 1], sf, sb);
+    A.lf.resize(nn);
+    A.lb.resize(nn);
+    for (int i = 0; i < nn; ++i) {
+      A.lf[i] = sf[i] * dlf[a][i] * s.k0;
+      A.lb[i] = sb[i] * dlb[a][i] * s.k0;
+    }
+    // complex test on the derivative matrices (solver.py:402, 779-793) via their 1-D factors
+    if (nn > 1) {
+      std::vector<cd> c;
+      A.coefficients(c);
+      for (int half = 0; half < 2; ++half) {
+        double i2 = 0, a2 = 0;
+        for (int i = 0; i < 2 * nn; ++i) {
+          cd v = c[(size_t)half * 2 * nn + i];
+          i2 += v.imag() * v.imag();
+          a2 += std::norm(v);
+        }
+        if (std::sqrt(i2) / (std::sqrt(a2) + kFpEps) > kFpEps) der_complex = true;
+      }
+    }
+  }
+
+  // PEC -> high-conductivity model (solver.py:327-333), tensorial test (solver.py:336-339),
+  // complex test on the full tensors (solver.py:355, 399-401)
+  const cd pec_model(1.0, std::abs(kPecVal));
+  auto is_pec = [](cd v) { return v.real() < 0.9 * kPecVal || (v.real() == 0.9 * kPecVal && v.imag() <= 0); };
+  double mu_i2 = 0, mu_a2 = 0;
+  for (int ix = 0; ix < nx; ++ix)
+    for (int iy = 0; iy < ny; ++iy) {
+      const size_t c = (size_t)ix * ny + iy;
+      double d_e = bend ? de[norm_axis == 0 ? ix : iy] : 1.0;
+      for (int k = 0; k < 3; ++k) {
+        if (is_pec(s.f[k][c])) s.f[k][c] = pec_model;
+        im2 += s.f[k][c].imag() * s.f[k][c].imag();
+        all2 += std::norm(s.f[k][c]);
+      }
+      const double sc[3] = {1.0, 1.0, d_e};
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          if (a == b) continue;
+          cd v = eps[(size_t)(3 * a + b) * n + c] * (sc[a] * sc[b] / d_e);
+          if (is_pec(v)) v = pec_model;
+          double av = std::abs(v);
+          if (av > off_max) off_max = av;
+          im2 += v.imag() * v.imag();
+          all2 += std::norm(v);
+        }
+      for (int k = 3; k < 6; ++k) {
+        mu_i2 += s.f[k][c].imag() * s.f[k][c].imag();
+        mu_a2 += std::norm(s.f[k][c]);
+      }
+      if (std::abs(s.f[0][c]) < 1e7 && std::abs(s.f[1][c]) < 1e7)
+        s.max_k2 = std::max(s.max_k2, std::max(s.f[0][c].real(), s.f[1][c].real()) - s.target * s.target);
+    }
+  if (off_max > kTolTensorial) s.tensorial = true;
+  const bool eps_complex = std::sqrt(im2) / (std::sqrt(all2) + kFpEps) > kFpEps;
+  const bool mu_complex = std::sqrt(mu_i2) / (std::sqrt(mu_a2) + kFpEps) > kFpEps;
+  s.coef_complex = eps_complex || mu_complex;
+  s.is_complex = s.coef_complex || der_complex;
+  if (s.tensorial) {
+    s.is_complex = true;
+    s.eps_spec = eps_complex ? B200MS_SPEC_TENSORIAL_COMPLEX : B200MS_SPEC_TENSORIAL_REAL;
+    s.status = B200MS_ERR_UNSUPPORTED;
+    s.error = "tensorial permittivity (angled / off-diagonal eps, solver.py:594) is not built yet";
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multigrid hierarchy (geometry part, shared by every problem of a batch)
+// ------------------------------------------------------------------------------------------------
+struct Transfer1D {
+  // prolongation: fine i <- w0*coarse[i0] + w1*coarse[i1]
+  std::vector<int> p_i0, p_i1;
+  std::vector<double> p_w0, p_w1;
+  // restriction (normalised transpose): coarse I <- sum_k r_w[k] * fine[r_idx[k]], k in [r_ptr[I], r_ptr[I+1])
+  std::vector<int> r_ptr, r_idx;
+  std::vector<double> r_w;
+  void build_restriction(int nc) {
+    const int n = (int)p_i0.size();
+    std::vector<std::vector<std::pair<int, double>>> rows(nc);
+    for (int i = 0; i < n; ++i) {
+      if (p_w0[i] != 0.0) rows[p_i0[i]].push_back({i, p_w0[i]});
+      if (p_w1[i] != 0.0 && p_i1[i] != p_i0[i]) rows[p_i1[i]].push_back({i, p_w1[i]});
+      else if (p_w1[i] != 0.0) rows[p_i0[i]].back().second += p_w1[i];
+    }
+    r_ptr.assign(nc + 1, 0);
+    r_idx.clear();
+    r_w.clear();
+    for (int I = 0; I < nc; ++I) {
+      double tot = 0;
+      for (auto &e : rows[I]) tot += e.second;
+      for (auto &e : rows[I]) {
+        r_idx.push_back(e.first);
+        r_w.push_back(tot > 0 ? e.second / tot : 0.0);
+      }
+      r_ptr[I + 1] = (int)r_idx.size();
+    }
+  }
+};
+
+struct AxisTransfer {
+  std::vector<int> start;  // aggregate starts, size nc+1
+  Transfer1D node, edge;
+};
+
+// Greedy aggregation of neighbouring cells by |stretched length| (semi-coarsening that leaves cells
+// already longer than the target alone -- PML layers and coarse regions of graded meshes).
+inline std::vector<int> aggregate_axis(const std::vector<cd> &lf, double H, double slack = 1.25, int max_cells = 3) {
+  const int n = (int)lf.size();
+  std::vector<int> st;
+  int i = 0;
+  while (i < n) {
+    st.push_back(i);
+    double tot = std::abs(lf[i]);
+    int cnt = 1;
+    while (i + cnt < n && cnt < max_cells && tot + std::abs(lf[i + cnt]) <= slack * H) {
+      tot += std::abs(lf[i + cnt]);
+      ++cnt;
+      if (cnt >= 2 && tot >= 0.75 * H) break;
+    }
+    i += cnt;
+  }
+  st.push_back(n);
+  return st;
+}
+
+inline void build_axis_transfer(const std::vector<int> &a, const std::vector<double> &pos, AxisTransfer &t) {
+  t.start = a;
+  const int nc = (int)a.size() - 1, n = a.back();
+  Transfer1D &nd = t.node, &ed = t.edge;
+  nd.p_i0.assign(n, 0); nd.p_i1.assign(n, 0); nd.p_w0.assign(n, 0); nd.p_w1.assign(n, 0);
+  ed.p_i0.assign(n, 0); ed.p_i1.assign(n, 0); ed.p_w0.assign(n, 0); ed.p_w1.assign(n, 0);
+  std::vector<double> Xc(nc);
+  for (int I = 0; I < nc; ++I) Xc[I] = 0.5 * (pos[a[I]] + pos[a[I + 1]]);
+  for (int I = 0; I < nc; ++I) {
+    const double x0 = pos[a[I]], x1 = pos[a[I + 1]];
+    for (int i = a[I]; i < a[I + 1]; ++i) {
+      // node type: coarse node I sits on fine node a[I]; past the last coarse node -> zero wall
+      double tt = (pos[i] - x0) / (x1 - x0);
+      nd.p_i0[i] = I;
+      nd.p_i1[i] = std::min(I + 1, nc - 1);
+      nd.p_w0[i] = 1.0 - tt;
+      nd.p_w1[i] = (I + 1 < nc) ? tt : 0.0;
+      // edge type: linear between coarse cell centres, constant at the ends
+      double xc = 0.5 * (pos[i] + pos[i + 1]);
+      if (xc < Xc[I] && I > 0) {
+        double u = (xc - Xc[I - 1]) / (Xc[I] - Xc[I - 1]);
+        ed.p_i0[i] = I - 1; ed.p_i1[i] = I; ed.p_w0[i] = 1.0 - u; ed.p_w1[i] = u;
+      } else if (xc > Xc[I] && I + 1 < nc) {
+        double u = (xc - Xc[I]) / (Xc[I + 1] - Xc[I]);
+        ed.p_i0[i] = I; ed.p_i1[i] = I + 1; ed.p_w0[i] = 1.0 - u; ed.p_w1[i] = u;
+      } else {
+        ed.p_i0[i] = I; ed.p_i1[i] = I; ed.p_w0[i] = 1.0; ed.p_w1[i] = 0.0;
+      }
+    }
+  }
+  nd.build_restriction(nc);
+  ed.build_restriction(nc);
+}
+
+inline void coarsen_axis(const Axis &fine, const std::vector<int> &a, Axis &c) {
+  const int nc = (int)a.size() - 1;
+  c.n = nc;
+  c.pmc = fine.pmc;
+  c.lf.assign(nc, cd(0, 0));
+  c.lb.assign(nc, cd(0, 0));
+  c.pos.resize(nc + 1);
+  for (int I = 0; I < nc; ++I) {
+    for (int i = a[I]; i < a[I + 1]; ++i) c.lf[I] += fine.lf[i];
+    c.pos[I] = fine.pos[a[I]];
+  }
+  c.pos[nc] = fine.pos[a[nc]];
+  c.lb[0] = c.lf[0];
+  for (int I = 1; I < nc; ++I) c.lb[I] = 0.5 * (c.lf[I - 1] + c.lf[I]);
+}
+
+struct HierarchyPlan {
+  // level l has shape (nx[l], ny[l]); tr[l] maps level l+1 -> l
+  std::vector<int> nx, ny;
+  std::vector<AxisTransfer> trx, try_;
+};
+
+// Geometry of the hierarchy from the axes of one representative problem.  `kh_limit` > 0 stops
+// coarsening once k_max * H would exceed it (indefinite shifts: coarse grids must still resolve the
+// local wavelength); k_max is in the k0-scaled units of the lengths.
+inline void plan_hierarchy(const Axis fine_ax[2], int min_size, int max_levels, double kh_limit, double kmax,
+                           HierarchyPlan &plan, std::vector<std::vector<Axis>> *axes_out = nullptr) {
+  plan = HierarchyPlan();
+  plan.nx.push_back(fine_ax[0].n);
+  plan.ny.push_back(fine_ax[1].n);
+  Axis cur[2] = {fine_ax[0], fine_ax[1]};
+  if (axes_out) axes_out->push_back({cur[0], cur[1]});
+  double h0 = 1e300;
+  for (int a = 0; a < 2; ++a)
+    if (cur[a].n > 1)
+      for (auto &v : cur[a].lf) h0 = std::min(h0, std::abs(v));
+  double H = h0;
+  int guard = 0;
+  while ((int)plan.nx.size() < max_levels && std::max(cur[0].n, cur[1].n) > min_size && guard++ < 40) {
+    H *= 2;
+    if (kh_limit > 0 && kmax * H > kh_limit) break;
+    std::vector<int> agg[2];
+    for (int a = 0; a < 2; ++a) {
+      if (cur[a].n > 1)
+        agg[a] = aggregate_axis(cur[a].lf, H);
+      else
+        agg[a] = {0, 1};
+    }
+    const int ncx = (int)agg[0].size() - 1, ncy = (int)agg[1].size() - 1;
+    if (ncx == cur[0].n && ncy == cur[1].n) continue;  // nothing merged at this H, try a larger one
+    AxisTransfer tx, ty;
+    build_axis_transfer(agg[0], cur[0].pos, tx);
+    build_axis_transfer(agg[1], cur[1].pos, ty);
+    plan.trx.push_back(tx);
+    plan.try_.push_back(ty);
+    Axis nxt[2];
+    coarsen_axis(cur[0], agg[0], nxt[0]);
+    coarsen_axis(cur[1], agg[1], nxt[1]);
+    cur[0] = nxt[0];
+    cur[1] = nxt[1];
+    plan.nx.push_back(ncx);
+    plan.ny.push_back(ncy);
+    if (axes_out) axes_out->push_back({cur[0], cur[1]});
+  }
+}
+
+}  // namespace b200ms

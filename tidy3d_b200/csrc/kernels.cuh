@@ -1,0 +1,626 @@
+// Device kernels of the B200 mode solver (sm_100a).  All kernels are batched: blockIdx.z (or .y for
+// the 1-D kernels) is the problem index inside a batch of same-shaped eigenproblems.
+//
+// Vector layout: a "batched vector" is [B][2][nx][ny] (Ex then Ey, y fastest), scalar type T (double
+// or cplx).  Coefficient fields are [B or 1][nf][nx][ny] of type C (double or cplx).  The 1-D
+// difference coefficients are [B][4][n] of type T per axis (f0, f1, b0, bm).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace b200ms {
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) cplx {
+  double re, im;
+};
+#define HD __host__ __device__ __forceinline__
+HD cplx mk(double r, double i) { cplx c; c.re = r; c.im = i; return c; }
+HD cplx operator+(cplx a, cplx b) { return mk(a.re + b.re, a.im + b.im); }
+HD cplx operator-(cplx a, cplx b) { return mk(a.re - b.re, a.im - b.im); }
+HD cplx operator-(cplx a) { return mk(-a.re, -a.im); }
+HD cplx operator*(cplx a, cplx b) { return mk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+HD cplx operator*(double a, cplx b) { return mk(a * b.re, a * b.im); }
+HD cplx operator*(cplx a, double b) { return mk(a.re * b, a.im * b); }
+HD cplx &operator+=(cplx &a, cplx b) { a.re += b.re; a.im += b.im; return a; }
+HD cplx &operator-=(cplx &a, cplx b) { a.re -= b.re; a.im -= b.im; return a; }
+HD double cj(double a) { return a; }
+HD cplx cj(cplx a) { return mk(a.re, -a.im); }
+HD double recip(double a) { return 1.0 / a; }
+HD cplx recip(cplx a) { double d = 1.0 / (a.re * a.re + a.im * a.im); return mk(a.re * d, -a.im * d); }
+HD double abs2(double a) { return a * a; }
+HD double abs2(cplx a) { return a.re * a.re + a.im * a.im; }
+template <typename T> HD T zero_of();
+template <> HD double zero_of<double>() { return 0.0; }
+template <> HD cplx zero_of<cplx>() { return mk(0.0, 0.0); }
+template <typename T> HD T from_real(double r);
+template <> HD double from_real<double>(double r) { return r; }
+template <> HD cplx from_real<cplx>(double r) { return mk(r, 0.0); }
+// conversions between storage types (real <- complex drops the imaginary part)
+template <typename T> HD T cast_to(cplx v);
+template <> HD double cast_to<double>(cplx v) { return v.re; }
+template <> HD cplx cast_to<cplx>(cplx v) { return v; }
+HD cplx to_cplx(double v) { return mk(v, 0.0); }
+HD cplx to_cplx(cplx v) { return v; }
+
+template <typename T> __device__ __forceinline__ T ldg(const T *p) { return *p; }
+template <> __device__ __forceinline__ double ldg<double>(const double *p) { return __ldg(p); }
+template <> __device__ __forceinline__ cplx ldg<cplx>(const cplx *p) {
+  double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+  return mk(v.x, v.y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused curl-curl stencil
+// ------------------------------------------------------------------------------------------------
+enum { MODE_APPLY = 0, MODE_RESID = 1, MODE_JACOBI = 2 };
+
+template <typename T, typename C>
+struct StencilArgs {
+  int nx, ny;
+  const T *x;        // [B][2][N] input vector
+  const T *rhs;      // [B][2][N] (RESID / JACOBI)
+  T *y;              // [B][2][N] output
+  const C *fields;   // exx, eyy, iez, (mxx, myy, imz)   [field_bstride*b + k*N]
+  size_t field_bstride;
+  const T *cx;       // [B][4][nx]
+  const T *cy;       // [B][4][ny]
+  const T *sigma;    // [B]
+  double omega;      // Jacobi damping
+};
+
+template <typename T> struct Tile;
+template <> struct Tile<double> { static constexpr int TX = 8, TY = 64; };
+template <> struct Tile<cplx> { static constexpr int TX = 8, TY = 32; };
+
+// y = (A - sigma) x                       MODE_APPLY
+// y = rhs - (A - sigma) x                 MODE_RESID
+// y = x + omega * D^-1 (rhs - (A-sigma)x) MODE_JACOBI   (D = diag(A) - sigma, recomputed on the fly)
+//
+// A v for v = [Ex; Ey] in the radius-1 form:
+//   t = imz * (Dxf v2 - Dyf v1)                      (Hz sites)
+//   u = -iez * (Dxb (exx v1) + Dyb (eyy v2))         (Ez sites)
+//   p1 = Dxf u + myy * (Dyb t - exx v1),  p2 = Dyf u - mxx * (Dxb t + eyy v2)
+// which equals P.Q of tidy3d/plugins/mode/solver.py:479-490 (the Dxb Dyb - Dyb Dxb terms cancel).
+// One CTA computes a TX x TY tile: the halo of v, exx*v1, eyy*v2 is staged in shared memory, then
+// u and t on the (TX+1) x (TY+1) dual tiles, then the outputs.
+template <typename T, typename C, int MODE, bool HAS_MU>
+__global__ void __launch_bounds__(256) stencil_kernel(StencilArgs<T, C> a) {
+  constexpr int TX = Tile<T>::TX, TY = Tile<T>::TY;
+  constexpr int RY = 256 / TY;       // thread rows
+  constexpr int PER = TX / RY;       // output rows per thread
+  constexpr int HW = TY + 2, HH = TX + 2;
+  __shared__ T sV1[HH][HW], sV2[HH][HW], sA[HH][HW], sB[HH][HW];
+  __shared__ T sU[TX + 1][TY + 1], sT[TX + 1][TY + 1];
+  __shared__ C sIez[(MODE == MODE_JACOBI) ? TX + 1 : 1][(MODE == MODE_JACOBI) ? TY + 1 : 1];
+  __shared__ C sImz[(MODE == MODE_JACOBI && HAS_MU) ? TX + 1 : 1][(MODE == MODE_JACOBI && HAS_MU) ? TY + 1 : 1];
+  __shared__ T sCx[4][HH + 1], sCy[4][HW + 1];
+
+  const int nx = a.nx, ny = a.ny;
+  const size_t N = (size_t)nx * ny;
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * TX, j0 = blockIdx.x * TY;
+  const int tid = threadIdx.y * TY + threadIdx.x;
+  const T *x1 = a.x + (size_t)b * 2 * N, *x2 = x1 + N;
+  const C *fb = a.fields + a.field_bstride * b;
+  const C *exx = fb, *eyy = fb + N, *iez = fb + 2 * N;
+  const C *mxx = fb + 3 * N, *myy = fb + 4 * N, *imz = fb + 5 * N;
+  const T *cx = a.cx + (size_t)b * 4 * nx, *cy = a.cy + (size_t)b * 4 * ny;
+
+  // 1-D coefficients for rows i0-1 .. i0+TX+1 and columns j0-1 .. j0+TY+1 (zero outside the grid)
+  for (int k = tid; k < 4 * (HH + 1); k += 256) {
+    int w = k / (HH + 1), r = k % (HH + 1), gi = i0 - 1 + r;
+    sCx[w][r] = (gi >= 0 && gi < nx) ? ldg(cx + (size_t)w * nx + gi) : zero_of<T>();
+  }
+  for (int k = tid; k < 4 * (HW + 1); k += 256) {
+    int w = k / (HW + 1), c = k % (HW + 1), gj = j0 - 1 + c;
+    sCy[w][c] = (gj >= 0 && gj < ny) ? ldg(cy + (size_t)w * ny + gj) : zero_of<T>();
+  }
+  // halo of v and eps*v
+  for (int k = tid; k < HH * HW; k += 256) {
+    int r = k / HW, c = k % HW, gi = i0 - 1 + r, gj = j0 - 1 + c;
+    T v1 = zero_of<T>(), v2 = zero_of<T>(), pa = zero_of<T>(), pb = zero_of<T>();
+    if (gi >= 0 && gi < nx && gj >= 0 && gj < ny) {
+      size_t g = (size_t)gi * ny + gj;
+      v1 = ldg(x1 + g);
+      v2 = ldg(x2 + g);
+      pa = ldg(exx + g) * v1;
+      pb = ldg(eyy + g) * v2;
+    }
+    sV1[r][c] = v1; sV2[r][c] = v2; sA[r][c] = pa; sB[r][c] = pb;
+  }
+  __syncthreads();
+  // dual tiles: u at (i0+r, j0+c), t at (i0-1+r, j0-1+c), r in [0,TX], c in [0,TY]
+  for (int k = tid; k < (TX + 1) * (TY + 1); k += 256) {
+    int r = k / (TY + 1), c = k % (TY + 1);
+    {
+      int gi = i0 + r, gj = j0 + c;
+      T u = zero_of<T>();
+      C ie = C();
+      if (gi < nx && gj < ny) {
+        ie = ldg(iez + (size_t)gi * ny + gj);
+        T acc = sCx[2][r + 1] * sA[r + 1][c + 1] + sCx[3][r + 1] * sA[r][c + 1] +
+                sCy[2][c + 1] * sB[r + 1][c + 1] + sCy[3][c + 1] * sB[r + 1][c];
+        u = -(ie * acc);
+      }
+      sU[r][c] = u;
+      if (MODE == MODE_JACOBI) sIez[r][c] = ie;
+    }
+    {
+      int gi = i0 - 1 + r, gj = j0 - 1 + c;
+      T t = zero_of<T>();
+      C im = C();
+      if (gi >= 0 && gi < nx && gj >= 0 && gj < ny) {
+        T acc = sCx[0][r] * sV2[r][c] + sCx[1][r] * sV2[r + 1][c] - sCy[0][c] * sV1[r][c] - sCy[1][c] * sV1[r][c + 1];
+        if (HAS_MU) {
+          im = ldg(imz + (size_t)gi * ny + gj);
+          t = im * acc;
+        } else {
+          t = acc;
+        }
+      }
+      sT[r][c] = t;
+      if (MODE == MODE_JACOBI && HAS_MU) sImz[r][c] = im;
+    }
+  }
+  __syncthreads();
+  const T sg = ldg(a.sigma + b);
+  T *y1 = a.y + (size_t)b * 2 * N, *y2 = y1 + N;
+  const T *r1 = (MODE != MODE_APPLY) ? a.rhs + (size_t)b * 2 * N : nullptr;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int r = threadIdx.y + q * RY, c = threadIdx.x;
+    const int gi = i0 + r, gj = j0 + c;
+    if (gi >= nx || gj >= ny) continue;
+    const size_t g = (size_t)gi * ny + gj;
+    const T u00 = sU[r][c], u10 = sU[r + 1][c], u01 = sU[r][c + 1];
+    const T t00 = sT[r + 1][c + 1], t0m = sT[r + 1][c], tm0 = sT[r][c + 1];
+    const T pa = sA[r + 1][c + 1], pb = sB[r + 1][c + 1];
+    const T v1 = sV1[r + 1][c + 1], v2 = sV2[r + 1][c + 1];
+    const T xf0 = sCx[0][r + 1], xf1 = sCx[1][r + 1], xb0 = sCx[2][r + 1], xbm = sCx[3][r + 1];
+    const T yf0 = sCy[0][c + 1], yf1 = sCy[1][c + 1], yb0 = sCy[2][c + 1], ybm = sCy[3][c + 1];
+    T p1 = xf0 * u00 + xf1 * u10;
+    T p2 = yf0 * u00 + yf1 * u01;
+    T c1 = yb0 * t00 + ybm * t0m - pa;
+    T c2 = xb0 * t00 + xbm * tm0 + pb;
+    C mx = C(), my = C();
+    if (HAS_MU) {
+      mx = ldg(mxx + g);
+      my = ldg(myy + g);
+      p1 += my * c1;
+      p2 -= mx * c2;
+    } else {
+      p1 += c1;
+      p2 -= c2;
+    }
+    T o1 = p1 - sg * v1, o2 = p2 - sg * v2;
+    if (MODE == MODE_APPLY) {
+      y1[g] = o1;
+      y2[g] = o2;
+    } else if (MODE == MODE_RESID) {
+      y1[g] = ldg(r1 + g) - o1;
+      y2[g] = ldg(r1 + N + g) - o2;
+    } else {
+      const C ex = ldg(exx + g), ey = ldg(eyy + g);
+      const T xbm_n = sCx[3][r + 2], ybm_n = sCy[3][c + 2];  // xbm[i+1], ybm[j+1]
+      const T xf1_p = sCx[1][r], yf1_p = sCy[1][c];          // xf1[i-1], yf1[j-1]
+      T s1 = sIez[r][c] * (xf0 * xb0) + sIez[r + 1][c] * (xf1 * xbm_n);
+      T s2 = sIez[r][c] * (yf0 * yb0) + sIez[r][c + 1] * (yf1 * ybm_n);
+      T d1, d2;
+      if (HAS_MU) {
+        T m1 = sImz[r + 1][c + 1] * (yb0 * yf0) + sImz[r + 1][c] * (ybm * yf1_p);
+        T m2 = sImz[r + 1][c + 1] * (xb0 * xf0) + sImz[r][c + 1] * (xbm * xf1_p);
+        d1 = -(ex * s1) - my * m1 - (my * ex) * from_real<T>(1.0) - sg;
+        d2 = -(ey * s2) - mx * m2 - (mx * ey) * from_real<T>(1.0) - sg;
+      } else {
+        T m1 = yb0 * yf0 + ybm * yf1_p;
+        T m2 = xb0 * xf0 + xbm * xf1_p;
+        d1 = -(ex * s1) - m1 - ex * from_real<T>(1.0) - sg;
+        d2 = -(ey * s2) - m2 - ey * from_real<T>(1.0) - sg;
+      }
+      y1[g] = v1 + a.omega * (recip(d1) * (ldg(r1 + g) - o1));
+      y2[g] = v2 + a.omega * (recip(d2) * (ldg(r1 + N + g) - o2));
+    }
+  }
+}
+
+// y = omega * D^-1 rhs  (first Jacobi sweep from a zero guess; no halo needed)
+template <typename T, typename C, bool HAS_MU>
+__global__ void __launch_bounds__(256) jacobi0_kernel(StencilArgs<T, C> a) {
+  const int nx = a.nx, ny = a.ny;
+  const size_t N = (size_t)nx * ny;
+  const int b = blockIdx.z;
+  const int gj = blockIdx.x * 64 + threadIdx.x, gi = blockIdx.y * 4 + threadIdx.y;
+  if (gi >= nx || gj >= ny) return;
+  const size_t g = (size_t)gi * ny + gj;
+  const C *fb = a.fields + a.field_bstride * b;
+  const C *exx = fb, *eyy = fb + N, *iez = fb + 2 * N, *mxx = fb + 3 * N, *myy = fb + 4 * N, *imz = fb + 5 * N;
+  const T *cx = a.cx + (size_t)b * 4 * nx, *cy = a.cy + (size_t)b * 4 * ny;
+  const T z = zero_of<T>();
+  const T xf0 = ldg(cx + gi), xf1 = ldg(cx + nx + gi), xb0 = ldg(cx + 2 * nx + gi), xbm = ldg(cx + 3 * nx + gi);
+  const T yf0 = ldg(cy + gj), yf1 = ldg(cy + ny + gj), yb0 = ldg(cy + 2 * ny + gj), ybm = ldg(cy + 3 * ny + gj);
+  const T xbm_n = gi + 1 < nx ? ldg(cx + 3 * nx + gi + 1) : z, ybm_n = gj + 1 < ny ? ldg(cy + 3 * ny + gj + 1) : z;
+  const T xf1_p = gi > 0 ? ldg(cx + nx + gi - 1) : z, yf1_p = gj > 0 ? ldg(cy + ny + gj - 1) : z;
+  const C ie00 = ldg(iez + g);
+  const C ie10 = gi + 1 < nx ? ldg(iez + g + ny) : C();
+  const C ie01 = gj + 1 < ny ? ldg(iez + g + 1) : C();
+  const C ex = ldg(exx + g), ey = ldg(eyy + g);
+  const T sg = ldg(a.sigma + b);
+  T s1 = ie00 * (xf0 * xb0) + ie10 * (xf1 * xbm_n);
+  T s2 = ie00 * (yf0 * yb0) + ie01 * (yf1 * ybm_n);
+  T d1, d2;
+  if (HAS_MU) {
+    const C im00 = ldg(imz + g);
+    const C im0m = gj > 0 ? ldg(imz + g - 1) : C();
+    const C imm0 = gi > 0 ? ldg(imz + g - ny) : C();
+    const C mx = ldg(mxx + g), my = ldg(myy + g);
+    T m1 = im00 * (yb0 * yf0) + im0m * (ybm * yf1_p);
+    T m2 = im00 * (xb0 * xf0) + imm0 * (xbm * xf1_p);
+    d1 = -(ex * s1) - my * m1 - (my * ex) * from_real<T>(1.0) - sg;
+    d2 = -(ey * s2) - mx * m2 - (mx * ey) * from_real<T>(1.0) - sg;
+  } else {
+    T m1 = yb0 * yf0 + ybm * yf1_p;
+    T m2 = xb0 * xf0 + xbm * xf1_p;
+    d1 = -(ex * s1) - m1 - ex * from_real<T>(1.0) - sg;
+    d2 = -(ey * s2) - m2 - ey * from_real<T>(1.0) - sg;
+  }
+  const T *r1 = a.rhs + (size_t)b * 2 * N;
+  T *y1 = a.y + (size_t)b * 2 * N;
+  y1[g] = a.omega * (recip(d1) * ldg(r1 + g));
+  y1[N + g] = a.omega * (recip(d2) * ldg(r1 + N + g));
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid transfer (tensor product of 1-D lists, see host_setup.hpp)
+// ------------------------------------------------------------------------------------------------
+struct Transfer1DDev {
+  const int *p_i0, *p_i1;
+  const double *p_w0, *p_w1;
+  const int *r_ptr, *r_idx;
+  const double *r_w;
+};
+struct TransferArgs {
+  int nxf, nyf, nxc, nyc;
+  Transfer1DDev xn, xe, yn, ye;  // node / edge lists per axis
+  int mask_x, mask_y;            // PEC min walls: zero Ey[0,:] (mask_x) and Ex[:,0] (mask_y)
+};
+
+// coarse[b][comp] = R fine[b][comp]   (Ex: x edge / y node, Ey: x node / y edge)
+template <typename T>
+__global__ void __launch_bounds__(256) restrict_kernel(TransferArgs a, const T *fine, T *coarse) {
+  const int J = blockIdx.x * 64 + threadIdx.x, I = blockIdx.y * 4 + threadIdx.y;
+  const int comp = blockIdx.z & 1, b = blockIdx.z >> 1;
+  if (I >= a.nxc || J >= a.nyc) return;
+  const Transfer1DDev &tx = comp == 0 ? a.xe : a.xn;
+  const Transfer1DDev &ty = comp == 0 ? a.yn : a.ye;
+  const size_t Nf = (size_t)a.nxf * a.nyf, Nc = (size_t)a.nxc * a.nyc;
+  const T *f = fine + ((size_t)b * 2 + comp) * Nf;
+  T acc = zero_of<T>();
+  const int kx0 = tx.r_ptr[I], kx1 = tx.r_ptr[I + 1], ky0 = ty.r_ptr[J], ky1 = ty.r_ptr[J + 1];
+  for (int kx = kx0; kx < kx1; ++kx) {
+    const double wx = tx.r_w[kx];
+    const T *row = f + (size_t)tx.r_idx[kx] * a.nyf;
+    T racc = zero_of<T>();
+    for (int ky = ky0; ky < ky1; ++ky) racc += ty.r_w[ky] * ldg(row + ty.r_idx[ky]);
+    acc += wx * racc;
+  }
+  if ((comp == 0 && a.mask_y && J == 0 && a.nyc > 1) || (comp == 1 && a.mask_x && I == 0 && a.nxc > 1)) acc = zero_of<T>();
+  coarse[((size_t)b * 2 + comp) * Nc + (size_t)I * a.nyc + J] = acc;
+}
+
+// fine[b][comp] += P coarse[b][comp]
+template <typename T>
+__global__ void __launch_bounds__(256) prolong_add_kernel(TransferArgs a, const T *coarse, T *fine) {
+  const int j = blockIdx.x * 64 + threadIdx.x, i = blockIdx.y * 4 + threadIdx.y;
+  const int comp = blockIdx.z & 1, b = blockIdx.z >> 1;
+  if (i >= a.nxf || j >= a.nyf) return;
+  if ((comp == 0 && a.mask_y && j == 0 && a.nyf > 1) || (comp == 1 && a.mask_x && i == 0 && a.nxf > 1)) return;
+  const Transfer1DDev &tx = comp == 0 ? a.xe : a.xn;
+  const Transfer1DDev &ty = comp == 0 ? a.yn : a.ye;
+  const size_t Nf = (size_t)a.nxf * a.nyf, Nc = (size_t)a.nxc * a.nyc;
+  const T *c = coarse + ((size_t)b * 2 + comp) * Nc;
+  const int I0 = tx.p_i0[i], I1 = tx.p_i1[i], J0 = ty.p_i0[j], J1 = ty.p_i1[j];
+  const double wx0 = tx.p_w0[i], wx1 = tx.p_w1[i], wy0 = ty.p_w0[j], wy1 = ty.p_w1[j];
+  T v = wx0 * (wy0 * ldg(c + (size_t)I0 * a.nyc + J0) + wy1 * ldg(c + (size_t)I0 * a.nyc + J1)) +
+        wx1 * (wy0 * ldg(c + (size_t)I1 * a.nyc + J0) + wy1 * ldg(c + (size_t)I1 * a.nyc + J1));
+  T *f = fine + ((size_t)b * 2 + comp) * Nf + (size_t)i * a.nyf + j;
+  *f = *f + v;
+}
+
+// coefficient field restriction: out = R in (optionally on reciprocals: out = 1 / R (1 / in))
+template <typename C>
+__global__ void __launch_bounds__(256) restrict_field_kernel(int nxf, int nyf, int nxc, int nyc, Transfer1DDev tx,
+                                                             Transfer1DDev ty, const C *in, size_t in_bstride, C *out,
+                                                             size_t out_bstride, int reciprocal) {
+  const int J = blockIdx.x * 64 + threadIdx.x, I = blockIdx.y * 4 + threadIdx.y, b = blockIdx.z;
+  if (I >= nxc || J >= nyc) return;
+  const C *f = in + in_bstride * b;
+  C acc = C();
+  for (int kx = tx.r_ptr[I]; kx < tx.r_ptr[I + 1]; ++kx) {
+    const C *row = f + (size_t)tx.r_idx[kx] * nyf;
+    C racc = C();
+    for (int ky = ty.r_ptr[J]; ky < ty.r_ptr[J + 1]; ++ky) {
+      C v = ldg(row + ty.r_idx[ky]);
+      if (reciprocal) v = recip(v);
+      racc += ty.r_w[ky] * v;
+    }
+    acc += tx.r_w[kx] * racc;
+  }
+  if (reciprocal) acc = recip(acc);
+  out[out_bstride * b + (size_t)I * nyc + J] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched Krylov vector kernels.  Basis vector i of problem b: V + i*vstride + b*len
+// ------------------------------------------------------------------------------------------------
+constexpr int kDotGroup = 8;
+constexpr int kDotChunks = 64;  // partial sums per problem
+
+// partial[b][chunk][i] = sum_{e in chunk} conj(V_i[b][e]) * w[b][e],  i in [i0, i0+nv)
+template <typename T>
+__global__ void __launch_bounds__(256) multidot_partial_kernel(const T *V, size_t vstride, size_t len, const T *w,
+                                                               int nv, T *partial, int pstride) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const T *wb = w + (size_t)b * len;
+  __shared__ T red[8][kDotGroup];
+  const size_t per = (len + gridDim.x - 1) / gridDim.x;
+  const size_t e0 = (size_t)chunk * per, e1 = (e0 + per < len) ? e0 + per : len;
+  for (int g0 = 0; g0 < nv; g0 += kDotGroup) {
+    const int ng = (nv - g0 < kDotGroup) ? nv - g0 : kDotGroup;
+    T acc[kDotGroup];
+#pragma unroll
+    for (int k = 0; k < kDotGroup; ++k) acc[k] = zero_of<T>();
+    for (size_t e = e0 + threadIdx.x; e < e1; e += 256) {
+      const T we = ldg(wb + e);
+#pragma unroll
+      for (int k = 0; k < kDotGroup; ++k)
+        if (k < ng) acc[k] += cj(ldg(V + (size_t)(g0 + k) * vstride + (size_t)b * len + e)) * we;
+    }
+#pragma unroll
+    for (int k = 0; k < kDotGroup; ++k) {
+      T v = acc[k];
+      if constexpr (sizeof(T) == 8) {
+        double d = *reinterpret_cast<double *>(&v);
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+        *reinterpret_cast<double *>(&v) = d;
+      } else {
+        cplx cv = *reinterpret_cast<cplx *>(&v);
+        for (int o = 16; o > 0; o >>= 1) {
+          cv.re += __shfl_down_sync(0xffffffffu, cv.re, o);
+          cv.im += __shfl_down_sync(0xffffffffu, cv.im, o);
+        }
+        *reinterpret_cast<cplx *>(&v) = cv;
+      }
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ng) {
+      T s = zero_of<T>();
+      for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+      partial[((size_t)b * gridDim.x + chunk) * pstride + g0 + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// out[b][i] (+)= sum_chunk partial[b][chunk][i]
+template <typename T>
+__global__ void multidot_final_kernel(const T *partial, int nchunk, int pstride, int nv, T *out, int ostride,
+                                      int accumulate) {
+  const int b = blockIdx.x, i = threadIdx.x;
+  if (i >= nv) return;
+  T s = zero_of<T>();
+  for (int c = 0; c < nchunk; ++c) s += partial[((size_t)b * nchunk + c) * pstride + i];
+  if (accumulate) s += out[(size_t)b * ostride + i];
+  out[(size_t)b * ostride + i] = s;
+}
+
+// w[b] += sign * sum_i coef[b][i] * V_i[b]
+template <typename T>
+__global__ void __launch_bounds__(256) multiaxpy_kernel(const T *V, size_t vstride, size_t len, const T *coef,
+                                                        int cstride, int nv, double sign, T *w) {
+  const int b = blockIdx.y;
+  extern __shared__ unsigned char smem_raw[];
+  T *sc = reinterpret_cast<T *>(smem_raw);
+  for (int i = threadIdx.x; i < nv; i += 256) sc[i] = coef[(size_t)b * cstride + i];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < len; e += stride) {
+    T acc = zero_of<T>();
+    for (int i = 0; i < nv; ++i) acc += sc[i] * ldg(V + (size_t)i * vstride + (size_t)b * len + e);
+    T *p = w + (size_t)b * len + e;
+    *p = *p + sign * acc;
+  }
+}
+
+// out_k[b] = sum_i Q[b][i][k] * V_i[b],  k in [0, nk); Q row-major [nv][qld]
+template <typename T>
+__global__ void __launch_bounds__(256) lincomb_kernel(const T *V, size_t vstride, size_t len, const T *Q, int nv,
+                                                      int nk, int qld, T *out, size_t ostride) {
+  const int b = blockIdx.y;
+  extern __shared__ unsigned char smem_raw[];
+  T *sq = reinterpret_cast<T *>(smem_raw);
+  for (int i = threadIdx.x; i < nv * qld; i += 256) sq[i] = Q[(size_t)b * nv * qld + i];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < len; e += stride) {
+    for (int k0 = 0; k0 < nk; k0 += 8) {
+      T acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = zero_of<T>();
+      for (int i = 0; i < nv; ++i) {
+        const T v = ldg(V + (size_t)i * vstride + (size_t)b * len + e);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k0 + k < nk) acc[k] += sq[i * qld + k0 + k] * v;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k0 + k < nk) out[(size_t)(k0 + k) * ostride + (size_t)b * len + e] = acc[k];
+    }
+  }
+}
+
+// y[b] = alpha[b] * x[b]  with alpha = 1/sqrt(re(nrm2[b])) (guarded) when inv_sqrt, else alpha[b]
+template <typename T>
+__global__ void __launch_bounds__(256) scale_kernel(const T *x, T *y, size_t len, const T *alpha, int astride,
+                                                    int inv_sqrt) {
+  const int b = blockIdx.y;
+  T al = alpha[(size_t)b * astride];
+  if (inv_sqrt) {
+    double n2 = *reinterpret_cast<double *>(&al);
+    al = from_real<T>(n2 > 1e-280 ? rsqrt(n2) : 0.0);
+  }
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < len; e += stride)
+    y[(size_t)b * len + e] = al * ldg(x + (size_t)b * len + e);
+}
+
+// y = a*x + b*y (scalars shared by the batch)
+template <typename T>
+__global__ void __launch_bounds__(256) axpby_kernel(size_t total, double a, const T *x, double bcoef, T *y) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) {
+    T v = a * ldg(x + e);
+    if (bcoef != 0.0) v = v + bcoef * y[e];
+    y[e] = v;
+  }
+}
+
+// dst[b][i] += src[b][i], i < n (tiny per-problem vectors)
+template <typename T>
+__global__ void add_small_kernel(T *dst, int dstride, const T *src, int sstride, int n) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[(size_t)b * dstride + i] = dst[(size_t)b * dstride + i] + src[(size_t)b * sstride + i];
+}
+
+// Least-squares solve of the small GMRES Hessenberg systems, one thread per problem, in place.
+// H is [B][kc][ld] column-major by Arnoldi step: H[b][j][i] = h_{i,j} for i <= j, and H[b][j][j+1]
+// holds ||w_j||^2 (squared norm, as written by the dot kernel).  beta2[b] = ||r0||^2.
+// Output y[b][0..kc).
+template <typename T>
+__global__ void gmres_lsq_kernel(T *H, int kc, int ld, const T *beta2, int bstride, T *y, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  T *Hb = H + (size_t)b * kc * ld;
+  T *yb = y + (size_t)b * kc;
+  // g is kept in the unused tail of y? no: use the last column slot of each H column (index ld-1)
+  // g[i] lives at Hb[i*ld + ld-1] for i < kc, and g[kc] in a register.
+  T b2 = beta2[(size_t)b * bstride];
+  double beta = sqrt(fmax(0.0, *reinterpret_cast<double *>(&b2)));
+  T gnext = from_real<T>(beta);
+  for (int j = 0; j < kc; ++j) {
+    T *col = Hb + (size_t)j * ld;
+    // sub-diagonal entry: sqrt of the stored squared norm
+    T n2 = col[j + 1];
+    double sub = sqrt(fmax(0.0, *reinterpret_cast<double *>(&n2)));
+    // apply previous rotations (stored in columns' slots ld-3 (c) and ld-2 (s))
+    for (int i = 0; i < j; ++i) {
+      const T c = Hb[(size_t)i * ld + ld - 3], sn = Hb[(size_t)i * ld + ld - 2];
+      const T a0 = col[i], a1 = col[i + 1];
+      col[i] = cj(c) * a0 + cj(sn) * a1;
+      col[i + 1] = c * a1 - sn * a0;
+    }
+    const T a0 = col[j];
+    const double d = sqrt(abs2(a0) + sub * sub);
+    T c = from_real<T>(1.0), sn = zero_of<T>();
+    if (d > 0.0) {
+      c = (1.0 / d) * a0;
+      sn = from_real<T>(sub / d);
+    }
+    col[ld - 3] = c;
+    col[ld - 2] = sn;
+    col[j] = from_real<T>(d);
+    const T gj = gnext;
+    col[ld - 1] = cj(c) * gj;   // g[j]
+    gnext = -(sn * gj);          // g[j+1]
+  }
+  // back substitution R y = g
+  for (int i = kc - 1; i >= 0; --i) {
+    T acc = Hb[(size_t)i * ld + ld - 1];
+    for (int j = i + 1; j < kc; ++j) acc -= Hb[(size_t)j * ld + i] * yb[j];
+    const T rii = Hb[(size_t)i * ld + i];
+    yb[i] = abs2(rii) > 1e-280 ? recip(rii) * acc : zero_of<T>();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue: eigenvector -> six field components in the reference layout (solver.py:556-589,254-269)
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename C>
+struct EpilogueArgs {
+  int nx, ny, num_modes;
+  const T *vec;      // [M][B][2][N] eigenvectors (mode-major like a Krylov basis): vec + m*vstride + b*2N
+  size_t vstride;
+  const C *fields;   // exx, eyy, iez, (mxx, myy, imz)
+  size_t field_bstride;
+  const T *cx, *cy;  // [B][4][n]
+  const cplx *ncomplex;  // [B][M]  n_eff + i k_eff in solver (transformed) coordinates
+  const double *jz_e, *jz_h;  // [B][n_jz] or null: bend back-transform of the z components
+  int jz_axis, jz_len;
+  int direction;
+  double h_scale;    // 1 / ETA_0
+  cplx *out;         // [B][2][3][nx][ny][M]
+};
+
+// E = (Ex, Ey, u / (i n)),  H = (-i/eta0) * (q1/(i n), q2/(i n), t)
+// with q1 = Dxb t + eyy v2, q2 = Dyb t - exx v1 (Q v, solver.py:483-489,578-582); the Ez identity
+// iez (Dxb Hy - Dyb Hx) = u/(i n) follows from Dxb Dyb = Dyb Dxb.
+template <typename T, typename C, bool HAS_MU>
+__global__ void __launch_bounds__(256) epilogue_kernel(EpilogueArgs<T, C> a) {
+  const int nx = a.nx, ny = a.ny, M = a.num_modes;
+  const size_t N = (size_t)nx * ny;
+  const int j = blockIdx.x * 64 + threadIdx.x, i = blockIdx.y * 4 + threadIdx.y;
+  const int m = blockIdx.z % M, b = blockIdx.z / M;
+  if (i >= nx || j >= ny) return;
+  const T *v1 = a.vec + (size_t)m * a.vstride + (size_t)b * 2 * N, *v2 = v1 + N;
+  const C *fb = a.fields + a.field_bstride * b;
+  const C *exx = fb, *eyy = fb + N, *iez = fb + 2 * N, *imz = fb + 5 * N;
+  const T *cx = a.cx + (size_t)b * 4 * nx, *cy = a.cy + (size_t)b * 4 * ny;
+  const T z = zero_of<T>();
+  auto V1 = [&](int ii, int jj) { return (ii >= 0 && ii < nx && jj >= 0 && jj < ny) ? ldg(v1 + (size_t)ii * ny + jj) : z; };
+  auto V2 = [&](int ii, int jj) { return (ii >= 0 && ii < nx && jj >= 0 && jj < ny) ? ldg(v2 + (size_t)ii * ny + jj) : z; };
+  auto CX = [&](int w, int ii) { return (ii >= 0 && ii < nx) ? ldg(cx + (size_t)w * nx + ii) : z; };
+  auto CY = [&](int w, int jj) { return (jj >= 0 && jj < ny) ? ldg(cy + (size_t)w * ny + jj) : z; };
+  auto TT = [&](int ii, int jj) {
+    if (ii < 0 || jj < 0 || ii >= nx || jj >= ny) return z;
+    T acc = CX(0, ii) * V2(ii, jj) + CX(1, ii) * V2(ii + 1, jj) - CY(0, jj) * V1(ii, jj) - CY(1, jj) * V1(ii, jj + 1);
+    if (HAS_MU) acc = ldg(imz + (size_t)ii * ny + jj) * acc;
+    return acc;
+  };
+  const size_t g = (size_t)i * ny + j;
+  const T e1 = V1(i, j), e2 = V2(i, j);
+  const C ex = ldg(exx + g), ey = ldg(eyy + g);
+  const T t00 = TT(i, j), tm0 = TT(i - 1, j), t0m = TT(i, j - 1);
+  const T q1 = CX(2, i) * t00 + CX(3, i) * tm0 + ey * e2;
+  const T q2 = CY(2, j) * t00 + CY(3, j) * t0m - ex * e1;
+  T uacc = CX(2, i) * (ex * e1) + CY(2, j) * (ey * e2);
+  if (i > 0) uacc += CX(3, i) * (ldg(exx + g - ny) * V1(i - 1, j));
+  if (j > 0) uacc += CY(3, j) * (ldg(eyy + g - 1) * V2(i, j - 1));
+  const T u = -(ldg(iez + g) * uacc);
+  const cplx nc = a.ncomplex[(size_t)b * M + m];
+  const cplx inv_in = recip(mk(-nc.im, nc.re));  // 1 / (i n)
+  const cplx hs = mk(0.0, -a.h_scale);           // -i / eta0
+  cplx Ex = to_cplx(e1), Ey = to_cplx(e2), Ez = to_cplx(u) * inv_in;
+  cplx Hx = hs * (to_cplx(q1) * inv_in), Hy = hs * (to_cplx(q2) * inv_in), Hz = hs * to_cplx(t00);
+  if (a.direction < 0) {  // solver.py:370-373
+    Hx = -Hx; Hy = -Hy; Ez = -Ez;
+  }
+  if (a.jz_axis >= 0) {   // E = J^T E' with J = diag(1, 1, dwdz) (solver.py:254-259)
+    const int t = a.jz_axis == 0 ? i : j;
+    Ez = a.jz_e[(size_t)b * a.jz_len + t] * Ez;
+    Hz = a.jz_h[(size_t)b * a.jz_len + t] * Hz;
+  }
+  cplx *o = a.out + (size_t)b * 6 * N * M;
+  o[(0 * N + g) * M + m] = Ex;
+  o[(1 * N + g) * M + m] = Ey;
+  o[(2 * N + g) * M + m] = Ez;
+  o[(3 * N + g) * M + m] = Hx;
+  o[(4 * N + g) * M + m] = Hy;
+  o[(5 * N + g) * M + m] = Hz;
+}
+
+}  // namespace b200ms

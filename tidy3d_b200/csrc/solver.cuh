@@ -1,0 +1,925 @@
+// Batched device eigen-solver: multigrid-preconditioned FGMRES shift-invert inside a Krylov-Schur
+// (thick-restart Arnoldi) iteration.  Replaces scipy.sparse.linalg.eigs(mat, k, sigma, tol, v0)
+// (ARPACK + SuperLU) at tidy3d/plugins/mode/solver.py:744-746 for a batch of same-shaped problems.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dense.hpp"
+#include "host_setup.hpp"
+#include "kernels.cuh"
+
+namespace b200ms {
+
+#define CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                               std::to_string(__LINE__));                                             \
+  } while (0)
+
+// ---- simple device arena ---------------------------------------------------------------------------
+struct Arena {
+  unsigned char *base = nullptr;
+  size_t cap = 0, used = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) {
+      used = 0;
+      return;
+    }
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    CUDA_CHECK(cudaMalloc(&base, bytes));
+    cap = bytes;
+    used = 0;
+  }
+  template <typename U>
+  U *get(size_t count) {
+    size_t bytes = (count * sizeof(U) + 255) & ~size_t(255);
+    if (used + bytes > cap) throw std::runtime_error("device arena exhausted");
+    U *p = reinterpret_cast<U *>(base + used);
+    used += bytes;
+    return p;
+  }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = used = 0;
+  }
+};
+struct ArenaSizer {
+  size_t total = 0;
+  template <typename U>
+  void add(size_t count) { total += (count * sizeof(U) + 255) & ~size_t(255); }
+};
+
+struct SolveStats {
+  int op_applies = 0, inner_iters = 0, restarts = 0;
+  long stencil_applies = 0;
+};
+
+template <typename T> inline cd to_cd(T v);
+template <> inline cd to_cd<double>(double v) { return cd(v, 0.0); }
+template <> inline cd to_cd<cplx>(cplx v) { return cd(v.re, v.im); }
+template <typename T> inline T from_cd(cd v);
+template <> inline double from_cd<double>(cd v) { return v.real(); }
+template <> inline cplx from_cd<cplx>(cd v) { return mk(v.real(), v.imag()); }
+
+struct TransferDevStore {
+  Transfer1DDev d;
+};
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T, typename C>
+class BatchSolver {
+ public:
+  struct Level {
+    int nx = 0, ny = 0;
+    size_t N = 0;
+    C *fields = nullptr;
+    size_t fbstride = 0;
+    T *cx = nullptr, *cy = nullptr;
+    T *x = nullptr, *b = nullptr, *r = nullptr, *tmp = nullptr;
+    TransferArgs tr;  // to the next coarser level
+  };
+
+  BatchSolver(Arena &arena, cudaStream_t stream, const b200ms_options &opt) : arena_(arena), st_(stream), opt_(opt) {}
+
+  int B = 0, nx = 0, ny = 0, k = 0, m = 0, restart = 0, nf = 3;
+  size_t N = 0, len = 0, vstride = 0;
+  bool has_mu = false, shared_fields = false;
+  std::vector<Level> lv;
+  SolveStats stats;
+  std::vector<int> level_shapes;
+
+  // -- build ---------------------------------------------------------------------------------------
+  void build(const std::vector<const ProblemSetup *> &ps, bool share_fields) {
+    B = (int)ps.size();
+    const ProblemSetup &p0 = *ps[0];
+    nx = p0.nx;
+    ny = p0.ny;
+    N = (size_t)nx * ny;
+    len = 2 * N;
+    vstride = (size_t)B * len;
+    k = p0.num_modes;
+    has_mu = p0.has_mu;
+    nf = has_mu ? 6 : 3;
+    shared_fields = share_fields;
+    const int ncv = opt_.ncv > 0 ? opt_.ncv : std::max(2 * k + 1, 20);
+    m = std::min(ncv, (int)std::min<size_t>(len - 1, 1 << 20));
+    if (m < k + 2) m = std::min<int>(k + 2, (int)len);
+    restart = std::max(2, opt_.gmres_restart);
+    mask_x_ = (!p0.ax[0].pmc && nx > 1) ? 1 : 0;
+    mask_y_ = (!p0.ax[1].pmc && ny > 1) ? 1 : 0;
+
+    // hierarchy geometry from problem 0; indefinite shifts limit the coarsest spacing
+    double kh_limit = 0.0, kmax = 0.0;
+    double max_k2 = 0.0;
+    for (auto *p : ps) max_k2 = std::max(max_k2, p->max_k2);
+    if (max_k2 > 1e-6 && opt_.mg_ppw > 0) {
+      kmax = std::sqrt(max_k2);
+      kh_limit = 2.0 * M_PI / opt_.mg_ppw;
+    }
+    std::vector<std::vector<Axis>> axes0;
+    plan_hierarchy(p0.ax, opt_.mg_min_size, 12, kh_limit, kmax, plan_, &axes0);
+    const int L = (int)plan_.nx.size();
+    level_shapes.clear();
+    for (int l = 0; l < L; ++l) {
+      level_shapes.push_back(plan_.nx[l]);
+      level_shapes.push_back(plan_.ny[l]);
+    }
+
+    // ---- size the arena ----
+    ArenaSizer sz;
+    const size_t fB = shared_fields ? 1 : B;
+    for (int l = 0; l < L; ++l) {
+      size_t Nl = (size_t)plan_.nx[l] * plan_.ny[l];
+      sz.add<C>(fB * nf * Nl);
+      sz.add<T>((size_t)B * 4 * plan_.nx[l]);
+      sz.add<T>((size_t)B * 4 * plan_.ny[l]);
+      for (int q = 0; q < 4; ++q) sz.add<T>((size_t)B * 2 * Nl);
+      if (l + 1 < L) {
+        size_t ints = 0, dbls = 0;
+        transfer_sizes(plan_.trx[l], ints, dbls);
+        transfer_sizes(plan_.try_[l], ints, dbls);
+        sz.add<int>(ints + 64);
+        sz.add<double>(dbls + 64);
+      }
+    }
+    sz.add<T>((size_t)(m + 1) * vstride);        // outer basis
+    sz.add<T>((size_t)(restart + 1) * vstride);  // FGMRES V
+    sz.add<T>((size_t)restart * vstride);        // FGMRES Z
+    sz.add<T>(vstride * 2);                      // xsol, rhs scratch
+    sz.add<T>((size_t)k * vstride);              // Ritz vectors
+    sz.add<T>((size_t)B * kDotChunks * pstride());
+    sz.add<T>((size_t)B * hstride());
+    sz.add<T>((size_t)B * (m + 1) * (m + 1));
+    sz.add<T>((size_t)B * 4);
+    sz.add<cplx>((size_t)B * k);
+    sz.add<cplx>((size_t)B * 6 * N * k);
+    sz.add<double>((size_t)B * 2 * std::max(nx, ny) + 64);
+    coarse_krylov_ = kh_limit > 0.0;
+    kc_ = std::max(2, std::min(opt_.mg_coarse_iters, std::max(m, restart) - 1));
+    {
+      const size_t NL = (size_t)plan_.nx[L - 1] * plan_.ny[L - 1];
+      if (coarse_krylov_) {
+        sz.add<T>((size_t)(kc_ + 1) * B * 2 * NL);
+        sz.add<T>((size_t)kc_ * B * 2 * NL);
+        sz.add<T>((size_t)B * kc_ * (kc_ + 4));
+        sz.add<T>((size_t)B * (kc_ + 1));
+        sz.add<T>((size_t)B * kc_);
+        sz.add<T>((size_t)B + 8);
+        sz.add<T>(8);
+      }
+    }
+    arena_.reserve(sz.total + (1 << 20));
+
+    // ---- allocate + upload ----
+    lv.assign(L, Level());
+    std::vector<std::vector<Axis>> axes_b(B);  // per problem, per level axes (2 per level flattened)
+    for (int l = 0; l < L; ++l) {
+      Level &v = lv[l];
+      v.nx = plan_.nx[l];
+      v.ny = plan_.ny[l];
+      v.N = (size_t)v.nx * v.ny;
+      v.fbstride = shared_fields ? 0 : nf * v.N;
+      v.fields = arena_.get<C>(fB * nf * v.N);
+      v.cx = arena_.get<T>((size_t)B * 4 * v.nx);
+      v.cy = arena_.get<T>((size_t)B * 4 * v.ny);
+      v.x = arena_.get<T>((size_t)B * 2 * v.N);
+      v.b = arena_.get<T>((size_t)B * 2 * v.N);
+      v.r = arena_.get<T>((size_t)B * 2 * v.N);
+      v.tmp = arena_.get<T>((size_t)B * 2 * v.N);
+    }
+    // 1-D coefficients for every problem and level
+    for (int l = 0; l < L; ++l) {
+      std::vector<T> hx((size_t)B * 4 * lv[l].nx), hy((size_t)B * 4 * lv[l].ny);
+      for (int b = 0; b < B; ++b) {
+        if (l == 0) {
+          axes_b[b] = {ps[b]->ax[0], ps[b]->ax[1]};
+        } else {
+          Axis cxa, cya;
+          coarsen_axis(axes_b[b][0], plan_.trx[l - 1].start, cxa);
+          coarsen_axis(axes_b[b][1], plan_.try_[l - 1].start, cya);
+          axes_b[b] = {cxa, cya};
+        }
+        std::vector<cd> c;
+        axes_b[b][0].coefficients(c);
+        for (size_t i = 0; i < c.size(); ++i) hx[(size_t)b * 4 * lv[l].nx + i] = from_cd<T>(c[i]);
+        axes_b[b][1].coefficients(c);
+        for (size_t i = 0; i < c.size(); ++i) hy[(size_t)b * 4 * lv[l].ny + i] = from_cd<T>(c[i]);
+      }
+      CUDA_CHECK(cudaMemcpyAsync(lv[l].cx, hx.data(), hx.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaMemcpyAsync(lv[l].cy, hy.data(), hy.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    // fine-level coefficient fields: exx, eyy, 1/ezz, (mxx, myy, 1/mzz)
+    {
+      std::vector<C> hf(fB * nf * N);
+      for (size_t b = 0; b < fB; ++b) {
+        const ProblemSetup &p = *ps[b];
+        for (int q = 0; q < nf; ++q) {
+          const bool inv = (q == 2 || q == 5);
+          C *dst = hf.data() + (b * nf + q) * N;
+          const std::vector<cd> &src = p.f[q];
+          for (size_t i = 0; i < N; ++i) dst[i] = from_cd<C>(inv ? 1.0 / src[i] : src[i]);
+        }
+      }
+      CUDA_CHECK(cudaMemcpyAsync(lv[0].fields, hf.data(), hf.size() * sizeof(C), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    // transfer lists + coarse fields
+    for (int l = 0; l + 1 < L; ++l) {
+      TransferArgs &t = lv[l].tr;
+      t.nxf = lv[l].nx;
+      t.nyf = lv[l].ny;
+      t.nxc = lv[l + 1].nx;
+      t.nyc = lv[l + 1].ny;
+      t.mask_x = mask_x_;
+      t.mask_y = mask_y_;
+      upload_transfer(plan_.trx[l].node, t.xn);
+      upload_transfer(plan_.trx[l].edge, t.xe);
+      upload_transfer(plan_.try_[l].node, t.yn);
+      upload_transfer(plan_.try_[l].edge, t.ye);
+      // site types: exx (e,n)  eyy (n,e)  ezz (n,n)  mxx (n,e)  myy (e,n)  mzz (e,e)
+      const Transfer1DDev *fx[6] = {&t.xe, &t.xn, &t.xn, &t.xn, &t.xe, &t.xe};
+      const Transfer1DDev *fy[6] = {&t.yn, &t.ye, &t.yn, &t.ye, &t.yn, &t.ye};
+      dim3 blk(64, 4), grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, (unsigned)fB);
+      for (int q = 0; q < nf; ++q) {
+        const bool inv = (q == 2 || q == 5);
+        restrict_field_kernel<C><<<grd, blk, 0, st_>>>(t.nxf, t.nyf, t.nxc, t.nyc, *fx[q], *fy[q],
+                                                       lv[l].fields + (size_t)q * lv[l].N, shared_fields ? 0 : nf * lv[l].N,
+                                                       lv[l + 1].fields + (size_t)q * lv[l + 1].N,
+                                                       shared_fields ? 0 : nf * lv[l + 1].N, inv ? 1 : 0);
+      }
+      CUDA_CHECK(cudaGetLastError());
+    }
+    // Krylov storage
+    Vout_ = arena_.get<T>((size_t)(m + 1) * vstride);
+    Vg_ = arena_.get<T>((size_t)(restart + 1) * vstride);
+    Zg_ = arena_.get<T>((size_t)restart * vstride);
+    xsol_ = arena_.get<T>(vstride);
+    rhs_ = arena_.get<T>(vstride);
+    ritz_ = arena_.get<T>((size_t)k * vstride);
+    partial_ = arena_.get<T>((size_t)B * kDotChunks * pstride());
+    hbuf_ = arena_.get<T>((size_t)B * hstride());
+    qbuf_ = arena_.get<T>((size_t)B * (m + 1) * (m + 1));
+    sigma_ = arena_.get<T>((size_t)B * 4);
+    ncomplex_ = arena_.get<cplx>((size_t)B * k);
+    fields_out_ = arena_.get<cplx>((size_t)B * 6 * N * k);
+    jz_ = arena_.get<double>((size_t)B * 2 * std::max(nx, ny) + 64);
+    if (coarse_krylov_) {
+      const size_t NL = lv[L - 1].N;
+      cV_ = arena_.get<T>((size_t)(kc_ + 1) * B * 2 * NL);
+      cZ_ = arena_.get<T>((size_t)kc_ * B * 2 * NL);
+      cH_ = arena_.get<T>((size_t)B * kc_ * (kc_ + 4));
+      cH2_ = arena_.get<T>((size_t)B * (kc_ + 1));
+      cy_ = arena_.get<T>((size_t)B * kc_);
+      cbeta_ = arena_.get<T>((size_t)B + 8);
+      cone_ = arena_.get<T>(8);
+      T one = from_real<T>(1.0);
+      CUDA_CHECK(cudaMemcpyAsync(cone_, &one, sizeof(T), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    hhost_.resize((size_t)B * hstride());
+    sig_host_.resize(B);
+    for (int b = 0; b < B; ++b) sig_host_[b] = ps[b]->sigma;
+    set_sigma(sig_host_);
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+  }
+
+  void set_sigma(const std::vector<cd> &s) {
+    std::vector<T> h(B);
+    for (int b = 0; b < B; ++b) h[b] = from_cd<T>(s[b]);
+    CUDA_CHECK(cudaMemcpyAsync(sigma_, h.data(), B * sizeof(T), cudaMemcpyHostToDevice, st_));
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+  }
+
+  // -- operator ------------------------------------------------------------------------------------
+  void apply(int l, int mode, const T *x, const T *rhs, T *y) {
+    Level &v = lv[l];
+    StencilArgs<T, C> a;
+    a.nx = v.nx; a.ny = v.ny; a.x = x; a.rhs = rhs; a.y = y;
+    a.fields = v.fields; a.field_bstride = v.fbstride; a.cx = v.cx; a.cy = v.cy; a.sigma = sigma_;
+    a.omega = opt_.mg_omega;
+    constexpr int TX = Tile<T>::TX, TY = Tile<T>::TY;
+    dim3 blk(TY, 256 / TY), grd((v.ny + TY - 1) / TY, (v.nx + TX - 1) / TX, B);
+    if (has_mu) {
+      if (mode == MODE_APPLY) stencil_kernel<T, C, MODE_APPLY, true><<<grd, blk, 0, st_>>>(a);
+      else if (mode == MODE_RESID) stencil_kernel<T, C, MODE_RESID, true><<<grd, blk, 0, st_>>>(a);
+      else stencil_kernel<T, C, MODE_JACOBI, true><<<grd, blk, 0, st_>>>(a);
+    } else {
+      if (mode == MODE_APPLY) stencil_kernel<T, C, MODE_APPLY, false><<<grd, blk, 0, st_>>>(a);
+      else if (mode == MODE_RESID) stencil_kernel<T, C, MODE_RESID, false><<<grd, blk, 0, st_>>>(a);
+      else stencil_kernel<T, C, MODE_JACOBI, false><<<grd, blk, 0, st_>>>(a);
+    }
+    if (l == 0) stats.stencil_applies++;
+  }
+  void jacobi0(int l, const T *rhs, T *y) {
+    Level &v = lv[l];
+    StencilArgs<T, C> a;
+    a.nx = v.nx; a.ny = v.ny; a.x = nullptr; a.rhs = rhs; a.y = y;
+    a.fields = v.fields; a.field_bstride = v.fbstride; a.cx = v.cx; a.cy = v.cy; a.sigma = sigma_;
+    a.omega = opt_.mg_omega;
+    dim3 blk(64, 4), grd((v.ny + 63) / 64, (v.nx + 3) / 4, B);
+    if (has_mu) jacobi0_kernel<T, C, true><<<grd, blk, 0, st_>>>(a);
+    else jacobi0_kernel<T, C, false><<<grd, blk, 0, st_>>>(a);
+  }
+
+  // -- multigrid V-cycle: z = M^-1 rin on level l.  Result lands in `out` (or lv[l].x if null). ----
+  void vcycle(int l, const T *rin, T *out) {
+    Level &v = lv[l];
+    const int L = (int)lv.size();
+    const int nu = std::max(1, opt_.mg_nu);
+    T *cur = v.x, *oth = v.tmp;
+    auto sweep = [&](T *dst) {  // dst = jacobi(cur)
+      apply(l, MODE_JACOBI, cur, rin, dst);
+    };
+    if (l == L - 1 && coarse_krylov_) {
+      coarse_gmres(l, rin, out ? out : cur);
+      return;
+    }
+    if (l == L - 1) {
+      const int n_sw = std::max(2, opt_.mg_coarse_iters);
+      jacobi0(l, rin, cur);
+      for (int s = 1; s < n_sw; ++s) {
+        T *dst = (s == n_sw - 1 && out) ? out : oth;
+        sweep(dst);
+        if (dst != out) std::swap(cur, oth);
+      }
+      if (!out) { v.x = cur; v.tmp = oth; }
+      return;
+    }
+    jacobi0(l, rin, cur);
+    for (int s = 1; s < nu; ++s) {
+      sweep(oth);
+      std::swap(cur, oth);
+    }
+    apply(l, MODE_RESID, cur, rin, v.r);
+    {
+      const TransferArgs &t = v.tr;
+      dim3 blk(64, 4), grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, 2 * B);
+      restrict_kernel<T><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+    }
+    vcycle(l + 1, lv[l + 1].b, nullptr);
+    {
+      const TransferArgs &t = v.tr;
+      dim3 blk(64, 4), grd((t.nyf + 63) / 64, (t.nxf + 3) / 4, 2 * B);
+      prolong_add_kernel<T><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
+    }
+    for (int s = 0; s < nu; ++s) {
+      T *dst = (s == nu - 1 && out) ? out : oth;
+      sweep(dst);
+      if (dst != out) std::swap(cur, oth);
+    }
+    if (!out) { v.x = cur; v.tmp = oth; }
+  }
+
+  // -- coarsest-level Krylov solve (indefinite shifts): GMRES(kc), Jacobi right-preconditioned, CGS2, run entirely
+  //    on the device (no host synchronisation; the small least-squares problem is solved by one thread per problem)
+  void coarse_gmres(int l, const T *rin, T *xout) {
+    Level &v = lv[l];
+    const int kc = kc_;
+    const size_t ln = 2 * v.N, vs = (size_t)B * ln;
+    const int ld = kc + 4;
+    CUDA_CHECK(cudaMemsetAsync(cH_, 0, (size_t)B * kc * ld * sizeof(T), st_));
+    dots(rin, 1, rin, cbeta_, 1, 0, false, ln, vs);
+    scale_inv_norm(rin, cV_, cbeta_, 1, ln);
+    for (int j = 0; j < kc; ++j) {
+      T *vj = cV_ + (size_t)j * vs, *zj = cZ_ + (size_t)j * vs, *w = cV_ + (size_t)(j + 1) * vs;
+      jacobi0(l, vj, zj);
+      apply(l, MODE_APPLY, zj, nullptr, w);
+      T *col = cH_ + (size_t)j * ld;  // problem stride kc*ld
+      dots(cV_, j + 1, w, col, kc * ld, 0, false, ln, vs);
+      axpys(cV_, j + 1, col, kc * ld, -1.0, w, ln, vs);
+      dots(cV_, j + 1, w, cH2_, kc + 1, 0, false, ln, vs);
+      axpys(cV_, j + 1, cH2_, kc + 1, -1.0, w, ln, vs);
+      add_small_kernel<T><<<B, 64, 0, st_>>>(col, kc * ld, cH2_, kc + 1, j + 1);  // H[:, j] += second-pass coefficients
+      dots(w, 1, w, col, kc * ld, j + 1, false, ln, vs);
+      scale_inv_norm(w, w, col + j + 1, kc * ld, ln);
+    }
+    gmres_lsq_kernel<T><<<(B + 31) / 32, 32, 0, st_>>>(cH_, kc, ld, cbeta_, 1, cy_, B);
+    CUDA_CHECK(cudaMemsetAsync(xout, 0, vs * sizeof(T), st_));
+    axpys(cZ_, kc, cy_, kc, +1.0, xout, ln, vs);
+  }
+
+  // -- batched BLAS-1 helpers -----------------------------------------------------------------------
+  int pstride() const { return std::max(m, restart) + 2; }
+  int hstride() const { return 2 * (std::max(m, restart) + 2) + 2; }
+  int vec_blocks() const { return (int)std::min<size_t>((len + 255) / 256, 1024); }
+
+  // dst[b][off + i] (+)= <V_i, w>, i < nv   (vectors of length ln, basis stride vs)
+  void dots(const T *V, int nv, const T *w, T *dst, int dstride, int off, bool accumulate, size_t ln = 0, size_t vs = 0) {
+    if (!ln) { ln = len; vs = vstride; }
+    const int chunks = (int)std::max<size_t>(1, std::min<size_t>(kDotChunks, (ln + 2047) / 2048));
+    dim3 grd(chunks, B);
+    multidot_partial_kernel<T><<<grd, 256, 0, st_>>>(V, vs, ln, w, nv, partial_, pstride());
+    multidot_final_kernel<T><<<B, std::max(32, ((nv + 31) / 32) * 32), 0, st_>>>(partial_, chunks, pstride(), nv, dst + off,
+                                                                                dstride, accumulate ? 1 : 0);
+  }
+  void axpys(const T *V, int nv, const T *coef, int cstride, double sign, T *w, size_t ln = 0, size_t vs = 0) {
+    if (!ln) { ln = len; vs = vstride; }
+    dim3 grd((unsigned)std::min<size_t>((ln + 255) / 256, 1024), B);
+    multiaxpy_kernel<T><<<grd, 256, nv * sizeof(T), st_>>>(V, vs, ln, coef, cstride, nv, sign, w);
+  }
+  void scale_inv_norm(const T *x, T *y, const T *nrm2, int stride, size_t ln = 0) {
+    if (!ln) ln = len;
+    dim3 grd((unsigned)std::min<size_t>((ln + 255) / 256, 1024), B);
+    scale_kernel<T><<<grd, 256, 0, st_>>>(x, y, ln, nrm2, stride, 1);
+  }
+  void copy(const T *src, T *dst) { CUDA_CHECK(cudaMemcpyAsync(dst, src, vstride * sizeof(T), cudaMemcpyDeviceToDevice, st_)); }
+  void fetch_h(size_t count) {
+    CUDA_CHECK(cudaMemcpyAsync(hhost_.data(), hbuf_, count * sizeof(T), cudaMemcpyDeviceToHost, st_));
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+  }
+
+  // CGS2 of w against V_0..V_{nv-1}; leaves h (nv values) and ||w||^2 in hhost_: layout per problem
+  // [h1 (nvmax) | h2 (nvmax) | nrm2], then normalises w into `dst`.
+  void orthonormalise(const T *V, int nv, T *w, T *dst, std::vector<cd> &h, std::vector<double> &nrm) {
+    const int hs = hstride(), half = std::max(m, restart) + 2;
+    dots(V, nv, w, hbuf_, hs, 0, false);
+    axpys(V, nv, hbuf_, hs, -1.0, w);
+    dots(V, nv, w, hbuf_, hs, half, false);
+    axpys(V, nv, hbuf_ + half, hs, -1.0, w);
+    dots(w, 1, w, hbuf_, hs, 2 * half, false);
+    scale_inv_norm(w, dst, hbuf_ + 2 * half, hs);
+    fetch_h((size_t)B * hs);
+    h.assign((size_t)B * nv, cd(0, 0));
+    nrm.assign(B, 0.0);
+    for (int b = 0; b < B; ++b) {
+      for (int i = 0; i < nv; ++i) h[(size_t)b * nv + i] = to_cd(hhost_[(size_t)b * hs + i]) + to_cd(hhost_[(size_t)b * hs + half + i]);
+      nrm[b] = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hs + 2 * half]).real()));
+    }
+  }
+
+  // -- FGMRES: xsol_ = (A - sigma)^-1 rhs ------------------------------------------------------------
+  // returns max relative residual estimate; iters_out = iterations of the slowest problem
+  double fgmres(const T *rhs, T *xsol, int &iters_out, const std::vector<char> *skip = nullptr) {
+    const double tol = opt_.inner_tol;
+    std::vector<char> done(B, 0);
+    if (skip) done = *skip;
+    std::vector<double> bnorm(B, 0.0), res(B, 0.0);
+    std::vector<cd> h;
+    std::vector<double> nrm;
+    CUDA_CHECK(cudaMemsetAsync(xsol, 0, vstride * sizeof(T), st_));
+    int total_it = 0;
+    bool first = true;
+    while (true) {
+      // r -> Vg_[0] normalised
+      T *r0 = Vg_;
+      if (first) copy(rhs, rhs_); else apply(0, MODE_RESID, xsol, rhs, rhs_);
+      dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
+      scale_inv_norm(rhs_, r0, hbuf_, hstride());
+      fetch_h((size_t)B * hstride());
+      std::vector<double> beta(B);
+      bool all_done = true;
+      for (int b = 0; b < B; ++b) {
+        beta[b] = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hstride()]).real()));
+        if (first) bnorm[b] = beta[b];
+        res[b] = bnorm[b] > 0 ? beta[b] / bnorm[b] : 0.0;
+        if (!(beta[b] > 0) || res[b] <= tol) done[b] = 1;
+        if (!done[b]) all_done = false;
+      }
+      first = false;
+      if (all_done || total_it >= opt_.gmres_maxit) break;
+      // per-problem least-squares state
+      std::vector<CMat> R(B, CMat(restart + 1, restart));
+      std::vector<std::vector<cd>> g(B, std::vector<cd>(restart + 1, cd(0, 0))), cs(B), sn(B);
+      std::vector<int> kused(B, 0);
+      std::vector<char> cyc_done = done;
+      for (int b = 0; b < B; ++b) g[b][0] = beta[b];
+      int kk = 0;
+      for (; kk < restart && total_it < opt_.gmres_maxit; ++kk) {
+        T *vk = Vg_ + (size_t)kk * vstride, *zk = Zg_ + (size_t)kk * vstride, *w = Vg_ + (size_t)(kk + 1) * vstride;
+        vcycle(0, vk, zk);
+        apply(0, MODE_APPLY, zk, nullptr, w);
+        orthonormalise(Vg_, kk + 1, w, w, h, nrm);
+        ++total_it;
+        bool all = true;
+        for (int b = 0; b < B; ++b) {
+          if (cyc_done[b]) continue;
+          CMat &Rb = R[b];
+          for (int i = 0; i <= kk; ++i) Rb(i, kk) = h[(size_t)b * (kk + 1) + i];
+          Rb(kk + 1, kk) = nrm[b];
+          for (int i = 0; i < kk; ++i) {  // previous rotations
+            cd a0 = Rb(i, kk), a1 = Rb(i + 1, kk);
+            Rb(i, kk) = std::conj(cs[b][i]) * a0 + std::conj(sn[b][i]) * a1;
+            Rb(i + 1, kk) = -sn[b][i] * a0 + cs[b][i] * a1;
+          }
+          cd a0 = Rb(kk, kk), a1 = Rb(kk + 1, kk);
+          double d = std::sqrt(std::norm(a0) + std::norm(a1));
+          cd c = d > 0 ? a0 / d : cd(1, 0), s = d > 0 ? a1 / d : cd(0, 0);
+          cs[b].push_back(c);
+          sn[b].push_back(s);
+          Rb(kk, kk) = d;
+          Rb(kk + 1, kk) = 0.0;
+          g[b][kk + 1] = -s * g[b][kk];
+          g[b][kk] = std::conj(c) * g[b][kk];
+          kused[b] = kk + 1;
+          res[b] = std::abs(g[b][kk + 1]) / bnorm[b];
+          if (res[b] <= tol || !(nrm[b] > 0)) cyc_done[b] = 1;
+          if (!cyc_done[b]) all = false;
+        }
+        if (all) {
+          ++kk;
+          break;
+        }
+      }
+      // y = R^-1 g, x += Z y
+      const int kmax = kk;
+      std::vector<T> yh((size_t)B * restart, zero_of<T>());
+      for (int b = 0; b < B; ++b) {
+        if (done[b]) continue;
+        const int ku = kused[b];
+        std::vector<cd> y(ku);
+        for (int i = ku - 1; i >= 0; --i) {
+          cd acc = g[b][i];
+          for (int j = i + 1; j < ku; ++j) acc -= R[b](i, j) * y[j];
+          y[i] = (std::abs(R[b](i, i)) > 0) ? acc / R[b](i, i) : cd(0, 0);
+        }
+        for (int i = 0; i < ku; ++i) yh[(size_t)b * restart + i] = from_cd<T>(y[i]);
+      }
+      CUDA_CHECK(cudaMemcpyAsync(qbuf_, yh.data(), yh.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+      if (kmax > 0) axpys(Zg_, kmax, qbuf_, restart, +1.0, xsol);
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      bool all_conv = true;
+      for (int b = 0; b < B; ++b) {
+        if (cyc_done[b] && res[b] <= tol) done[b] = 1;
+        if (!done[b]) all_conv = false;
+      }
+      if (all_conv) break;  // the FGMRES residual estimate is the true residual up to rounding
+    }
+    iters_out = total_it;
+    stats.inner_iters += total_it;
+    double worst = 0.0;
+    for (int b = 0; b < B; ++b)
+      if (!skip || !(*skip)[b]) worst = std::max(worst, res[b]);
+    return worst;
+  }
+
+  // -- Krylov-Schur ---------------------------------------------------------------------------------
+  struct EigResult {
+    std::vector<cd> theta;      // [B][k] Ritz values of OP
+    std::vector<int> nconv;     // [B]
+    std::vector<double> resid;  // [B] max Ritz residual estimate relative to |theta|
+    bool ok = true;
+  };
+
+  void init_start_vector(uint64_t seed) {
+    // random start vector (the reference seeds numpy's PCG64 with 0, solver.py:846; converged eigenpairs do
+    // not depend on it) with the PEC wall rows zeroed (solver.py:849-853)
+    std::vector<T> hv(len);
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    for (size_t e = 0; e < len; ++e) {
+      cd v(U(rng), U(rng));
+      hv[e] = from_cd<T>(v);
+    }
+    for (int c = 0; c < 2; ++c)
+      for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j)
+          if ((nx > 1 && i == 0) || (ny > 1 && j == 0)) hv[c * N + (size_t)i * ny + j] = zero_of<T>();
+    for (int b = 0; b < B; ++b)
+      CUDA_CHECK(cudaMemcpyAsync(rhs_ + (size_t)b * len, hv.data(), len * sizeof(T), cudaMemcpyHostToDevice, st_));
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+    dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
+    scale_inv_norm(rhs_, Vout_, hbuf_, hstride());
+  }
+
+  EigResult krylov_schur(bool real_arith) {
+    EigResult out;
+    out.theta.assign((size_t)B * k, cd(0, 0));
+    out.nconv.assign(B, 0);
+    out.resid.assign(B, 0.0);
+    std::vector<CMat> Bm(B, CMat(m + 1, m));
+    std::vector<char> done(B, 0);
+    std::vector<CMat> Yfinal(B, CMat(m, k));
+    std::vector<cd> h;
+    std::vector<double> nrm;
+    int nkeep = 0;
+    const int keep_target = std::min(m - 1, k + std::max(1, (m - k) / 2));
+    for (int rst = 0; rst <= opt_.max_restarts; ++rst) {
+      for (int j = nkeep; j < m; ++j) {
+        T *vj = Vout_ + (size_t)j * vstride, *w = Vout_ + (size_t)(j + 1) * vstride;
+        int its = 0;
+        fgmres(vj, w, its, &done);
+        stats.op_applies++;
+        orthonormalise(Vout_, j + 1, w, w, h, nrm);
+        for (int b = 0; b < B; ++b) {
+          if (done[b]) continue;
+          for (int i = 0; i <= j; ++i) Bm[b](i, j) += h[(size_t)b * (j + 1) + i];
+          Bm[b](j + 1, j) = nrm[b];
+        }
+      }
+      stats.restarts = rst;
+      // Rayleigh-Ritz + restart matrices
+      std::vector<T> qh((size_t)B * m * m, zero_of<T>());
+      bool all_done = true;
+      for (int b = 0; b < B; ++b) {
+        if (done[b]) continue;
+        CMat Tm(m, m), Q;
+        for (int i = 0; i < m; ++i)
+          for (int j = 0; j < m; ++j) Tm(i, j) = Bm[b](i, j);
+        CMat Horig = Tm;
+        if (!schur(Tm, Q)) {
+          out.ok = false;
+          done[b] = 1;
+          continue;
+        }
+        // rank Ritz values by |theta| (ARPACK which='LM' on OP)
+        std::vector<int> idx(m);
+        for (int i = 0; i < m; ++i) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int c) { return std::abs(Tm(a, a)) > std::abs(Tm(c, c)); });
+        std::vector<int> sel = select_closed(Tm, idx, keep_target, real_arith);
+        // wanted k first (they are the first k of the ranking, inside sel)
+        schur_reorder(Tm, Q, sel);
+        const int keep = (int)sel.size();
+        if (keep != keep_target) {
+          out.ok = false;
+          done[b] = 1;
+          continue;
+        }
+        const cd hlast = Bm[b](m, m - 1);
+        std::vector<cd> brow(keep);
+        for (int i = 0; i < keep; ++i) brow[i] = hlast * Q(m - 1, i);
+        CMat S = tri_eigvecs(Tm, keep);
+        // the k wanted = k largest |theta| among the kept
+        std::vector<int> w(keep);
+        for (int i = 0; i < keep; ++i) w[i] = i;
+        std::stable_sort(w.begin(), w.end(), [&](int a, int c) { return std::abs(Tm(a, a)) > std::abs(Tm(c, c)); });
+        int nconv = 0;
+        double worst = 0.0;
+        for (int q = 0; q < k; ++q) {
+          const int i = w[q];
+          cd acc = 0.0;
+          for (int j = 0; j <= i; ++j) acc += brow[j] * S(j, i);
+          double rel = std::abs(acc) / std::max(std::abs(Tm(i, i)), 1e-300);
+          worst = std::max(worst, rel);
+          if (rel <= opt_.eig_tol) ++nconv;
+        }
+        out.nconv[b] = nconv;
+        out.resid[b] = worst;
+        if (nconv == k || rst == opt_.max_restarts) {
+          done[b] = 1;
+          for (int q = 0; q < k; ++q) {
+            const int i = w[q];
+            out.theta[(size_t)b * k + q] = Tm(i, i);
+            if (real_arith && std::abs(Tm(i, i).imag()) > 1e-7 * std::abs(Tm(i, i))) out.ok = false;  // complex pair in real arithmetic
+            for (int r = 0; r < m; ++r) {
+              cd acc = 0.0;
+              for (int j = 0; j <= i; ++j) acc += Q(r, j) * S(j, i);
+              Yfinal[b](r, q) = acc;
+            }
+          }
+          continue;
+        }
+        all_done = false;
+        // restart matrices
+        CMat Qk(m, keep);
+        if (real_arith) {
+          CMat Qc(m, keep);
+          for (int r = 0; r < m; ++r)
+            for (int i = 0; i < keep; ++i) Qc(r, i) = Q(r, i);
+          int rank = real_basis(Qc, Qk);
+          if (rank < keep) {
+            out.ok = false;
+            done[b] = 1;
+            continue;
+          }
+        } else {
+          for (int r = 0; r < m; ++r)
+            for (int i = 0; i < keep; ++i) Qk(r, i) = Q(r, i);
+        }
+        CMat Bn(m + 1, m);
+        if (real_arith) {
+          // B_new = Qk^T H Qk (full), b_new = h * Qk[m-1, :]
+          CMat HQ = matmul(Horig, Qk);
+          for (int i = 0; i < keep; ++i)
+            for (int j = 0; j < keep; ++j) {
+              cd acc = 0.0;
+              for (int r = 0; r < m; ++r) acc += std::conj(Qk(r, i)) * HQ(r, j);
+              Bn(i, j) = acc;
+            }
+        } else {
+          for (int i = 0; i < keep; ++i)
+            for (int j = i; j < keep; ++j) Bn(i, j) = Tm(i, j);
+        }
+        for (int j = 0; j < keep; ++j) Bn(keep, j) = hlast * Qk(m - 1, j);
+        Bm[b] = Bn;
+        for (int r = 0; r < m; ++r)
+          for (int i = 0; i < keep; ++i) qh[((size_t)b * m + r) * m + i] = from_cd<T>(Qk(r, i));
+      }
+      if (all_done) break;
+      // V[:, :keep] <- V Q ; V[keep] <- V[m]      (Zg_ is free between inner solves: scratch)
+      const int keep = keep_of(keep_target);
+      CUDA_CHECK(cudaMemcpyAsync(qbuf_, qh.data(), qh.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+      {
+        dim3 grd(vec_blocks(), B);
+        lincomb_kernel<T><<<grd, 256, (size_t)m * m * sizeof(T), st_>>>(Vout_, vstride, len, qbuf_, m, keep, m, Zg_, vstride);
+      }
+      CUDA_CHECK(cudaMemcpyAsync(Vout_, Zg_, (size_t)keep * vstride * sizeof(T), cudaMemcpyDeviceToDevice, st_));
+      CUDA_CHECK(cudaMemcpyAsync(Vout_ + (size_t)keep * vstride, Vout_ + (size_t)m * vstride, vstride * sizeof(T),
+                                 cudaMemcpyDeviceToDevice, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      nkeep = keep;
+    }
+    // Ritz vectors X = V Y (unit norm); real arithmetic: make Y real (phase fix) for real eigenvalues
+    std::vector<T> yh((size_t)B * m * k, zero_of<T>());
+    for (int b = 0; b < B; ++b)
+      for (int q = 0; q < k; ++q) {
+        cd ph(1, 0);
+        if (real_arith) {
+          int best = 0;
+          for (int r = 1; r < m; ++r)
+            if (std::abs(Yfinal[b](r, q)) > std::abs(Yfinal[b](best, q))) best = r;
+          cd v = Yfinal[b](best, q);
+          if (std::abs(v) > 0) ph = std::conj(v) / std::abs(v);
+        }
+        double nn = 0.0;
+        for (int r = 0; r < m; ++r) {
+          cd v = Yfinal[b](r, q) * ph;
+          if (real_arith) v = cd(v.real(), 0.0);
+          nn += std::norm(v);
+        }
+        nn = nn > 0 ? 1.0 / std::sqrt(nn) : 0.0;
+        for (int r = 0; r < m; ++r) {
+          cd v = Yfinal[b](r, q) * ph;
+          if (real_arith) v = cd(v.real(), 0.0);
+          yh[((size_t)b * m + r) * k + q] = from_cd<T>(v * nn);
+        }
+      }
+    CUDA_CHECK(cudaMemcpyAsync(qbuf_, yh.data(), yh.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+    {
+      dim3 grd(vec_blocks(), B);
+      lincomb_kernel<T><<<grd, 256, (size_t)m * k * sizeof(T), st_>>>(Vout_, vstride, len, qbuf_, m, k, k, ritz_, vstride);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+    return out;
+  }
+
+  // true eigen-residuals ||A x - lambda x|| / (|lambda| ||x||) for Ritz vector slot q, per problem
+  std::vector<double> eigen_residuals(int q, const std::vector<cd> &lambda) {
+    set_sigma(lambda);
+    T *x = ritz_ + (size_t)q * vstride;
+    apply(0, MODE_APPLY, x, nullptr, rhs_);
+    dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
+    dots(x, 1, x, hbuf_, hstride(), 1, false);
+    fetch_h((size_t)B * hstride());
+    std::vector<double> r(B);
+    for (int b = 0; b < B; ++b) {
+      double rn = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hstride()]).real()));
+      double xn = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hstride() + 1]).real()));
+      r[b] = rn / std::max(1e-300, xn * std::abs(lambda[b]));
+    }
+    set_sigma(sig_host_);
+    return r;
+  }
+
+  // reorder Ritz vector slots: ritz_[new q] = old slot order[b][q] is per problem -> done through lincomb
+  // with permutation matrices; here slots are shared by the batch so we permute per problem on the fly
+  // in the epilogue via `perm`.
+  void epilogue(const std::vector<cd> &ncomplex_sorted, const std::vector<int> &perm, const std::vector<const ProblemSetup *> &ps,
+                cplx *host_dst_per_problem[], bool want_fields) {
+    // permute Ritz vectors so that slot q holds mode q (descending n_eff) for every problem
+    std::vector<T> ph((size_t)B * k * k, zero_of<T>());
+    for (int b = 0; b < B; ++b)
+      for (int q = 0; q < k; ++q) ph[((size_t)b * k + perm[(size_t)b * k + q]) * k + q] = from_real<T>(1.0);
+    CUDA_CHECK(cudaMemcpyAsync(qbuf_, ph.data(), ph.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+    {
+      dim3 grd(vec_blocks(), B);
+      lincomb_kernel<T><<<grd, 256, (size_t)k * k * sizeof(T), st_>>>(ritz_, vstride, len, qbuf_, k, k, k, Zg_, vstride);
+    }
+    if (!want_fields) {
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      return;
+    }
+    std::vector<cplx> nh((size_t)B * k);
+    for (size_t i = 0; i < nh.size(); ++i) nh[i] = mk(ncomplex_sorted[i].real(), ncomplex_sorted[i].imag());
+    CUDA_CHECK(cudaMemcpyAsync(ncomplex_, nh.data(), nh.size() * sizeof(cplx), cudaMemcpyHostToDevice, st_));
+    const ProblemSetup &p0 = *ps[0];
+    int jz_len = 0;
+    if (p0.jz_axis >= 0) {
+      jz_len = (int)p0.jz_e.size();
+      std::vector<double> je((size_t)B * jz_len), jh((size_t)B * jz_len);
+      for (int b = 0; b < B; ++b)
+        for (int i = 0; i < jz_len; ++i) {
+          je[(size_t)b * jz_len + i] = ps[b]->jz_e[i];
+          jh[(size_t)b * jz_len + i] = ps[b]->jz_h[i];
+        }
+      CUDA_CHECK(cudaMemcpyAsync(jz_, je.data(), je.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaMemcpyAsync(jz_ + (size_t)B * jz_len, jh.data(), jh.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    EpilogueArgs<T, C> a;
+    a.nx = nx; a.ny = ny; a.num_modes = k; a.vec = Zg_; a.vstride = vstride;
+    a.fields = lv[0].fields; a.field_bstride = lv[0].fbstride; a.cx = lv[0].cx; a.cy = lv[0].cy;
+    a.ncomplex = ncomplex_; a.jz_e = jz_; a.jz_h = jz_ + (size_t)B * jz_len; a.jz_axis = p0.jz_axis; a.jz_len = jz_len;
+    a.direction = p0.direction; a.h_scale = 1.0 / eta0(); a.out = fields_out_;
+    dim3 blk(64, 4), grd((ny + 63) / 64, (nx + 3) / 4, B * k);
+    if (has_mu) epilogue_kernel<T, C, true><<<grd, blk, 0, st_>>>(a);
+    else epilogue_kernel<T, C, false><<<grd, blk, 0, st_>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    for (int b = 0; b < B; ++b)
+      if (host_dst_per_problem[b])
+        CUDA_CHECK(cudaMemcpyAsync(host_dst_per_problem[b], fields_out_ + (size_t)b * 6 * N * k, 6 * N * k * sizeof(cplx),
+                                   cudaMemcpyDeviceToHost, st_));
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+  }
+
+  T *scratch_vec(int i) { return i == 0 ? xsol_ : rhs_; }
+  T *basis0() { return Vout_; }
+  T *gmres_z() { return Zg_; }
+  T *ritz_ptr() { return ritz_; }
+
+ private:
+  static void transfer_sizes(const AxisTransfer &t, size_t &ints, size_t &dbls) {
+    for (const Transfer1D *q : {&t.node, &t.edge}) {
+      ints += q->p_i0.size() * 2 + q->r_ptr.size() + q->r_idx.size() + 256;
+      dbls += q->p_w0.size() * 2 + q->r_w.size() + 256;
+    }
+  }
+  template <typename U>
+  const U *up(const std::vector<U> &v) {
+    U *d = arena_.get<U>(std::max<size_t>(v.size(), 1));
+    if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice, st_));
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+    return d;
+  }
+  void upload_transfer(const Transfer1D &h, Transfer1DDev &d) {
+    d.p_i0 = up(h.p_i0); d.p_i1 = up(h.p_i1); d.p_w0 = up(h.p_w0); d.p_w1 = up(h.p_w1);
+    d.r_ptr = up(h.r_ptr); d.r_idx = up(h.r_idx); d.r_w = up(h.r_w);
+  }
+  int keep_of(int keep_target) const { return keep_target; }
+
+  // choose `count` Ritz values (indices into diag(T)) in ranking order such that, in real arithmetic,
+  // the set is closed under complex conjugation
+  static std::vector<int> select_closed(const CMat &Tm, const std::vector<int> &ranked, int count, bool real_arith) {
+    std::vector<int> sel;
+    if (!real_arith) {
+      sel.assign(ranked.begin(), ranked.begin() + count);
+      return sel;
+    }
+    const int mtot = (int)ranked.size();
+    std::vector<char> used(mtot, 0);
+    auto is_cplx = [&](int i) { return std::abs(Tm(i, i).imag()) > 1e-10 * std::max(1e-300, std::abs(Tm(i, i))); };
+    auto partner = [&](int i) {
+      int best = -1;
+      double bd = 1e300;
+      for (int j = 0; j < mtot; ++j) {
+        if (j == i || used[j]) continue;
+        double d = std::abs(Tm(j, j) - std::conj(Tm(i, i)));
+        if (d < bd) { bd = d; best = j; }
+      }
+      return best;
+    };
+    for (int r = 0; r < mtot && (int)sel.size() < count; ++r) {
+      int i = ranked[r];
+      if (used[i]) continue;
+      if (!is_cplx(i)) {
+        used[i] = 1;
+        sel.push_back(i);
+      } else if ((int)sel.size() + 2 <= count) {
+        used[i] = 1;
+        int p = partner(i);
+        sel.push_back(i);
+        if (p >= 0) { used[p] = 1; sel.push_back(p); }
+      }
+    }
+    // top up with the best remaining real Ritz values if pairs were skipped
+    for (int r = 0; r < mtot && (int)sel.size() < count; ++r) {
+      int i = ranked[r];
+      if (!used[i] && !is_cplx(i)) { used[i] = 1; sel.push_back(i); }
+    }
+    for (int r = 0; r < mtot && (int)sel.size() < count; ++r) {
+      int i = ranked[r];
+      if (!used[i]) { used[i] = 1; sel.push_back(i); }
+    }
+    return sel;
+  }
+
+  Arena &arena_;
+  cudaStream_t st_;
+  b200ms_options opt_;
+  HierarchyPlan plan_;
+  int mask_x_ = 0, mask_y_ = 0;
+  T *Vout_ = nullptr, *Vg_ = nullptr, *Zg_ = nullptr, *xsol_ = nullptr, *rhs_ = nullptr, *ritz_ = nullptr;
+  T *partial_ = nullptr, *hbuf_ = nullptr, *qbuf_ = nullptr, *sigma_ = nullptr;
+  cplx *ncomplex_ = nullptr, *fields_out_ = nullptr;
+  double *jz_ = nullptr;
+  bool coarse_krylov_ = false;
+  int kc_ = 16;
+  T *cV_ = nullptr, *cZ_ = nullptr, *cH_ = nullptr, *cH2_ = nullptr, *cy_ = nullptr, *cbeta_ = nullptr, *cone_ = nullptr;
+  std::vector<T> hhost_;
+  std::vector<cd> sig_host_;
+};
+
+}  // namespace b200ms

@@ -169,7 +169,12 @@ class Transfer:
         return out
 
     def restrict(self, f):
-        return np.stack((self.Rxe @ f[0] @ self.Ryn.T, self.Rxn @ f[1] @ self.Rye.T))
+        out = np.stack((self.Rxe @ f[0] @ self.Ryn.T, self.Rxn @ f[1] @ self.Rye.T))
+        if not self.pmc[1] and out.shape[2] > 1:
+            out[0][:, 0] = 0
+        if not self.pmc[0] and out.shape[1] > 1:
+            out[1][0, :] = 0
+        return out
 
     # coefficient fields by site type
     def avg(self, f, xt, yt):
@@ -213,13 +218,15 @@ def fine_level(st, sigma):
 # ------------------------------------------------------------------------------------------------
 class Multigrid:
     def __init__(self, lv0, min_size=12, max_levels=10, nu=2, omega=0.8, coarse_sweeps=40, ratio=1.5,
-                 smoother="jacobi", cheb_deg=3, lam_max=2.0, lam_frac=4.0, exact_coarse=False, coarse_gmres=0):
+                 smoother="jacobi", cheb_deg=3, lam_max=2.0, lam_frac=4.0, exact_coarse=False, coarse_gmres=0, kh_limit=0.0, kmax=0.0):
         self.exact_coarse = exact_coarse; self._lu = None; self.coarse_gmres = coarse_gmres
         self.levels, self.tr = [lv0], []
         h0 = min(np.abs(l[0]).min() for l, n in zip(lv0.lens, (lv0.nx, lv0.ny)) if n > 1)
         H = h0
         while len(self.levels) < max_levels and max(self.levels[-1].nx, self.levels[-1].ny) > min_size:
             H *= 2
+            if kh_limit and kmax * H > kh_limit:
+                break
             c, tr = coarsen(self.levels[-1], H)
             if c is None:
                 continue
