@@ -74,7 +74,7 @@ typedef struct {
   int outer_iters;       /* out: Krylov-Schur restarts */
   int op_applies;        /* out: shift-invert (OP^-1) applications */
   int inner_iters;       /* out: total preconditioned GMRES iterations */
-  int stencil_applies;   /* out: fine-grid operator applications (all kinds) */
+  int stencil_applies;   /* out: kernels launched for this batch (all kinds) */
   int is_complex;        /* out: 1 if the eigenproblem was solved in complex arithmetic (solver.py:389-411) */
   double solve_ms;       /* out: device time of the batch this problem was solved in */
   double max_residual;   /* out: max_i ||A v_i - lambda_i v_i|| / (|lambda_i| ||v_i||) */
@@ -95,6 +95,7 @@ typedef struct {
   double mg_omega;       /* Jacobi damping (default 0.8) */
   double mg_ppw;         /* indefinite problems: keep >= this many cells per local wavelength (default 4) */
   int verbose;
+  double mg_pml_phase;   /* multigrid operator: clamp |arg| of the PML stretch to this (default pi/4; <=0: off) */
 } b200ms_options;
 
 int b200ms_version(void);

@@ -1,0 +1,158 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the reference -- golden fixtures generated from the
+unmodified reference, the oracle restatement on seeded inputs, and size-independent properties at full size."""
+import numpy as np
+import pytest
+
+from oracle import restatement as R
+from tests.golden.cases import CASES
+from tests.helpers import N_TOL, OVERLAP_MIN, load_golden, mode_overlaps
+from tidy3d_b200 import compute_modes, compute_modes_batch
+from tidy3d_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["c1_64", "c1_64_minus", "c1_64_sym_pmc_pec", "lossy_48", "nonuniform_56", "slab1d_x1", "slab1d_y1",
+         "c3_96", "c4_96", "c4_96_axis0", "strip_128_m4", "c3_128", "c4_128"]  # fmt: skip
+LARGE = ["c2_256_f0", "headline_512_f0", "c3_512", "c4_512"]
+
+
+def _solve(name, **opts):
+    fac, kw, _ = CASES[name]
+    wl = fac()
+    out, info = compute_modes_batch(
+        [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], return_info=True
+    )
+    return wl, out[0], info[0]
+
+
+def _check_against_golden(name, fields, n, spec):
+    g = load_golden(name)
+    assert spec == str(g["spec"])
+    # tolerance stated in DESIGN.md section 6: |dn_eff|, |dk_eff| <= 1e-6 against the reference run at its own
+    # ARPACK tolerance, and <= 1e-8 against the reference re-run with TOL_EIGS = 1e-12
+    assert np.abs(n - g["n_ref"]).max() < N_TOL
+    assert np.abs(n - g["n_tight"]).max() < 1e-8
+    if "fields_tight" in g.files:
+        nt = g["n_tight"]
+        gaps = np.abs(nt[:, None] - nt[None, :]) + np.eye(nt.size)
+        ok = gaps.min(axis=1) > 1e-4
+        ov = mode_overlaps(fields, g["fields_tight"])
+        assert (ov[ok] > OVERLAP_MIN).all(), ov
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_golden_small(name):
+    wl, (fields, n, spec), info = _solve(name)
+    assert fields.shape == (2, 3, wl.eps_cross[0].shape[0], wl.eps_cross[0].shape[1], 1, wl.mode_spec.num_modes)
+    assert fields.dtype == np.complex128 and info["converged"] == wl.mode_spec.num_modes
+    _check_against_golden(name, fields, n, spec)
+
+
+@pytest.mark.parametrize("name", LARGE)
+def test_golden_full_size(name):
+    """BASELINE.json configs at their full grid sizes (n_complex pinned by the unmodified reference)."""
+    wl, (fields, n, spec), info = _solve(name)
+    _check_against_golden(name, fields, n, spec)
+    assert info["max_residual"] < 1e-6
+
+
+def test_against_oracle_seeded_random_sections():
+    """Random (seeded) smooth cross-sections: CUDA path vs the oracle restatement run side by side."""
+    rng = np.random.default_rng(1234)
+    for trial in range(3):
+        nx, ny = int(rng.integers(30, 60)), int(rng.integers(30, 60))
+        x = np.linspace(-1.2, 1.2, nx + 1)
+        y = np.linspace(-1.0, 1.0, ny + 1)
+        xm, ym = 0.5 * (x[:-1] + x[1:]), 0.5 * (y[:-1] + y[1:])
+        blob = np.exp(-((xm[:, None] / 0.35) ** 2) - ((ym[None, :] - 0.1) / 0.25) ** 2)
+        base = 2.1 + 8.0 * blob + 0.2 * rng.random((nx, ny))
+        eps = [np.zeros((nx, ny), complex) for _ in range(9)]
+        eps[0], eps[4], eps[8] = base + 0j, 1.05 * base + 0j, 0.95 * base + 0j
+        spec = W.ModeSpecLike(num_modes=3, num_pml=(0, 6) if trial == 1 else (0, 0), target_neff=None if trial < 2 else 2.2)
+        f, n, s = compute_modes(eps, [x, y], W.C_0 / 1.31, spec)
+        f0, n0, s0 = R.compute_modes(eps, [x, y], W.C_0 / 1.31, spec, tol=1e-12)
+        assert s == s0
+        assert np.abs(n - n0).max() < 1e-8
+        gaps = np.abs(n0[:, None] - n0[None, :]) + np.eye(n0.size)
+        ok = gaps.min(axis=1) > 1e-4
+        assert (mode_overlaps(f, f0)[ok] > OVERLAP_MIN).all()
+
+
+def test_frequency_batch_equals_single_solves():
+    """Batched sweep (one device call) == independent solves; also pins two sweep points to the oracle."""
+    wl = W.c2(nf=6, n=96)
+    probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=f, mode_spec=wl.mode_spec) for f in wl.freqs]
+    batch = compute_modes_batch(probs)
+    for i in (0, 5):
+        f1, n1, _ = compute_modes(wl.eps_cross, wl.coords, wl.freqs[i], wl.mode_spec)
+        assert np.abs(batch[i][1] - n1).max() < 1e-9
+        assert (mode_overlaps(batch[i][0], f1) > 1 - 1e-6).all()
+        _, n0, _ = R.compute_modes(wl.eps_cross, wl.coords, wl.freqs[i], wl.mode_spec, tol=1e-12)
+        assert np.abs(batch[i][1] - n0).max() < 1e-8
+    ns = np.array([b[1] for b in batch])
+    assert (np.diff(ns[:, 0].real) < 0).all()  # n_eff falls with wavelength along the sweep
+
+
+def test_mixed_batch_groups_and_ragged_inputs():
+    """One call with different grid sizes, arithmetic kinds and mode counts; and an empty batch."""
+    assert compute_modes_batch([]) == []
+    names = ["c1_64", "lossy_48", "slab1d_x1", "c1_64_sym_pmc_pec"]
+    probs, refs = [], []
+    for name in names:
+        fac, kw, _ = CASES[name]
+        wl = fac()
+        probs.append(dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw))
+        refs.append(load_golden(name)["n_tight"])
+    out = compute_modes_batch(probs)
+    for (f, n, s), nref in zip(out, refs):
+        assert np.abs(n - nref).max() < 1e-8
+
+
+def test_direction_and_precision_contract():
+    wl = W.c1()
+    fp, n_p, _ = compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, direction="+")
+    fm, n_m, _ = compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, direction="-")
+    assert np.abs(n_p - n_m).max() < 1e-10
+    sign = np.ones((2, 3, 1, 1, 1, 1))
+    sign[1, 0] = sign[1, 1] = sign[0, 2] = -1  # solver.py:370-373
+    for m in range(2):
+        ph = np.vdot(fp[0, 0, ..., m].ravel(), fm[0, 0, ..., m].ravel())
+        ph /= abs(ph)
+        assert np.abs(fm[..., m] - ph * (sign[..., 0] * fp[..., m])).max() < 1e-6 * np.abs(fp[..., m]).max()
+    wl.mode_spec.precision = "single"
+    fs, n_s, _ = compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec)
+    assert fs.dtype == np.complex64  # solver.py:265-267
+    assert np.abs(n_s - n_p).max() < 1e-5
+
+
+def test_unsupported_paths_fail_loudly():
+    wl = W.angled(32)
+    with pytest.raises(NotImplementedError):
+        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec)
+
+
+def test_full_size_properties_headline_batch():
+    """Size-independent checks at the headline size on a multi-frequency batch: true eigen-residuals, unit-norm
+    eigenvectors, H/E consistency of the recovered fields (Hz = (Dxf Ey - Dyf Ex) recomputed on the host)."""
+    wl = W.headline(nf=4)
+    probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=f, mode_spec=wl.mode_spec) for f in wl.freqs]
+    out, info = compute_modes_batch(probs, return_info=True)
+    g = load_golden("headline_512_f0")
+    assert np.abs(out[0][1] - g["n_tight"]).max() < 1e-8
+    for (f, n, _), inf, freq in zip(out, info, wl.freqs):
+        assert inf["converged"] == 4 and inf["max_residual"] < 1e-6
+        ex, ey, hz = f[0, 0, :, :, 0, :], f[0, 1, :, :, 0, :], f[1, 2, :, :, 0, :]
+        nrm = np.sqrt((np.abs(ex) ** 2 + np.abs(ey) ** 2).sum(axis=(0, 1)))
+        assert np.allclose(nrm, 1.0, atol=1e-9)
+        k0 = 2 * np.pi * freq / W.C_0
+        dl = wl.coords[0][1] - wl.coords[0][0]
+        dxf_ey = np.zeros_like(ey)
+        dxf_ey[:-1] = (ey[1:] - ey[:-1]) / dl
+        dxf_ey[-1] = -ey[-1] / dl
+        dxf_ey[0] = ey[1] / dl  # PEC row (derivatives.py:15-16)
+        dyf_ex = np.zeros_like(ex)
+        dyf_ex[:, :-1] = (ex[:, 1:] - ex[:, :-1]) / dl
+        dyf_ex[:, -1] = -ex[:, -1] / dl
+        dyf_ex[:, 0] = ex[:, 1] / dl
+        hz_ref = (dxf_ey - dyf_ex) / k0 * (-1j / R.ETA_0)
+        assert np.abs(hz - hz_ref).max() < 1e-9 * np.abs(hz_ref).max() + 1e-12

@@ -1,0 +1,122 @@
+"""CPU: the C-ABI library loads, exports every declared symbol, and its host-side logic (problem set-up, dense
+Schur, hierarchy planning, input validation) agrees with the oracle.  No compute kernels are launched."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+from oracle import restatement as R
+from tests.golden.cases import CASES
+
+
+def test_abi_exports_every_declared_symbol(built_lib):
+    import os
+
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "b200ms.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200ms_[a-z_]+)\s*\(", hdr)))
+    L = built_lib.lib()
+    assert set(declared) == set(built_lib.EXPORTS)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert L.b200ms_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        built_lib.Handle()
+    from tidy3d_b200 import compute_modes
+    from tidy3d_b200 import workloads as W
+
+    wl = W.c1()
+    with pytest.raises(RuntimeError):
+        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec)
+
+
+def test_dense_schur(built_lib):
+    L = built_lib.lib()
+    rng = np.random.default_rng(0)
+    for n, real in [(1, False), (2, True), (7, False), (20, True), (41, False)]:
+        A = rng.standard_normal((n, n)) + (0 if real else 1j) * rng.standard_normal((n, n))
+        A = np.ascontiguousarray(A.astype(complex))
+        T = np.zeros((n, n), complex)
+        Q = np.zeros((n, n), complex)
+        rc = L.b200ms_debug_schur(n, built_lib._ptr(A.view(float)), built_lib._ptr(T.view(float)), built_lib._ptr(Q.view(float)))
+        assert rc == 0
+        assert np.abs(Q @ T @ Q.conj().T - A).max() < 1e-12 * max(1, np.abs(A).max()) * n
+        assert np.abs(np.tril(T, -1)).max() == 0
+        assert np.abs(Q.conj().T @ Q - np.eye(n)).max() < 1e-13
+        ev, ev0 = np.diag(T), np.linalg.eigvals(A)
+        assert np.abs(ev[:, None] - ev0[None, :]).min(axis=1).max() < 1e-10
+        assert np.abs(ev[:, None] - ev0[None, :]).min(axis=0).max() < 1e-10
+
+
+def _setup(built_lib, wl, kw):
+    sym = kw.get("symmetry", (0, 0))
+    pk = built_lib.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, sym, kw.get("direction", "+"))
+    nx, ny = pk.nx, pk.ny
+    sigma = np.zeros(2)
+    flags = (C.c_int * 4)()
+    tgt, kn = C.c_double(), C.c_double()
+    cx, cy, f = np.zeros(4 * nx, complex), np.zeros(4 * ny, complex), np.zeros((6, nx * ny), complex)
+    rc = built_lib.lib().b200ms_debug_setup(
+        C.byref(pk.struct), built_lib._ptr(sigma), flags, C.byref(tgt), C.byref(kn),
+        built_lib._ptr(cx.view(float)), built_lib._ptr(cy.view(float)), built_lib._ptr(f.view(float)),
+    )  # fmt: skip
+    return rc, sigma, list(flags), tgt.value, kn.value, cx, cy, f, pk
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if "512" not in n and "256" not in n])
+def test_host_setup_matches_oracle(built_lib, name):
+    fac, kw, _ = CASES[name]
+    wl = fac()
+    rc, sigma, flags, tgt, kn, cx, cy, f, pk = _setup(built_lib, wl, kw)
+    st = R.setup(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, kw.get("symmetry", (0, 0)))
+    assert bool(flags[1]) == st["tensorial"]
+    assert rc == (3 if st["tensorial"] else 0)
+    dt = R.solver_dtype(st, "double")
+    assert bool(flags[0]) == np.issubdtype(dt, np.complexfloating)
+    assert abs(tgt - st["target"]) < 1e-14 and abs(kn - st["knorm"]) < 1e-14
+    assert abs(sigma[0] + st["target"] ** 2) < 1e-13
+    rel = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)  # noqa: E731
+    assert rel(cx, np.concatenate(st["coef"][0])) < 1e-13
+    assert rel(cy, np.concatenate(st["coef"][1])) < 1e-13
+    if not st["tensorial"]:
+        e, m = st["eps"], st["mu"]
+        assert rel(f, np.stack([e[0, 0], e[1, 1], e[2, 2], m[0, 0], m[1, 1], m[2, 2]])) < 1e-13
+
+
+def test_hierarchy_plan(built_lib):
+    from tidy3d_b200 import workloads as W
+
+    L = built_lib.lib()
+    shapes = (C.c_int * 40)()
+    wl = W.si_strip(512, 4)
+    pk = built_lib.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec)
+    n = L.b200ms_debug_hierarchy(C.byref(pk.struct), None, 20, shapes)
+    got = [(shapes[2 * i], shapes[2 * i + 1]) for i in range(n)]
+    assert got == [(512, 512), (256, 256), (128, 128), (64, 64), (32, 32), (16, 16), (8, 8)]
+    # PML layers are not merged while they are longer than the target spacing; indefinite shift limits depth
+    wl = W.c3(128)
+    pk = built_lib.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec)
+    n = L.b200ms_debug_hierarchy(C.byref(pk.struct), None, 20, shapes)
+    got = [(shapes[2 * i], shapes[2 * i + 1]) for i in range(n)]
+    assert got[0] == (128, 128) and got[1][0] > 64 and all(a[0] > b[0] for a, b in zip(got, got[1:]))
+
+
+def test_input_validation(built_lib):
+    from tidy3d_b200 import workloads as W
+
+    wl = W.c1()
+    with pytest.raises(ValueError, match="Mismatch between 'coords' and 'esp_cross' shapes."):
+        built_lib.PackedProblem(wl.eps_cross, [wl.coords[0][:-1], wl.coords[1]], wl.freqs[0], wl.mode_spec)
+    with pytest.raises(ValueError, match="Wrong input to mode solver"):
+        built_lib.PackedProblem(wl.eps_cross[:8], wl.coords, wl.freqs[0], wl.mode_spec)
+    from tidy3d_b200.solver import compute_modes
+
+    with pytest.raises(NotImplementedError):
+        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, mu_cross=wl.eps_cross)

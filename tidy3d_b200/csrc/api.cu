@@ -42,6 +42,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->mg_omega = 0.8;
   o->mg_ppw = 4.0;
   o->verbose = 0;
+  o->mg_pml_phase = 0.7853981633974483;
 }
 
 extern "C" int b200ms_create(int device, b200ms_handle **out) {
@@ -177,11 +178,11 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
     r.outer_iters = S.stats.restarts;
     r.op_applies = S.stats.op_applies;
     r.inner_iters = S.stats.inner_iters;
-    r.stencil_applies = (int)std::min<long>(S.stats.stencil_applies, 2147483647L);
+    r.stencil_applies = (int)std::min<long>(S.stats.launches, 2147483647L);
     r.is_complex = real_arith ? 0 : 1;
     r.solve_ms = ms;
     r.max_residual = maxres[b];
-    r.status = (eig.nconv[b] == k && eig.ok) ? B200MS_OK : B200MS_ERR_NOCONV;
+    r.status = (eig.nconv[b] == k && eig.ok && maxres[b] < 1e-6) ? B200MS_OK : B200MS_ERR_NOCONV;
     if (h->opt.verbose)
       fprintf(stderr, "[b200ms] prob %d: conv %d/%d restarts %d op %d inner %d stencil %ld res %.2e ms %.1f\n", ids[b],
               eig.nconv[b], k, S.stats.restarts, S.stats.op_applies, S.stats.inner_iters, S.stats.stencil_applies,
@@ -282,13 +283,13 @@ static void bench_group(b200ms_handle *h, const ProblemSetup &s, int nbatch, int
     CUDA_CHECK(cudaMalloc(&h->flush_buf, h->flush_bytes));
   }
   const int md = mode == 1 ? MODE_JACOBI : MODE_APPLY;
-  for (int w = 0; w < 3; ++w) S.apply(0, md, dx, drhs, dy);
+  for (int w = 0; w < 3; ++w) S.apply(0, md, dx, drhs, dy, true);
   double total = 0.0;
   if (flush_l2) {
     for (int r = 0; r < nrep; ++r) {
       CUDA_CHECK(cudaMemsetAsync(h->flush_buf, r & 0xff, h->flush_bytes, h->stream));
       CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-      S.apply(0, md, dx, drhs, dy);
+      S.apply(0, md, dx, drhs, dy, true);
       CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
       CUDA_CHECK(cudaEventSynchronize(h->ev1));
       float ms = 0.f;
@@ -297,7 +298,7 @@ static void bench_group(b200ms_handle *h, const ProblemSetup &s, int nbatch, int
     }
   } else {
     CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-    for (int r = 0; r < nrep; ++r) S.apply(0, md, dx, drhs, dy);
+    for (int r = 0; r < nrep; ++r) S.apply(0, md, dx, drhs, dy, true);
     CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
     CUDA_CHECK(cudaEventSynchronize(h->ev1));
     float ms = 0.f;
@@ -442,7 +443,7 @@ int debug_run(b200ms_handle *h, const ProblemSetup &s, int what, int level, int 
   CUDA_CHECK(cudaMemcpy(d1, b.data(), n2 * sizeof(T), cudaMemcpyHostToDevice));
   if (what == 0) {
     if (mode == 3) S.jacobi0(level, d1, d2);
-    else S.apply(level, mode, d0, d1, d2);
+    else S.apply(level, mode, d0, d1, d2, true);
   } else if (what == 1) {
     S.vcycle(0, d0, d2);
   } else {

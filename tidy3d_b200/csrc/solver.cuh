@@ -64,7 +64,7 @@ struct ArenaSizer {
 
 struct SolveStats {
   int op_applies = 0, inner_iters = 0, restarts = 0;
-  long stencil_applies = 0;
+  long stencil_applies = 0, launches = 0;
 };
 
 template <typename T> inline cd to_cd(T v);
@@ -87,7 +87,8 @@ class BatchSolver {
     size_t N = 0;
     C *fields = nullptr;
     size_t fbstride = 0;
-    T *cx = nullptr, *cy = nullptr;
+    T *cx = nullptr, *cy = nullptr;          // multigrid (phase-limited PML) coefficients
+    T *cx_true = nullptr, *cy_true = nullptr;  // level 0 only: the reference operator
     T *x = nullptr, *b = nullptr, *r = nullptr, *tmp = nullptr;
     TransferArgs tr;  // to the next coarser level
   };
@@ -144,8 +145,8 @@ class BatchSolver {
     for (int l = 0; l < L; ++l) {
       size_t Nl = (size_t)plan_.nx[l] * plan_.ny[l];
       sz.add<C>(fB * nf * Nl);
-      sz.add<T>((size_t)B * 4 * plan_.nx[l]);
-      sz.add<T>((size_t)B * 4 * plan_.ny[l]);
+      sz.add<T>((size_t)B * 4 * plan_.nx[l] * (l == 0 ? 2 : 1));
+      sz.add<T>((size_t)B * 4 * plan_.ny[l] * (l == 0 ? 2 : 1));
       for (int q = 0; q < 4; ++q) sz.add<T>((size_t)B * 2 * Nl);
       if (l + 1 < L) {
         size_t ints = 0, dbls = 0;
@@ -195,6 +196,10 @@ class BatchSolver {
       v.fields = arena_.get<C>(fB * nf * v.N);
       v.cx = arena_.get<T>((size_t)B * 4 * v.nx);
       v.cy = arena_.get<T>((size_t)B * 4 * v.ny);
+      if (l == 0) {
+        v.cx_true = arena_.get<T>((size_t)B * 4 * v.nx);
+        v.cy_true = arena_.get<T>((size_t)B * 4 * v.ny);
+      }
       v.x = arena_.get<T>((size_t)B * 2 * v.N);
       v.b = arena_.get<T>((size_t)B * 2 * v.N);
       v.r = arena_.get<T>((size_t)B * 2 * v.N);
@@ -203,9 +208,29 @@ class BatchSolver {
     // 1-D coefficients for every problem and level
     for (int l = 0; l < L; ++l) {
       std::vector<T> hx((size_t)B * 4 * lv[l].nx), hy((size_t)B * 4 * lv[l].ny);
+      std::vector<T> hxt, hyt;
+      if (l == 0) {
+        hxt.resize(hx.size());
+        hyt.resize(hy.size());
+      }
       for (int b = 0; b < B; ++b) {
         if (l == 0) {
           axes_b[b] = {ps[b]->ax[0], ps[b]->ax[1]};
+          // reference operator coefficients
+          std::vector<cd> ct;
+          ps[b]->ax[0].coefficients(ct);
+          for (size_t i = 0; i < ct.size(); ++i) hxt[(size_t)b * 4 * lv[0].nx + i] = from_cd<T>(ct[i]);
+          ps[b]->ax[1].coefficients(ct);
+          for (size_t i = 0; i < ct.size(); ++i) hyt[(size_t)b * 4 * lv[0].ny + i] = from_cd<T>(ct[i]);
+          // multigrid operator: same |stretch|, phase clamped so that Re(1/s^2) >= 0 (point smoothers are unstable on
+          // the strongly rotated PML operator; the outer FGMRES on the true operator absorbs the difference)
+          if (opt_.mg_pml_phase > 0)
+            for (int a = 0; a < 2; ++a)
+              for (std::vector<cd> *vec : {&axes_b[b][a].lf, &axes_b[b][a].lb})
+                for (cd &z : *vec) {
+                  double ph = std::arg(z);
+                  if (std::abs(ph) > opt_.mg_pml_phase) z = std::polar(std::abs(z), ph > 0 ? opt_.mg_pml_phase : -opt_.mg_pml_phase);
+                }
         } else {
           Axis cxa, cya;
           coarsen_axis(axes_b[b][0], plan_.trx[l - 1].start, cxa);
@@ -220,6 +245,10 @@ class BatchSolver {
       }
       CUDA_CHECK(cudaMemcpyAsync(lv[l].cx, hx.data(), hx.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
       CUDA_CHECK(cudaMemcpyAsync(lv[l].cy, hy.data(), hy.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+      if (l == 0) {
+        CUDA_CHECK(cudaMemcpyAsync(lv[0].cx_true, hxt.data(), hxt.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(lv[0].cy_true, hyt.data(), hyt.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+      }
       CUDA_CHECK(cudaStreamSynchronize(st_));
     }
     // fine-level coefficient fields: exx, eyy, 1/ezz, (mxx, myy, 1/mzz)
@@ -305,11 +334,14 @@ class BatchSolver {
   }
 
   // -- operator ------------------------------------------------------------------------------------
-  void apply(int l, int mode, const T *x, const T *rhs, T *y) {
+  void apply(int l, int mode, const T *x, const T *rhs, T *y, bool true_op = false) {
     Level &v = lv[l];
     StencilArgs<T, C> a;
     a.nx = v.nx; a.ny = v.ny; a.x = x; a.rhs = rhs; a.y = y;
-    a.fields = v.fields; a.field_bstride = v.fbstride; a.cx = v.cx; a.cy = v.cy; a.sigma = sigma_;
+    a.fields = v.fields; a.field_bstride = v.fbstride; a.sigma = sigma_;
+    a.cx = (true_op && l == 0) ? v.cx_true : v.cx;
+    a.cy = (true_op && l == 0) ? v.cy_true : v.cy;
+    stats.launches++;
     a.omega = opt_.mg_omega;
     constexpr int TX = Tile<T>::TX, TY = Tile<T>::TY;
     dim3 blk(TY, 256 / TY), grd((v.ny + TY - 1) / TY, (v.nx + TX - 1) / TX, B);
@@ -330,6 +362,7 @@ class BatchSolver {
     a.nx = v.nx; a.ny = v.ny; a.x = nullptr; a.rhs = rhs; a.y = y;
     a.fields = v.fields; a.field_bstride = v.fbstride; a.cx = v.cx; a.cy = v.cy; a.sigma = sigma_;
     a.omega = opt_.mg_omega;
+    stats.launches++;
     dim3 blk(64, 4), grd((v.ny + 63) / 64, (v.nx + 3) / 4, B);
     if (has_mu) jacobi0_kernel<T, C, true><<<grd, blk, 0, st_>>>(a);
     else jacobi0_kernel<T, C, false><<<grd, blk, 0, st_>>>(a);
@@ -369,6 +402,7 @@ class BatchSolver {
       const TransferArgs &t = v.tr;
       dim3 blk(64, 4), grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, 2 * B);
       restrict_kernel<T><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+      stats.launches += 2;
     }
     vcycle(l + 1, lv[l + 1].b, nullptr);
     {
@@ -421,6 +455,7 @@ class BatchSolver {
   void dots(const T *V, int nv, const T *w, T *dst, int dstride, int off, bool accumulate, size_t ln = 0, size_t vs = 0) {
     if (!ln) { ln = len; vs = vstride; }
     const int chunks = (int)std::max<size_t>(1, std::min<size_t>(kDotChunks, (ln + 2047) / 2048));
+    stats.launches += 2;
     dim3 grd(chunks, B);
     multidot_partial_kernel<T><<<grd, 256, 0, st_>>>(V, vs, ln, w, nv, partial_, pstride());
     multidot_final_kernel<T><<<B, std::max(32, ((nv + 31) / 32) * 32), 0, st_>>>(partial_, chunks, pstride(), nv, dst + off,
@@ -428,11 +463,13 @@ class BatchSolver {
   }
   void axpys(const T *V, int nv, const T *coef, int cstride, double sign, T *w, size_t ln = 0, size_t vs = 0) {
     if (!ln) { ln = len; vs = vstride; }
+    stats.launches++;
     dim3 grd((unsigned)std::min<size_t>((ln + 255) / 256, 1024), B);
     multiaxpy_kernel<T><<<grd, 256, nv * sizeof(T), st_>>>(V, vs, ln, coef, cstride, nv, sign, w);
   }
   void scale_inv_norm(const T *x, T *y, const T *nrm2, int stride, size_t ln = 0) {
     if (!ln) ln = len;
+    stats.launches++;
     dim3 grd((unsigned)std::min<size_t>((ln + 255) / 256, 1024), B);
     scale_kernel<T><<<grd, 256, 0, st_>>>(x, y, ln, nrm2, stride, 1);
   }
@@ -476,7 +513,7 @@ class BatchSolver {
     while (true) {
       // r -> Vg_[0] normalised
       T *r0 = Vg_;
-      if (first) copy(rhs, rhs_); else apply(0, MODE_RESID, xsol, rhs, rhs_);
+      if (first) copy(rhs, rhs_); else apply(0, MODE_RESID, xsol, rhs, rhs_, true);
       dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
       scale_inv_norm(rhs_, r0, hbuf_, hstride());
       fetch_h((size_t)B * hstride());
@@ -501,7 +538,7 @@ class BatchSolver {
       for (; kk < restart && total_it < opt_.gmres_maxit; ++kk) {
         T *vk = Vg_ + (size_t)kk * vstride, *zk = Zg_ + (size_t)kk * vstride, *w = Vg_ + (size_t)(kk + 1) * vstride;
         vcycle(0, vk, zk);
-        apply(0, MODE_APPLY, zk, nullptr, w);
+        apply(0, MODE_APPLY, zk, nullptr, w, true);
         orthonormalise(Vg_, kk + 1, w, w, h, nrm);
         ++total_it;
         bool all = true;
@@ -770,7 +807,7 @@ class BatchSolver {
   std::vector<double> eigen_residuals(int q, const std::vector<cd> &lambda) {
     set_sigma(lambda);
     T *x = ritz_ + (size_t)q * vstride;
-    apply(0, MODE_APPLY, x, nullptr, rhs_);
+    apply(0, MODE_APPLY, x, nullptr, rhs_, true);
     dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
     dots(x, 1, x, hbuf_, hstride(), 1, false);
     fetch_h((size_t)B * hstride());
@@ -821,7 +858,7 @@ class BatchSolver {
     }
     EpilogueArgs<T, C> a;
     a.nx = nx; a.ny = ny; a.num_modes = k; a.vec = Zg_; a.vstride = vstride;
-    a.fields = lv[0].fields; a.field_bstride = lv[0].fbstride; a.cx = lv[0].cx; a.cy = lv[0].cy;
+    a.fields = lv[0].fields; a.field_bstride = lv[0].fbstride; a.cx = lv[0].cx_true; a.cy = lv[0].cy_true;
     a.ncomplex = ncomplex_; a.jz_e = jz_; a.jz_h = jz_ + (size_t)B * jz_len; a.jz_axis = p0.jz_axis; a.jz_len = jz_len;
     a.direction = p0.direction; a.h_scale = 1.0 / eta0(); a.out = fields_out_;
     dim3 blk(64, 4), grd((ny + 63) / 64, (nx + 3) / 4, B * k);
