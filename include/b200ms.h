@@ -96,6 +96,10 @@ typedef struct {
   double mg_ppw;         /* indefinite problems: keep >= this many cells per local wavelength (default 4) */
   int verbose;
   double mg_pml_phase;   /* multigrid operator: clamp |arg| of the PML stretch to this (default pi/4; <=0: off) */
+  double inner_relax;    /* inexact shift-invert: inner tol = clamp(inner_relax * inner_tol / ritz_residual); 0 = off (default 1.0) */
+  double inner_relax_cap; /* loosest inner tolerance allowed (default 1e-4) */
+  int gmres_cgs2;        /* 1 (default): CGS2 in the inner FGMRES; 0: second pass only on cancellation (measured: 3x more iterations) */
+  int stencil_variant;   /* 0: marching kernel (default), 1: shared-memory tiled kernel (reference implementation) */
 } b200ms_options;
 
 int b200ms_version(void);

@@ -53,7 +53,7 @@ def test_golden_full_size(name):
     """BASELINE.json configs at their full grid sizes (n_complex pinned by the unmodified reference)."""
     wl, (fields, n, spec), info = _solve(name)
     _check_against_golden(name, fields, n, spec)
-    assert info["max_residual"] < 1e-6
+    assert info["max_residual"] < 1e-5
 
 
 def test_against_oracle_seeded_random_sections():
@@ -140,7 +140,7 @@ def test_full_size_properties_headline_batch():
     g = load_golden("headline_512_f0")
     assert np.abs(out[0][1] - g["n_tight"]).max() < 1e-8
     for (f, n, _), inf, freq in zip(out, info, wl.freqs):
-        assert inf["converged"] == 4 and inf["max_residual"] < 1e-6
+        assert inf["converged"] == 4 and inf["max_residual"] < 1e-5
         ex, ey, hz = f[0, 0, :, :, 0, :], f[0, 1, :, :, 0, :], f[1, 2, :, :, 0, :]
         nrm = np.sqrt((np.abs(ex) ** 2 + np.abs(ey) ** 2).sum(axis=(0, 1)))
         assert np.allclose(nrm, 1.0, atol=1e-9)

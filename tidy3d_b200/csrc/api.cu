@@ -43,6 +43,10 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->mg_ppw = 4.0;
   o->verbose = 0;
   o->mg_pml_phase = 0.7853981633974483;
+  o->stencil_variant = 0;
+  o->gmres_cgs2 = 1;
+  o->inner_relax = 1.0;
+  o->inner_relax_cap = 1e-4;
 }
 
 extern "C" int b200ms_create(int device, b200ms_handle **out) {
@@ -182,7 +186,9 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
     r.is_complex = real_arith ? 0 : 1;
     r.solve_ms = ms;
     r.max_residual = maxres[b];
-    r.status = (eig.nconv[b] == k && eig.ok && maxres[b] < 1e-6) ? B200MS_OK : B200MS_ERR_NOCONV;
+    // converged == Ritz residuals of OP below eig_tol (ARPACK's criterion).  The residual with respect to A itself is
+    // reported for information: it is amplified by ||A - sigma|| ~ 1/(k0 dl)^2 and only screened for garbage here.
+    r.status = (eig.nconv[b] == k && eig.ok && maxres[b] < 1e-3 && S.stats.inner_failures == 0) ? B200MS_OK : B200MS_ERR_NOCONV;
     if (h->opt.verbose)
       fprintf(stderr, "[b200ms] prob %d: conv %d/%d restarts %d op %d inner %d stencil %ld res %.2e ms %.1f\n", ids[b],
               eig.nconv[b], k, S.stats.restarts, S.stats.op_applies, S.stats.inner_iters, S.stats.stencil_applies,

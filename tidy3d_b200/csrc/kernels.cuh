@@ -227,6 +227,172 @@ __global__ void __launch_bounds__(256) stencil_kernel(StencilArgs<T, C> a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Marching variant of the fused stencil (the production kernel on grids with nx >= 32).
+// One thread per grid column (y index), 128 columns per CTA of which the inner 126 produce output; the
+// CTA marches over TXR rows.  Own-column neighbours (i-1, i+1) live in registers; the four values each
+// cell needs from its y-neighbours (eyy*v2 and v1 for u/t, then u and t themselves) are exchanged
+// through double-buffered shared-memory rows, one __syncthreads per row.  Per cell: 5 (+3 with mu)
+// coalesced global loads, 4 shared stores + 4 shared loads, ~35 fp64 FMAs, 2 global stores.
+// Software pipeline per iteration k (row index):
+//   step 0  row k+2 arrives from the prefetch registers; loads of row k+3 are issued
+//   step 1  publish b[k+2], v1[k+2]
+//   step 2  u[k+1], t[k+1] from registers + neighbours published in iteration k-1; publish them
+//   step 3  outputs of row k from u[k], u[k+1], t[k], t[k-1] (registers) and u[k][j+1], t[k][j-1]
+// ------------------------------------------------------------------------------------------------
+constexpr int kMarchCols = 128, kMarchOut = 126;
+
+template <typename T, typename C, int MODE, bool HAS_MU, int TXR>
+__global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T, C> a) {
+  constexpr bool JAC = (MODE == MODE_JACOBI);
+  __shared__ T sB[2][kMarchCols + 2], sV[2][kMarchCols + 2], sU[2][kMarchCols + 2], sTt[2][kMarchCols + 2];
+  __shared__ C sIe[JAC ? 2 : 1][JAC ? kMarchCols + 2 : 1];
+  __shared__ C sIm[(JAC && HAS_MU) ? 2 : 1][(JAC && HAS_MU) ? kMarchCols + 2 : 1];
+  __shared__ T sX[4][TXR + 6];
+
+  const int nx = a.nx, ny = a.ny;
+  const size_t N = (size_t)nx * ny;
+  const int b = blockIdx.z;
+  const int c = threadIdx.x;
+  const int gj = (int)blockIdx.x * kMarchOut - 1 + c;
+  const int i0 = blockIdx.y * TXR;
+  const int iend = (i0 + TXR < nx) ? i0 + TXR : nx;
+  const bool colv = (gj >= 0 && gj < ny);
+  const bool outc = colv && c >= 1 && c <= kMarchOut;
+  const T *x1 = a.x + (size_t)b * 2 * N, *x2 = x1 + N;
+  const C *fb = a.fields + a.field_bstride * b;
+  const C *exx = fb, *eyy = fb + N, *iez = fb + 2 * N;
+  const C *mxx = fb + 3 * N, *myy = fb + 4 * N, *imz = fb + 5 * N;
+  const T *cx = a.cx + (size_t)b * 4 * nx, *cy = a.cy + (size_t)b * 4 * ny;
+  const T zT = zero_of<T>();
+
+  for (int q = c; q < 4 * (TXR + 6); q += kMarchCols) {
+    const int w = q / (TXR + 6), r = q % (TXR + 6), gi = i0 - 3 + r;
+    sX[w][r] = (gi >= 0 && gi < nx) ? ldg(cx + (size_t)w * nx + gi) : zT;
+  }
+  for (int s = 0; s < 2; ++s) {
+    sB[s][c + 1] = zT; sV[s][c + 1] = zT; sU[s][c + 1] = zT; sTt[s][c + 1] = zT;
+    if (JAC) sIe[s][c + 1] = C();
+    if (JAC && HAS_MU) sIm[s][c + 1] = C();
+  }
+  if (c < 2) {
+    for (int s = 0; s < 2; ++s) {
+      const int e = c == 0 ? 0 : kMarchCols + 1;
+      sB[s][e] = zT; sV[s][e] = zT; sU[s][e] = zT; sTt[s][e] = zT;
+      if (JAC) sIe[s][e] = C();
+      if (JAC && HAS_MU) sIm[s][e] = C();
+    }
+  }
+  T yf0 = zT, yf1 = zT, yb0 = zT, ybm = zT, ybm_n = zT, yf1_p = zT;
+  if (colv) {
+    yf0 = ldg(cy + gj); yf1 = ldg(cy + ny + gj); yb0 = ldg(cy + 2 * ny + gj); ybm = ldg(cy + 3 * ny + gj);
+    if (JAC) {
+      if (gj + 1 < ny) ybm_n = ldg(cy + 3 * ny + gj + 1);
+      if (gj > 0) yf1_p = ldg(cy + ny + gj - 1);
+    }
+  }
+  const T sg = ldg(a.sigma + b);
+  T *y1 = a.y + (size_t)b * 2 * N, *y2 = y1 + N;
+  const T *r1 = (MODE != MODE_APPLY) ? a.rhs + (size_t)b * 2 * N : nullptr;
+
+  // prefetch registers (raw row), rows k+2 / k+1 / k
+  T pv1 = zT, pv2 = zT;
+  C pex = C(), pey = C(), pie = C(), pim = C(), pmx = C(), pmy = C();
+  T a1 = zT, b1 = zT, v11 = zT, v21 = zT, a0 = zT, b0 = zT, v10 = zT, v20 = zT;
+  C ie1 = C(), ie0 = C(), im1 = C(), im0 = C(), imm = C(), mx1 = C(), my1 = C(), mx0 = C(), my0 = C();
+  C ex1 = C(), ey1 = C(), ex0 = C(), ey0 = C();
+  T u0 = zT, t0 = zT, tm = zT;
+  T nr1 = zT, nr2 = zT;
+
+  auto load_row = [&](int gi) {
+    pv1 = zT; pv2 = zT; pex = C(); pey = C(); pie = C();
+    if (HAS_MU) { pim = C(); pmx = C(); pmy = C(); }
+    if (colv && gi >= 0 && gi < nx && gi >= i0 - 1 && gi <= i0 + TXR) {
+      const size_t g = (size_t)gi * ny + gj;
+      pv1 = ldg(x1 + g); pv2 = ldg(x2 + g);
+      pex = ldg(exx + g); pey = ldg(eyy + g); pie = ldg(iez + g);
+      if (HAS_MU) { pim = ldg(imz + g); pmx = ldg(mxx + g); pmy = ldg(myy + g); }
+    }
+  };
+  load_row(i0 - 1);
+  __syncthreads();
+
+  for (int k = i0 - 3; k < iend; ++k) {
+    const int s = k & 1, sp = s ^ 1;
+    const int xr = k - (i0 - 3);  // index of row k in sX
+    // step 0: row k+2 out of the prefetch registers, then prefetch row k+3 (and rhs of row k+1)
+    const T v12 = pv1, v22 = pv2;
+    const T a2 = pex * pv1, b2 = pey * pv2;
+    const C ie2 = pie, im2 = pim, mx2 = pmx, my2 = pmy, ex2 = pex, ey2 = pey;
+    load_row(k + 3);
+    T cr1 = nr1, cr2 = nr2;
+    if (MODE != MODE_APPLY) {
+      nr1 = zT; nr2 = zT;
+      if (outc && k + 1 >= i0 && k + 1 < iend) {
+        const size_t g = (size_t)(k + 1) * ny + gj;
+        nr1 = ldg(r1 + g); nr2 = ldg(r1 + N + g);
+      }
+    }
+    // step 1
+    sB[s][c + 1] = b2;
+    sV[s][c + 1] = v12;
+    // step 2: u[k+1], t[k+1]
+    const T bl = sB[sp][c], v1r = sV[sp][c + 2];
+    const T xf0n = sX[0][xr + 1], xf1n = sX[1][xr + 1], xb0n = sX[2][xr + 1], xbmn = sX[3][xr + 1];
+    T u1 = -(ie1 * (xb0n * a1 + xbmn * a0 + yb0 * b1 + ybm * bl));
+    T t1 = xf0n * v21 + xf1n * v22 - yf0 * v11 - yf1 * v1r;
+    if (HAS_MU) t1 = im1 * t1;
+    sU[s][c + 1] = u1;
+    sTt[s][c + 1] = t1;
+    if (JAC) sIe[s][c + 1] = ie1;
+    if (JAC && HAS_MU) sIm[s][c + 1] = im1;
+    // step 3: outputs of row k
+    if (outc && k >= i0) {
+      const T ur = sU[sp][c + 2], tl = sTt[sp][c];
+      const T xf0 = sX[0][xr], xf1 = sX[1][xr], xb0 = sX[2][xr], xbm = sX[3][xr];
+      T p1 = xf0 * u0 + xf1 * u1;
+      T p2 = yf0 * u0 + yf1 * ur;
+      const T c1 = yb0 * t0 + ybm * tl - a0;
+      const T c2 = xb0 * t0 + xbm * tm + b0;
+      if (HAS_MU) { p1 += my0 * c1; p2 -= mx0 * c2; } else { p1 += c1; p2 -= c2; }
+      const T o1 = p1 - sg * v10, o2 = p2 - sg * v20;
+      const size_t g = (size_t)k * ny + gj;
+      if (MODE == MODE_APPLY) {
+        y1[g] = o1; y2[g] = o2;
+      } else if (MODE == MODE_RESID) {
+        y1[g] = cr1 - o1; y2[g] = cr2 - o2;
+      } else {
+        const T xbm_n = sX[3][xr + 1], xf1_p = sX[1][xr - 1 >= 0 ? xr - 1 : 0];
+        const C ier = sIe[sp][c + 2];
+        T s1 = ie0 * (xf0 * xb0) + ie1 * (xf1 * xbm_n);
+        T s2 = ie0 * (yf0 * yb0) + ier * (yf1 * ybm_n);
+        T d1, d2;
+        if (HAS_MU) {
+          const C iml = sIm[sp][c];
+          T m1 = im0 * (yb0 * yf0) + iml * (ybm * yf1_p);
+          T m2 = im0 * (xb0 * xf0) + imm * (xbm * xf1_p);
+          d1 = -(ex0 * s1) - my0 * m1 - (my0 * ex0) * from_real<T>(1.0) - sg;
+          d2 = -(ey0 * s2) - mx0 * m2 - (mx0 * ey0) * from_real<T>(1.0) - sg;
+        } else {
+          T m1 = yb0 * yf0 + ybm * yf1_p;
+          T m2 = xb0 * xf0 + xbm * xf1_p;
+          d1 = -(ex0 * s1) - m1 - ex0 * from_real<T>(1.0) - sg;
+          d2 = -(ey0 * s2) - m2 - ey0 * from_real<T>(1.0) - sg;
+        }
+        y1[g] = v10 + a.omega * (recip(d1) * (cr1 - o1));
+        y2[g] = v20 + a.omega * (recip(d2) * (cr2 - o2));
+      }
+    }
+    // shift the register pipeline
+    tm = t0; t0 = t1; u0 = u1;
+    a0 = a1; b0 = b1; v10 = v11; v20 = v21; a1 = a2; b1 = b2; v11 = v12; v21 = v22;
+    ie0 = ie1; ie1 = ie2;
+    if (HAS_MU) { imm = im0; im0 = im1; im1 = im2; mx0 = mx1; my0 = my1; mx1 = mx2; my1 = my2; }
+    if (JAC) { ex0 = ex1; ey0 = ey1; ex1 = ex2; ey1 = ey2; }
+    __syncthreads();
+  }
+}
+
 // y = omega * D^-1 rhs  (first Jacobi sweep from a zero guess; no halo needed)
 template <typename T, typename C, bool HAS_MU>
 __global__ void __launch_bounds__(256) jacobi0_kernel(StencilArgs<T, C> a) {
@@ -495,6 +661,17 @@ template <typename T>
 __global__ void add_small_kernel(T *dst, int dstride, const T *src, int sstride, int n) {
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[(size_t)b * dstride + i] = dst[(size_t)b * dstride + i] + src[(size_t)b * sstride + i];
+}
+
+// out[b] = max(0, h[b][nv] - sum_{i<nv} |h[b][i]|^2): squared norm of w after one Gram-Schmidt pass
+template <typename T>
+__global__ void pythagoras_kernel(const T *h, int hstride, int nv, T *out, int ostride, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const T ww = h[(size_t)b * hstride + nv];
+  double acc = *reinterpret_cast<const double *>(&ww);
+  for (int i = 0; i < nv; ++i) acc -= abs2(h[(size_t)b * hstride + i]);
+  out[(size_t)b * ostride] = from_real<T>(acc > 0.0 ? acc : 0.0);
 }
 
 // Least-squares solve of the small GMRES Hessenberg systems, one thread per problem, in place.

@@ -65,6 +65,7 @@ struct ArenaSizer {
 struct SolveStats {
   int op_applies = 0, inner_iters = 0, restarts = 0;
   long stencil_applies = 0, launches = 0;
+  int inner_failures = 0;  // shift-invert solves that stopped above 1e4 x inner_tol
 };
 
 template <typename T> inline cd to_cd(T v);
@@ -343,6 +344,21 @@ class BatchSolver {
     a.cy = (true_op && l == 0) ? v.cy_true : v.cy;
     stats.launches++;
     a.omega = opt_.mg_omega;
+    if (l == 0) stats.stencil_applies++;
+    if (opt_.stencil_variant != 1 && v.nx >= 32 && v.ny >= 2) {
+      constexpr int TXR = 32;
+      dim3 blk(kMarchCols), grd((v.ny + kMarchOut - 1) / kMarchOut, (v.nx + TXR - 1) / TXR, B);
+      if (has_mu) {
+        if (mode == MODE_APPLY) stencil_march_kernel<T, C, MODE_APPLY, true, TXR><<<grd, blk, 0, st_>>>(a);
+        else if (mode == MODE_RESID) stencil_march_kernel<T, C, MODE_RESID, true, TXR><<<grd, blk, 0, st_>>>(a);
+        else stencil_march_kernel<T, C, MODE_JACOBI, true, TXR><<<grd, blk, 0, st_>>>(a);
+      } else {
+        if (mode == MODE_APPLY) stencil_march_kernel<T, C, MODE_APPLY, false, TXR><<<grd, blk, 0, st_>>>(a);
+        else if (mode == MODE_RESID) stencil_march_kernel<T, C, MODE_RESID, false, TXR><<<grd, blk, 0, st_>>>(a);
+        else stencil_march_kernel<T, C, MODE_JACOBI, false, TXR><<<grd, blk, 0, st_>>>(a);
+      }
+      return;
+    }
     constexpr int TX = Tile<T>::TX, TY = Tile<T>::TY;
     dim3 blk(TY, 256 / TY), grd((v.ny + TY - 1) / TY, (v.nx + TX - 1) / TX, B);
     if (has_mu) {
@@ -354,7 +370,6 @@ class BatchSolver {
       else if (mode == MODE_RESID) stencil_kernel<T, C, MODE_RESID, false><<<grd, blk, 0, st_>>>(a);
       else stencil_kernel<T, C, MODE_JACOBI, false><<<grd, blk, 0, st_>>>(a);
     }
-    if (l == 0) stats.stencil_applies++;
   }
   void jacobi0(int l, const T *rhs, T *y) {
     Level &v = lv[l];
@@ -479,29 +494,58 @@ class BatchSolver {
     CUDA_CHECK(cudaStreamSynchronize(st_));
   }
 
-  // CGS2 of w against V_0..V_{nv-1}; leaves h (nv values) and ||w||^2 in hhost_: layout per problem
-  // [h1 (nvmax) | h2 (nvmax) | nrm2], then normalises w into `dst`.
-  void orthonormalise(const T *V, int nv, T *w, T *dst, std::vector<cd> &h, std::vector<double> &nrm) {
+  // Gram-Schmidt of w = V_nv (the slot right after the basis) against V_0..V_{nv-1}, then normalise into dst.
+  // selective = false: two classical passes (CGS2).  selective = true: one pass, a second one only when the
+  // cancellation test ||w'|| < 1e-2 ||w|| fires for some problem (w.w comes for free as an extra column of the first
+  // multi-dot).  Leaves h (nv values per problem) and ||w'|| in the output vectors.
+  void orthonormalise(const T *V, int nv, T *w, T *dst, std::vector<cd> &h, std::vector<double> &nrm, bool selective = false,
+                      const std::vector<char> *skip = nullptr) {
     const int hs = hstride(), half = std::max(m, restart) + 2;
-    dots(V, nv, w, hbuf_, hs, 0, false);
-    axpys(V, nv, hbuf_, hs, -1.0, w);
+    h.assign((size_t)B * nv, cd(0, 0));
+    nrm.assign(B, 0.0);
+    bool second = !selective;
+    if (selective) {
+      dots(V, nv + 1, w, hbuf_, hs, 0, false);  // column nv is w.w (w sits in slot nv)
+      axpys(V, nv, hbuf_, hs, -1.0, w);
+      pythagoras_kernel<T><<<(B + 31) / 32, 32, 0, st_>>>(hbuf_, hs, nv, hbuf_ + 2 * half, hs, B);
+      stats.launches++;
+      fetch_h((size_t)B * hs);
+      for (int b = 0; b < B; ++b) {
+        if (skip && (*skip)[b]) continue;
+        const double ww = to_cd(hhost_[(size_t)b * hs + nv]).real();
+        const double after = to_cd(hhost_[(size_t)b * hs + 2 * half]).real();
+        if (!(after >= 1e-4 * ww)) second = true;  // ||w'|| < 1e-2 ||w||: cancellation would cost > 2 digits of orthogonality
+      }
+      for (int b = 0; b < B; ++b)
+        for (int i = 0; i < nv; ++i) h[(size_t)b * nv + i] = to_cd(hhost_[(size_t)b * hs + i]);
+      if (!second) {
+        scale_inv_norm(w, dst, hbuf_ + 2 * half, hs);
+        for (int b = 0; b < B; ++b) nrm[b] = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hs + 2 * half]).real()));
+        return;
+      }
+    } else {
+      dots(V, nv, w, hbuf_, hs, 0, false);
+      axpys(V, nv, hbuf_, hs, -1.0, w);
+    }
     dots(V, nv, w, hbuf_, hs, half, false);
     axpys(V, nv, hbuf_ + half, hs, -1.0, w);
     dots(w, 1, w, hbuf_, hs, 2 * half, false);
     scale_inv_norm(w, dst, hbuf_ + 2 * half, hs);
     fetch_h((size_t)B * hs);
-    h.assign((size_t)B * nv, cd(0, 0));
-    nrm.assign(B, 0.0);
     for (int b = 0; b < B; ++b) {
-      for (int i = 0; i < nv; ++i) h[(size_t)b * nv + i] = to_cd(hhost_[(size_t)b * hs + i]) + to_cd(hhost_[(size_t)b * hs + half + i]);
+      for (int i = 0; i < nv; ++i) {
+        cd first = selective ? h[(size_t)b * nv + i] : to_cd(hhost_[(size_t)b * hs + i]);
+        h[(size_t)b * nv + i] = first + to_cd(hhost_[(size_t)b * hs + half + i]);
+      }
       nrm[b] = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hs + 2 * half]).real()));
     }
   }
 
   // -- FGMRES: xsol_ = (A - sigma)^-1 rhs ------------------------------------------------------------
   // returns max relative residual estimate; iters_out = iterations of the slowest problem
-  double fgmres(const T *rhs, T *xsol, int &iters_out, const std::vector<char> *skip = nullptr) {
-    const double tol = opt_.inner_tol;
+  double fgmres(const T *rhs, T *xsol, int &iters_out, const std::vector<char> *skip = nullptr,
+                const std::vector<double> *tolv = nullptr) {
+    auto tol_of = [&](int b) { return tolv ? (*tolv)[b] : opt_.inner_tol; };
     std::vector<char> done(B, 0);
     if (skip) done = *skip;
     std::vector<double> bnorm(B, 0.0), res(B, 0.0);
@@ -523,7 +567,7 @@ class BatchSolver {
         beta[b] = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hstride()]).real()));
         if (first) bnorm[b] = beta[b];
         res[b] = bnorm[b] > 0 ? beta[b] / bnorm[b] : 0.0;
-        if (!(beta[b] > 0) || res[b] <= tol) done[b] = 1;
+        if (!(beta[b] > 0) || res[b] <= tol_of(b)) done[b] = 1;
         if (!done[b]) all_done = false;
       }
       first = false;
@@ -539,7 +583,7 @@ class BatchSolver {
         T *vk = Vg_ + (size_t)kk * vstride, *zk = Zg_ + (size_t)kk * vstride, *w = Vg_ + (size_t)(kk + 1) * vstride;
         vcycle(0, vk, zk);
         apply(0, MODE_APPLY, zk, nullptr, w, true);
-        orthonormalise(Vg_, kk + 1, w, w, h, nrm);
+        orthonormalise(Vg_, kk + 1, w, w, h, nrm, opt_.gmres_cgs2 == 0, &cyc_done);
         ++total_it;
         bool all = true;
         for (int b = 0; b < B; ++b) {
@@ -563,7 +607,7 @@ class BatchSolver {
           g[b][kk] = std::conj(c) * g[b][kk];
           kused[b] = kk + 1;
           res[b] = std::abs(g[b][kk + 1]) / bnorm[b];
-          if (res[b] <= tol || !(nrm[b] > 0)) cyc_done[b] = 1;
+          if (res[b] <= tol_of(b) || !(nrm[b] > 0)) cyc_done[b] = 1;
           if (!cyc_done[b]) all = false;
         }
         if (all) {
@@ -590,7 +634,7 @@ class BatchSolver {
       CUDA_CHECK(cudaStreamSynchronize(st_));
       bool all_conv = true;
       for (int b = 0; b < B; ++b) {
-        if (cyc_done[b] && res[b] <= tol) done[b] = 1;
+        if (cyc_done[b] && res[b] <= tol_of(b)) done[b] = 1;
         if (!done[b]) all_conv = false;
       }
       if (all_conv) break;  // the FGMRES residual estimate is the true residual up to rounding
@@ -642,14 +686,18 @@ class BatchSolver {
     std::vector<CMat> Yfinal(B, CMat(m, k));
     std::vector<cd> h;
     std::vector<double> nrm;
+    // inexact shift-invert: the inner tolerance is relaxed as the wanted Ritz pairs converge
+    // (tol_j ~ eps / ||r_{j-1}||, Bouras & Fraysse / Simoncini); capped and with a safety factor
+    std::vector<double> tolv(B, opt_.inner_tol);
     int nkeep = 0;
     const int keep_target = std::min(m - 1, k + std::max(1, (m - k) / 2));
     for (int rst = 0; rst <= opt_.max_restarts; ++rst) {
       for (int j = nkeep; j < m; ++j) {
         T *vj = Vout_ + (size_t)j * vstride, *w = Vout_ + (size_t)(j + 1) * vstride;
         int its = 0;
-        fgmres(vj, w, its, &done);
+        double worst = fgmres(vj, w, its, &done, &tolv);
         stats.op_applies++;
+        if (!(worst <= 1e-3)) stats.inner_failures++;
         orthonormalise(Vout_, j + 1, w, w, h, nrm);
         for (int b = 0; b < B; ++b) {
           if (done[b]) continue;
@@ -661,6 +709,7 @@ class BatchSolver {
       // Rayleigh-Ritz + restart matrices
       std::vector<T> qh((size_t)B * m * m, zero_of<T>());
       bool all_done = true;
+      std::vector<int> newly;
       for (int b = 0; b < B; ++b) {
         if (done[b]) continue;
         CMat Tm(m, m), Q;
@@ -705,8 +754,11 @@ class BatchSolver {
         }
         out.nconv[b] = nconv;
         out.resid[b] = worst;
+        if (opt_.inner_relax > 0)
+          tolv[b] = std::min(opt_.inner_relax_cap, std::max(opt_.inner_tol, opt_.inner_relax * opt_.inner_tol / std::max(worst, 1e-300)));
         if (nconv == k || rst == opt_.max_restarts) {
           done[b] = 1;
+          newly.push_back(b);
           for (int q = 0; q < k; ++q) {
             const int i = w[q];
             out.theta[(size_t)b * k + q] = Tm(i, i);
@@ -755,6 +807,9 @@ class BatchSolver {
         for (int r = 0; r < m; ++r)
           for (int i = 0; i < keep; ++i) qh[((size_t)b * m + r) * m + i] = from_cd<T>(Qk(r, i));
       }
+      // Ritz vectors of the problems that converged in this cycle must be formed now: their basis is not
+      // maintained once they are frozen
+      if (!newly.empty()) extract_ritz(newly, Yfinal, real_arith);
       if (all_done) break;
       // V[:, :keep] <- V Q ; V[keep] <- V[m]      (Zg_ is free between inner solves: scratch)
       const int keep = keep_of(keep_target);
@@ -769,9 +824,14 @@ class BatchSolver {
       CUDA_CHECK(cudaStreamSynchronize(st_));
       nkeep = keep;
     }
-    // Ritz vectors X = V Y (unit norm); real arithmetic: make Y real (phase fix) for real eigenvalues
+    return out;
+  }
+
+  // Ritz vectors X = V Y (unit norm) for the listed problems -> ritz_ slots; real arithmetic: Y is made real
+  // (phase fix) for real eigenvalues
+  void extract_ritz(const std::vector<int> &which, const std::vector<CMat> &Yfinal, bool real_arith) {
     std::vector<T> yh((size_t)B * m * k, zero_of<T>());
-    for (int b = 0; b < B; ++b)
+    for (int b : which)
       for (int q = 0; q < k; ++q) {
         cd ph(1, 0);
         if (real_arith) {
@@ -797,10 +857,13 @@ class BatchSolver {
     CUDA_CHECK(cudaMemcpyAsync(qbuf_, yh.data(), yh.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
     {
       dim3 grd(vec_blocks(), B);
-      lincomb_kernel<T><<<grd, 256, (size_t)m * k * sizeof(T), st_>>>(Vout_, vstride, len, qbuf_, m, k, k, ritz_, vstride);
+      lincomb_kernel<T><<<grd, 256, (size_t)m * k * sizeof(T), st_>>>(Vout_, vstride, len, qbuf_, m, k, k, Zg_, vstride);
     }
+    for (int b : which)
+      for (int q = 0; q < k; ++q)
+        CUDA_CHECK(cudaMemcpyAsync(ritz_ + (size_t)q * vstride + (size_t)b * len, Zg_ + (size_t)q * vstride + (size_t)b * len,
+                                   len * sizeof(T), cudaMemcpyDeviceToDevice, st_));
     CUDA_CHECK(cudaStreamSynchronize(st_));
-    return out;
   }
 
   // true eigen-residuals ||A x - lambda x|| / (|lambda| ||x||) for Ritz vector slot q, per problem

@@ -42,13 +42,17 @@ def components(name, wl, kw):
     real = not np.issubdtype(R.solver_dtype(st, "double"), np.complexfloating)
     sigma = -st["target"] ** 2
     lv0 = P.fine_level(st, sigma)
+    ph = 0.7853981633974483
+    lim = lambda l: np.abs(l) * np.exp(1j * np.clip(np.angle(l), -ph, ph))  # noqa: E731
+    st_p = dict(st); st_p["slen"] = [(lim(lf), lim(lb)) for lf, lb in st["slen"]]
+    lvp = P.fine_level(st_p, sigma)
     kmax = np.sqrt(max(0.0, max(lv0.exx.real.max(), lv0.eyy.real.max()) - st["target"] ** 2))
     indef = kmax**2 > 1e-6
-    mg = P.Multigrid(lv0, min_size=12, nu=2, omega=0.8, coarse_sweeps=16, coarse_gmres=16 if indef else 0,
+    mg = P.Multigrid(lvp, min_size=12, nu=2, omega=0.8, coarse_sweeps=16, coarse_gmres=16 if indef else 0,
                      kh_limit=2 * np.pi / 4 if indef else 0.0, kmax=kmax)
     print(f"== {name}: real={real} levels={[(l.nx, l.ny) for l in mg.levels]} indef={indef}")
     mk = (lambda s: cvec(s).real + 0j) if real else cvec
-    for li, lv in enumerate(mg.levels[:3]):
+    for li, lv in enumerate([lv0] + mg.levels[1:3]):
         x = mk((2, lv.nx, lv.ny)); rhs = mk((2, lv.nx, lv.ny))
         n2 = 2 * lv.nx * lv.ny
         y = dev_apply(pk, li, 0, x, None, n2)
@@ -111,8 +115,10 @@ def full(names):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["comp", "full"]
+    if "tiled" in which:
+        H.set_options(stencil_variant=1)
     if "comp" in which:
-        for name in ["c1_64", "c1_64_sym_pmc_pec", "c3_96", "lossy_48", "c4_96", "nonuniform_56", "slab1d_x1"]:
+        for name in ["c1_64", "c1_64_sym_pmc_pec", "c3_96", "lossy_48", "c4_96", "nonuniform_56", "slab1d_x1", "slab1d_y1", "strip_128_m4", "c4_128"]:
             fac, kw, _ = CASES[name]
             try:
                 components(name, fac(), kw)
