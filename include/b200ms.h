@@ -62,6 +62,9 @@ typedef struct {
                             each component C-order with y fastest (solver.py:890-901) */
   const double *coords_x; /* nx+1 */
   const double *coords_y; /* ny+1 */
+  const double *basis_e; /* NULL, or the in-plane E part of `solver_basis_fields` (solver.py:219-236, 750-776):
+                            2*nx*ny*num_modes complex128 (re,im) laid out [Ex|Ey][ix][iy][mode]; the modes are then
+                            computed as linear combinations of this basis (relative mode solver) */
 } b200ms_problem;
 
 typedef struct {
@@ -76,7 +79,9 @@ typedef struct {
   int inner_iters;       /* out: total preconditioned GMRES iterations */
   int stencil_applies;   /* out: kernels launched for this batch (all kinds) */
   int is_complex;        /* out: 1 if the eigenproblem was solved in complex arithmetic (solver.py:389-411) */
-  double solve_ms;       /* out: device time of the batch this problem was solved in */
+  double solve_ms;       /* out: device time (CUDA events) of the eigen-solve + field recovery of the batch this problem
+                            was in, operator data already resident in HBM, results still on the device */
+  double total_ms;       /* out: host wall time of that batch incl. upload of the operator and download of the fields */
   double max_residual;   /* out: max_i ||A v_i - lambda_i v_i|| / (|lambda_i| ||v_i||) */
 } b200ms_result;
 

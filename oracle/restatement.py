@@ -307,11 +307,22 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
                   symmetry=(0, 0), direction="+", solver_basis_fields=None, tol=FP_EPS, info=None):  # fmt: skip
     """Restatement of ``compute_modes`` (solver.py:33-269, 941).  ``tol`` defaults to the
     reference's ARPACK tolerance (solver.py:20); tests pass 1e-12 for a tight oracle.
-    ``split_curl_scaling`` / ``solver_basis_fields`` are not restated."""
-    if split_curl_scaling is not None or solver_basis_fields is not None:
-        raise NotImplementedError("oracle: split-curl / relative solver not restated")
+    ``split_curl_scaling`` is not restated."""
+    if split_curl_scaling is not None:
+        raise NotImplementedError("oracle: split-curl not restated")
     st = setup(eps_cross, coords, freq, mode_spec, symmetry, mu_cross)
     n, m_modes = st["n"], mode_spec.num_modes
+    basis_vecs = None
+    if solver_basis_fields is not None:  # solver.py:219-236, 523-528
+        if st["tensorial"]:
+            raise RuntimeError("Tensorial eps not yet supported in relative mode solver (with basis fields provided).")
+        try:
+            basis_e = np.asarray(solver_basis_fields)[:3, ...].reshape((3, n, m_modes))
+        except ValueError:
+            raise ValueError("Shape mismatch between 'basis_fields' and requested mode data.")
+        jinv = np.moveaxis(np.linalg.inv(np.moveaxis(st["jac_e"], [0, 1], [-2, -1])), [-2, -1], [0, 1])
+        basis_e = np.einsum("ijn,inm->jnm", jinv, basis_e)
+        basis_vecs = np.concatenate((basis_e[0], basis_e[1]), axis=0)
     e, m = st["eps"], st["mu"]
     dtype = solver_dtype(st, mode_spec.precision)
     dxf, dxb, dyf, dyb = d_matrices(st)
@@ -336,7 +347,14 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
             _trim(mat)
         v0 = _cast(initial_vector(st["nx"], st["ny"], 2), dtype)
         sigma = _cast(np.array([-(st["target"] ** 2)]), dtype)[0]
-        vals, vecs = eigs(mat, sigma, v0)
+        if basis_vecs is None:
+            vals, vecs = eigs(mat, sigma, v0)
+        else:  # solver_eigs_relative, solver.py:750-776: dense Rayleigh-Ritz in the span of the basis
+            import scipy.linalg as sl
+
+            qb, _ = np.linalg.qr(basis_vecs)
+            vals, coeffs = sl.eig(np.conj(qb.T) @ (mat @ qb))
+            vecs = qb @ coeffs
         if vals.size == 0:
             raise RuntimeError("Could not find any eigenmodes for this waveguide.")
         root = np.emath.sqrt(-vals + 0j)  # solver.py:884

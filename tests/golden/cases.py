@@ -79,6 +79,14 @@ CASES = {
 }
 
 
+def relative_case(n=48):
+    """Relative mode solver (solver.py:750-776): the basis is the reference's own modes at a nearby wavelength."""
+    wl = W.si_strip(n, 3, lam=1.55)
+    wl.name = f"relative_{n}"
+    wl.extra["basis_lam"] = 1.56
+    return wl
+
+
 def _axis0(wl):
     wl.mode_spec.bend_axis = 0
     wl.name += "_axis0"

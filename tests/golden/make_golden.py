@@ -51,7 +51,24 @@ def run(name):
           "%.1fs/%.1fs" % (out["sec_ref"], out["sec_tight"]), flush=True)  # fmt: skip
 
 
+def run_relative():
+    """Fixture for the relative solver: basis = reference modes at 1.56 um, solve at 1.55 um in that span."""
+    from tests.golden.cases import relative_case
+    from tidy3d_b200 import workloads as W
+
+    wl = relative_case()
+    basis, nb, _ = ref_shim.compute_modes(wl.eps_cross, wl.coords, W.C_0 / wl.extra["basis_lam"], wl.mode_spec)
+    sbf = np.concatenate((basis[0], basis[1]), axis=0)  # (6, Nx, Ny, 1, M) like _postprocess_solver_fields_inverse
+    fields, n_complex, spec = ref_shim.compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, solver_basis_fields=sbf)
+    np.savez_compressed(os.path.join(HERE, "relative_48.npz"), basis=sbf, n_ref=n_complex, n_tight=n_complex, spec=spec,
+                        fields_tight=fields, sig_ref=signature(fields))
+    print("relative_48", spec, n_complex, flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["relative"]:
+        run_relative()
+        sys.exit(0)
     names = sys.argv[1:] or [n for n in CASES if not os.path.exists(os.path.join(HERE, n + ".npz"))]
     for n in names:
         run(n)

@@ -125,6 +125,20 @@ def test_direction_and_precision_contract():
     assert np.abs(n_s - n_p).max() < 1e-5
 
 
+def test_relative_mode_solver_matches_reference():
+    """solver_basis_fields path (solver_eigs_relative, solver.py:750-776) against a fixture made by the reference."""
+    from tests.golden.cases import relative_case
+
+    wl = relative_case()
+    g = load_golden("relative_48")
+    f, n, spec = compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, solver_basis_fields=g["basis"])
+    assert spec == "diagonal"
+    assert np.abs(n - g["n_ref"]).max() < 1e-9
+    assert (mode_overlaps(f, g["fields_tight"]) > 1 - 1e-8).all()
+    with pytest.raises(ValueError, match="Shape mismatch between 'basis_fields'"):
+        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, solver_basis_fields=g["basis"][..., :2])
+
+
 def test_unsupported_paths_fail_loudly():
     wl = W.angled(32)
     with pytest.raises(NotImplementedError):

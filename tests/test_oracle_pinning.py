@@ -30,6 +30,16 @@ def test_restatement_matches_golden(name):
         assert (mode_overlaps(ft, g["fields_tight"])[ok] > 1 - 1e-6).all()
 
 
+def test_relative_solver_restatement_matches_golden():
+    from tests.golden.cases import relative_case
+
+    wl = relative_case()
+    g = load_golden("relative_48")
+    f, n, spec = R.compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, solver_basis_fields=g["basis"])
+    assert spec == str(g["spec"]) and np.abs(n - g["n_ref"]).max() < 1e-12
+    assert (mode_overlaps(f, g["fields_tight"]) > 1 - 1e-10).all()
+
+
 def test_pml_profile_known_answer():
     """Restates the reference's own exact test ``test_pml_params`` (tests/test_plugins/test_mode_solver.py:783-806)."""
     omega, n, npml = 1.0, 10, 4

@@ -30,7 +30,7 @@ class Problem(C.Structure):
         ("symmetry", C.c_int * 2), ("bend_axis", C.c_int), ("direction", C.c_int), ("precision", C.c_int),
         ("freq", C.c_double), ("target_neff", C.c_double), ("bend_radius", C.c_double),
         ("angle_theta", C.c_double), ("angle_phi", C.c_double),
-        ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp),
+        ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp), ("basis_e", _dp),
     ]  # fmt: skip
 
 
@@ -38,7 +38,7 @@ class Result(C.Structure):
     _fields_ = [
         ("fields", _dp), ("n_complex", _dp), ("eps_spec", C.c_int), ("status", C.c_int), ("converged", C.c_int),
         ("outer_iters", C.c_int), ("op_applies", C.c_int), ("inner_iters", C.c_int), ("stencil_applies", C.c_int),
-        ("is_complex", C.c_int), ("solve_ms", C.c_double), ("max_residual", C.c_double),
+        ("is_complex", C.c_int), ("solve_ms", C.c_double), ("total_ms", C.c_double), ("max_residual", C.c_double),
     ]  # fmt: skip
 
 
@@ -99,7 +99,7 @@ def _ptr(a):
 class PackedProblem:
     """Owns the contiguous arrays a ``Problem`` struct points to."""
 
-    def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None):
+    def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None, basis_fields=None):
         if eps_packed is not None:
             eps = eps_packed
         else:
@@ -138,6 +138,18 @@ class PackedProblem:
         p.angle_theta = float(getattr(mode_spec, "angle_theta", 0.0))
         p.angle_phi = float(getattr(mode_spec, "angle_phi", 0.0))
         p.eps, p.coords_x, p.coords_y = _ptr(self.eps.view(np.float64)), _ptr(self.cx), _ptr(self.cy)
+        self.basis = None
+        if basis_fields is not None:
+            try:  # solver.py:222-230
+                b = np.asarray(basis_fields)[:3, ...].reshape((3, self.nx * self.ny, p.num_modes))
+            except ValueError:
+                raise ValueError(
+                    "Shape mismatch between 'basis_fields' and requested mode data. "
+                    "Make sure the mode solvers are set up the same, and that the "
+                    "basis mode solver data has 'colocate=False'."
+                )
+            self.basis = np.ascontiguousarray(b[:2], dtype=np.complex128)
+            p.basis_e = _ptr(self.basis.view(np.float64))
         self.struct = p
         self.num_modes = p.num_modes
 

@@ -1,6 +1,7 @@
 // C ABI of libb200ms.so (see include/b200ms.h for the reference interfaces each entry point replaces).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -93,10 +94,21 @@ extern "C" const char *b200ms_last_error(b200ms_handle *h) { return h ? h->err.c
 namespace {
 
 struct GroupKey {
-  int nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir;
+  int nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel;
   bool operator<(const GroupKey &o) const {
-    return std::tie(nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir) <
-           std::tie(o.nx, o.ny, o.k, o.kind, o.has_mu, o.sx, o.sy, o.jz_axis, o.dir);
+    return std::tie(nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel) <
+           std::tie(o.nx, o.ny, o.k, o.kind, o.has_mu, o.sx, o.sy, o.jz_axis, o.dir, o.rel);
+  }
+};
+struct MediumKey {
+  const double *eps, *cx, *cy;
+  int nx, ny, k, p0, p1, s0, s1, bend_axis, dir;
+  double bend_radius, target, theta, phi;
+  bool operator==(const MediumKey &o) const {
+    auto same = [](double a, double b) { return (std::isnan(a) && std::isnan(b)) || a == b; };
+    return eps == o.eps && cx == o.cx && cy == o.cy && nx == o.nx && ny == o.ny && k == o.k && p0 == o.p0 && p1 == o.p1 &&
+           s0 == o.s0 && s1 == o.s1 && bend_axis == o.bend_axis && dir == o.dir && same(bend_radius, o.bend_radius) &&
+           same(target, o.target) && theta == o.theta && phi == o.phi;
   }
 };
 // kind: 0 real, 1 complex vectors + real fields, 2 all complex
@@ -117,20 +129,36 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
       share = false;
   }
   BatchSolver<T, C> S(h->arena, h->stream, h->opt);
-  CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  auto wall0 = std::chrono::steady_clock::now();
   S.build(ps, share);
-  S.init_start_vector(0);
+  CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));  // inputs are resident in HBM from here on
   const bool real_arith = std::is_same<T, double>::value;
-  auto eig = S.krylov_schur(real_arith);
+  const bool relative = ps[0]->relative;
   const int k = S.k;
+  typename BatchSolver<T, C>::EigResult eig;
+  std::vector<cd> rel_vals;
+  if (relative) {
+    std::vector<const cd *> basis(B);
+    for (int b = 0; b < B; ++b) basis[b] = reinterpret_cast<const cd *>(prob[ids[b]].basis_e);
+    rel_vals = S.solve_relative(basis);
+    eig.nconv.assign(B, k);
+    eig.resid.assign(B, 0.0);
+  } else {
+    S.init_start_vector(0);
+    eig = S.krylov_schur(real_arith);
+  }
   // eigenvalues of A: lambda = sigma + 1/theta; n = sqrt(-lambda) (principal root, solver.py:884)
   std::vector<cd> nsorted((size_t)B * k), lam((size_t)B * k);
   std::vector<int> perm((size_t)B * k);
   for (int b = 0; b < B; ++b) {
     std::vector<cd> nn(k), ll(k);
     for (int q = 0; q < k; ++q) {
-      cd th = eig.theta[(size_t)b * k + q];
-      ll[q] = ps[b]->sigma + (std::abs(th) > 0 ? 1.0 / th : cd(0, 0));
+      if (relative) {
+        ll[q] = rel_vals[(size_t)b * k + q];
+      } else {
+        cd th = eig.theta[(size_t)b * k + q];
+        ll[q] = ps[b]->sigma + (std::abs(th) > 0 ? 1.0 / th : cd(0, 0));
+      }
       nn[q] = std::sqrt(-ll[q]);
       if (nn[q].real() < 0) nn[q] = -nn[q];
     }
@@ -166,6 +194,8 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
   CUDA_CHECK(cudaEventSynchronize(h->ev1));
   float ms = 0.f;
   CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (want_fields) S.copy_fields_out(dst.data());
+  const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   for (int b = 0; b < B; ++b) {
     b200ms_result &r = res[ids[b]];
     for (int q = 0; q < k; ++q) {
@@ -185,10 +215,11 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
     r.stencil_applies = (int)std::min<long>(S.stats.launches, 2147483647L);
     r.is_complex = real_arith ? 0 : 1;
     r.solve_ms = ms;
+    r.total_ms = total_ms;
     r.max_residual = maxres[b];
     // converged == Ritz residuals of OP below eig_tol (ARPACK's criterion).  The residual with respect to A itself is
     // reported for information: it is amplified by ||A - sigma|| ~ 1/(k0 dl)^2 and only screened for garbage here.
-    r.status = (eig.nconv[b] == k && eig.ok && maxres[b] < 1e-3 && S.stats.inner_failures == 0) ? B200MS_OK : B200MS_ERR_NOCONV;
+    r.status = (relative || (eig.nconv[b] == k && eig.ok && maxres[b] < 1e-3 && S.stats.inner_failures == 0)) ? B200MS_OK : B200MS_ERR_NOCONV;
     if (h->opt.verbose)
       fprintf(stderr, "[b200ms] prob %d: conv %d/%d restarts %d op %d inner %d stencil %ld res %.2e ms %.1f\n", ids[b],
               eig.nconv[b], k, S.stats.restarts, S.stats.op_applies, S.stats.inner_iters, S.stats.stencil_applies,
@@ -214,13 +245,24 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
   try {
     std::vector<ProblemSetup> setups(nprob);
     std::map<GroupKey, std::vector<int>> groups;
+    std::vector<std::pair<MediumKey, int>> seen;
     for (int i = 0; i < nprob; ++i) {
       res[i].status = B200MS_OK;
       res[i].converged = 0;
       if (!res[i].n_complex) {
         res[i].status = B200MS_ERR_ARG;
       } else {
-        setup_problem(prob[i], setups[i]);
+        // a sweep over one cross-section sets the medium up once (pointer equality == identical content)
+        MediumKey mk{prob[i].eps, prob[i].coords_x, prob[i].coords_y, prob[i].nx, prob[i].ny, prob[i].num_modes,
+                     prob[i].num_pml[0], prob[i].num_pml[1], prob[i].symmetry[0], prob[i].symmetry[1], prob[i].bend_axis,
+                     prob[i].direction, prob[i].bend_radius, prob[i].target_neff, prob[i].angle_theta, prob[i].angle_phi};
+        auto it = std::find_if(seen.begin(), seen.end(), [&](const std::pair<MediumKey, int> &e) { return e.first == mk; });
+        if (it != seen.end() && setups[it->second].status == B200MS_OK) {
+          setup_problem_like(prob[i], setups[it->second], setups[i]);
+        } else {
+          setup_problem(prob[i], setups[i]);
+          seen.push_back({mk, i});
+        }
         res[i].status = setups[i].status;
         res[i].eps_spec = setups[i].eps_spec;
         res[i].is_complex = setups[i].is_complex;
@@ -234,7 +276,7 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
       }
       const ProblemSetup &s = setups[i];
       GroupKey key{s.nx, s.ny, s.num_modes, kind_of(s), s.has_mu ? 1 : 0, prob[i].symmetry[0], prob[i].symmetry[1],
-                   s.jz_axis, s.direction};
+                   s.jz_axis, s.direction, s.relative ? 1 : 0};
       groups[key].push_back(i);
     }
     size_t free_b = 0, total_b = 0;
@@ -399,8 +441,8 @@ extern "C" int b200ms_debug_setup(const b200ms_problem *prob, double *sigma, int
     const size_t n = (size_t)s.nx * s.ny;
     for (int q = 0; q < 6; ++q)
       for (size_t i = 0; i < n; ++i) {
-        fields[2 * (q * n + i)] = s.f[q][i].real();
-        fields[2 * (q * n + i) + 1] = s.f[q][i].imag();
+        fields[2 * (q * n + i)] = s.f(q)[i].real();
+        fields[2 * (q * n + i) + 1] = s.f(q)[i].imag();
       }
   }
   return s.status;

