@@ -105,6 +105,7 @@ typedef struct {
   double inner_relax_cap; /* loosest inner tolerance allowed (default 1e-4) */
   int gmres_cgs2;        /* 1 (default): CGS2 in the inner FGMRES; 0: second pass only on cancellation (measured: 3x more iterations) */
   int stencil_variant;   /* 0: marching kernel (default), 1: shared-memory tiled kernel (reference implementation) */
+  int mg_precision;      /* 1 (default): multigrid preconditioner in fp32 (Krylov iteration stays fp64); 0: all fp64 */
 } b200ms_options;
 
 int b200ms_version(void);
@@ -120,11 +121,12 @@ const char *b200ms_last_error(b200ms_handle *h);
  * result carries its own status). */
 int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_problem *prob, b200ms_result *res);
 
-/* Benchmark / roofline hook: run the fused curl-curl stencil y = (A - sigma) x `nrep` times on
- * `nbatch` device-resident copies of the operator of `prob` and return the mean kernel time (CUDA
- * events on the library stream).  mode 0: operator apply, 1: fused Jacobi sweep.  x (2*nx*ny values,
- * complex128 (re,im)) may be NULL (random); y may be NULL.  bytes_per_apply returns the algorithmic
- * bytes of one launch (N*(4*s_v + n_coef*s_c) per problem). */
+/* Benchmark / roofline hook: run one of the two hot stencil kernels `nrep` times on `nbatch` device-resident copies
+ * of the operator of `prob` and return the mean kernel time (CUDA events on the library stream).
+ * mode 0: y = (A - sigma) x, the fp64 operator apply of the Krylov iteration; mode 1: the production smoother sweep
+ * (stored-diagonal Jacobi in the multigrid precision).  x (2*nx*ny complex128 (re,im)) may be NULL (random); y may be
+ * NULL.  bytes_per_apply returns the algorithmic bytes of one launch: N*(4*s_v + nf*s_c) per problem for
+ * the apply, N*(8*s_v + nf*s_c) for the sweep. */
 int b200ms_bench_stencil(b200ms_handle *h, const b200ms_problem *prob, int nbatch, int mode, int nrep,
                          int flush_l2, const double *x, double *y, double *ms_per_launch,
                          double *bytes_per_apply);

@@ -45,6 +45,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->verbose = 0;
   o->mg_pml_phase = 0.7853981633974483;
   o->stencil_variant = 0;
+  o->mg_precision = 1;
   o->gmres_cgs2 = 1;
   o->inner_relax = 1.0;
   o->inner_relax_cap = 1e-4;
@@ -114,7 +115,7 @@ struct MediumKey {
 // kind: 0 real, 1 complex vectors + real fields, 2 all complex
 int kind_of(const ProblemSetup &s) { return !s.is_complex ? 0 : (s.coef_complex ? 2 : 1); }
 
-template <typename T, typename C>
+template <typename T, typename C, typename P, typename PC>
 void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vector<ProblemSetup> &setups,
                  const b200ms_problem *prob, b200ms_result *res) {
   const int B = (int)ids.size();
@@ -128,14 +129,14 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
         p.bend_axis != p0.bend_axis)
       share = false;
   }
-  BatchSolver<T, C> S(h->arena, h->stream, h->opt);
+  BatchSolver<T, C, P, PC> S(h->arena, h->stream, h->opt);
   auto wall0 = std::chrono::steady_clock::now();
   S.build(ps, share);
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));  // inputs are resident in HBM from here on
   const bool real_arith = std::is_same<T, double>::value;
   const bool relative = ps[0]->relative;
   const int k = S.k;
-  typename BatchSolver<T, C>::EigResult eig;
+  typename BatchSolver<T, C, P, PC>::EigResult eig;
   std::vector<cd> rel_vals;
   if (relative) {
     std::vector<const cd *> basis(B);
@@ -288,10 +289,20 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
       int bmax = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, h->opt.max_batch), (size_t)(0.6 * free_b) / per));
       for (size_t s0 = 0; s0 < all.size(); s0 += bmax) {
         std::vector<int> ids(all.begin() + s0, all.begin() + std::min(all.size(), s0 + bmax));
+        const bool f32 = h->opt.mg_precision == 1;
         switch (kv.first.kind) {
-          case 0: solve_group<double, double>(h, ids, setups, prob, res); break;
-          case 1: solve_group<cplx, double>(h, ids, setups, prob, res); break;
-          default: solve_group<cplx, cplx>(h, ids, setups, prob, res); break;
+          case 0:
+            if (f32) solve_group<double, double, float, float>(h, ids, setups, prob, res);
+            else solve_group<double, double, double, double>(h, ids, setups, prob, res);
+            break;
+          case 1:
+            if (f32) solve_group<cplx, double, cplxf, float>(h, ids, setups, prob, res);
+            else solve_group<cplx, double, cplx, double>(h, ids, setups, prob, res);
+            break;
+          default:
+            if (f32) solve_group<cplx, cplx, cplxf, cplxf>(h, ids, setups, prob, res);
+            else solve_group<cplx, cplx, cplx, cplx>(h, ids, setups, prob, res);
+            break;
         }
         for (int id : ids)
           if (res[id].status != B200MS_OK && first_err == B200MS_OK) {
@@ -308,36 +319,48 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
 }
 
 // ---- benchmark hook -----------------------------------------------------------------------------------
-template <typename T, typename C>
+// mode 0: the fp64 operator apply of the Krylov iteration (true PML);  mode 1: the production smoother sweep
+// (stored-diagonal Jacobi in the multigrid precision, fp32 by default)
+template <typename T, typename C, typename P, typename PC>
 static void bench_group(b200ms_handle *h, const ProblemSetup &s, int nbatch, int mode, int nrep, int flush_l2,
                         const double *x, double *y, double *ms_out, double *bytes_out) {
   std::vector<const ProblemSetup *> ps(nbatch, &s);
-  b200ms_options o = h->opt;
-  BatchSolver<T, C> S(h->arena, h->stream, o);
+  BatchSolver<T, C, P, PC> S(h->arena, h->stream, h->opt);
   S.build(ps, false);
   const size_t len = S.len;
   std::vector<T> hx(len);
+  std::vector<P> hp(len);
   std::mt19937_64 rng(7);
   std::uniform_real_distribution<double> U(-1.0, 1.0);
-  for (size_t e = 0; e < len; ++e) hx[e] = x ? from_cd<T>(cd(x[2 * e], x[2 * e + 1])) : from_cd<T>(cd(U(rng), U(rng)));
+  for (size_t e = 0; e < len; ++e) {
+    cd v = x ? cd(x[2 * e], x[2 * e + 1]) : cd(U(rng), U(rng));
+    hx[e] = from_cd<T>(v);
+    hp[e] = from_cd<P>(v);
+  }
   T *dx = S.basis0(), *dy = S.basis0() + S.vstride, *drhs = S.basis0() + 2 * S.vstride;
+  P *px = reinterpret_cast<P *>(S.basis0() + 3 * S.vstride), *py = px + S.vstride, *prhs = px + 2 * S.vstride;
   for (int b = 0; b < nbatch; ++b) {
     CUDA_CHECK(cudaMemcpyAsync(dx + (size_t)b * len, hx.data(), len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     CUDA_CHECK(cudaMemcpyAsync(drhs + (size_t)b * len, hx.data(), len * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(px + (size_t)b * len, hp.data(), len * sizeof(P), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(prhs + (size_t)b * len, hp.data(), len * sizeof(P), cudaMemcpyHostToDevice, h->stream));
   }
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (flush_l2 && !h->flush_buf) {
     h->flush_bytes = (size_t)256 << 20;
     CUDA_CHECK(cudaMalloc(&h->flush_buf, h->flush_bytes));
   }
-  const int md = mode == 1 ? MODE_JACOBI : MODE_APPLY;
-  for (int w = 0; w < 3; ++w) S.apply(0, md, dx, drhs, dy, true);
+  auto run = [&]() {
+    if (mode == 1) S.apply(0, MODE_JACOBI, px, prhs, py);
+    else S.apply_true(MODE_APPLY, dx, drhs, dy);
+  };
+  for (int w = 0; w < 3; ++w) run();
   double total = 0.0;
   if (flush_l2) {
     for (int r = 0; r < nrep; ++r) {
       CUDA_CHECK(cudaMemsetAsync(h->flush_buf, r & 0xff, h->flush_bytes, h->stream));
       CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-      S.apply(0, md, dx, drhs, dy, true);
+      run();
       CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
       CUDA_CHECK(cudaEventSynchronize(h->ev1));
       float ms = 0.f;
@@ -346,7 +369,7 @@ static void bench_group(b200ms_handle *h, const ProblemSetup &s, int nbatch, int
     }
   } else {
     CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-    for (int r = 0; r < nrep; ++r) S.apply(0, md, dx, drhs, dy, true);
+    for (int r = 0; r < nrep; ++r) run();
     CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
     CUDA_CHECK(cudaEventSynchronize(h->ev1));
     float ms = 0.f;
@@ -355,15 +378,23 @@ static void bench_group(b200ms_handle *h, const ProblemSetup &s, int nbatch, int
   }
   CUDA_CHECK(cudaGetLastError());
   if (ms_out) *ms_out = total / nrep;
-  // algorithmic bytes: per cell read v (2) + write Av (2) [+ rhs (2) for Jacobi] + coefficient fields
+  // algorithmic bytes: apply = read v (2) + write Av (2) + nf coefficient fields per cell;
+  // smoother sweep = read x, rhs, omega/diag (6) + write x' (2) + nf coefficient fields per cell
   const double ncell = (double)S.N * nbatch;
-  const double sv = sizeof(T), sc = sizeof(C);
-  if (bytes_out) *bytes_out = ncell * ((mode == 1 ? 6.0 : 4.0) * sv + (double)S.nf * sc);
+  if (bytes_out)
+    *bytes_out = mode == 1 ? ncell * (8.0 * sizeof(P) + (double)S.nf * sizeof(PC)) : ncell * (4.0 * sizeof(T) + (double)S.nf * sizeof(C));
   if (y) {
-    std::vector<T> hy(len);
-    CUDA_CHECK(cudaMemcpy(hy.data(), dy, len * sizeof(T), cudaMemcpyDeviceToHost));
     for (size_t e = 0; e < len; ++e) {
-      cd v = to_cd(hy[e]);
+      cd v;
+      if (mode == 1) {
+        P t;
+        CUDA_CHECK(cudaMemcpy(&t, py + e, sizeof(P), cudaMemcpyDeviceToHost));
+        v = to_cd(t);
+      } else {
+        T t;
+        CUDA_CHECK(cudaMemcpy(&t, dy + e, sizeof(T), cudaMemcpyDeviceToHost));
+        v = to_cd(t);
+      }
       y[2 * e] = v.real();
       y[2 * e + 1] = v.imag();
     }
@@ -382,10 +413,20 @@ extern "C" int b200ms_bench_stencil(b200ms_handle *h, const b200ms_problem *prob
       h->err = s.error;
       return s.status;
     }
+    const bool f32 = h->opt.mg_precision == 1;
     switch (kind_of(s)) {
-      case 0: bench_group<double, double>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply); break;
-      case 1: bench_group<cplx, double>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply); break;
-      default: bench_group<cplx, cplx>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply); break;
+      case 0:
+        if (f32) bench_group<double, double, float, float>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        else bench_group<double, double, double, double>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        break;
+      case 1:
+        if (f32) bench_group<cplx, double, cplxf, float>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        else bench_group<cplx, double, cplx, double>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        break;
+      default:
+        if (f32) bench_group<cplx, cplx, cplxf, cplxf>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        else bench_group<cplx, cplx, cplx, cplx>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        break;
     }
   } catch (const std::exception &e) {
     h->err = e.what();
@@ -473,12 +514,35 @@ extern "C" int b200ms_debug_hierarchy(const b200ms_problem *prob, const b200ms_o
 
 // ---- device debug hooks -------------------------------------------------------------------------------
 namespace {
-template <typename T, typename C>
+template <typename T, typename C, typename P, typename PC>
 int debug_run(b200ms_handle *h, const ProblemSetup &s, int what, int level, int mode, const double *in0, const double *in1,
               double *out, int *iters, double *relres) {
   std::vector<const ProblemSetup *> ps(1, &s);
-  BatchSolver<T, C> S(h->arena, h->stream, h->opt);
+  BatchSolver<T, C, P, PC> S(h->arena, h->stream, h->opt);
   S.build(ps, false);
+  if (what == 0 && (level > 0 || mode == 3)) {  // multigrid operator of level `level` in preconditioner precision
+    if (level < 0 || level >= (int)S.lv.size()) return B200MS_ERR_ARG;
+    const size_t n2 = 2 * S.lv[level].N;
+    std::vector<P> a(n2), b(n2), o(n2);
+    for (size_t e = 0; e < n2; ++e) {
+      a[e] = from_cd<P>(cd(in0[2 * e], in0[2 * e + 1]));
+      b[e] = in1 ? from_cd<P>(cd(in1[2 * e], in1[2 * e + 1])) : zero_of<P>();
+    }
+    P *d0 = reinterpret_cast<P *>(S.basis0()), *d1 = d0 + S.vstride, *d2 = d0 + 2 * S.vstride;
+    CUDA_CHECK(cudaMemcpy(d0, a.data(), n2 * sizeof(P), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d1, b.data(), n2 * sizeof(P), cudaMemcpyHostToDevice));
+    if (mode == 3) S.jacobi0(level, d1, d2);
+    else S.apply(level, mode, d0, d1, d2);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(o.data(), d2, n2 * sizeof(P), cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < n2; ++e) {
+      cd v = to_cd(o[e]);
+      out[2 * e] = v.real();
+      out[2 * e + 1] = v.imag();
+    }
+    return B200MS_OK;
+  }
   if (level < 0 || level >= (int)S.lv.size()) return B200MS_ERR_ARG;
   const size_t n2 = what == 0 ? 2 * S.lv[level].N : S.len;
   std::vector<T> a(n2), b(n2);
@@ -490,10 +554,9 @@ int debug_run(b200ms_handle *h, const ProblemSetup &s, int what, int level, int 
   CUDA_CHECK(cudaMemcpy(d0, a.data(), n2 * sizeof(T), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(d1, b.data(), n2 * sizeof(T), cudaMemcpyHostToDevice));
   if (what == 0) {
-    if (mode == 3) S.jacobi0(level, d1, d2);
-    else S.apply(level, mode, d0, d1, d2, true);
+    S.apply_true(mode, d0, d1, d2);
   } else if (what == 1) {
-    S.vcycle(0, d0, d2);
+    S.precondition(d0, d2);
   } else {
     int it = 0;
     double rr = S.fgmres(d0, d2, it);
@@ -523,10 +586,17 @@ int debug_dispatch(b200ms_handle *h, const b200ms_problem *prob, int what, int l
       h->err = s.error;
       return s.status;
     }
+    const bool f32 = h->opt.mg_precision == 1;
     switch (kind_of(s)) {
-      case 0: return debug_run<double, double>(h, s, what, level, mode, in0, in1, out, iters, relres);
-      case 1: return debug_run<cplx, double>(h, s, what, level, mode, in0, in1, out, iters, relres);
-      default: return debug_run<cplx, cplx>(h, s, what, level, mode, in0, in1, out, iters, relres);
+      case 0:
+        return f32 ? debug_run<double, double, float, float>(h, s, what, level, mode, in0, in1, out, iters, relres)
+                   : debug_run<double, double, double, double>(h, s, what, level, mode, in0, in1, out, iters, relres);
+      case 1:
+        return f32 ? debug_run<cplx, double, cplxf, float>(h, s, what, level, mode, in0, in1, out, iters, relres)
+                   : debug_run<cplx, double, cplx, double>(h, s, what, level, mode, in0, in1, out, iters, relres);
+      default:
+        return f32 ? debug_run<cplx, cplx, cplxf, cplxf>(h, s, what, level, mode, in0, in1, out, iters, relres)
+                   : debug_run<cplx, cplx, cplx, cplx>(h, s, what, level, mode, in0, in1, out, iters, relres);
     }
   } catch (const std::exception &e) {
     h->err = e.what();

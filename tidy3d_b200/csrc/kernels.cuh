@@ -33,10 +33,48 @@ HD double recip(double a) { return 1.0 / a; }
 HD cplx recip(cplx a) { double d = 1.0 / (a.re * a.re + a.im * a.im); return mk(a.re * d, -a.im * d); }
 HD double abs2(double a) { return a * a; }
 HD double abs2(cplx a) { return a.re * a.re + a.im * a.im; }
+// single-precision twins (multigrid preconditioner in fp32)
+struct __align__(8) cplxf {
+  float re, im;
+};
+HD cplxf mkf(float r, float i) { cplxf c; c.re = r; c.im = i; return c; }
+HD cplxf operator+(cplxf a, cplxf b) { return mkf(a.re + b.re, a.im + b.im); }
+HD cplxf operator-(cplxf a, cplxf b) { return mkf(a.re - b.re, a.im - b.im); }
+HD cplxf operator-(cplxf a) { return mkf(-a.re, -a.im); }
+HD cplxf operator*(cplxf a, cplxf b) { return mkf(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+HD cplxf operator*(float a, cplxf b) { return mkf(a * b.re, a * b.im); }
+HD cplxf operator*(cplxf a, float b) { return mkf(a.re * b, a.im * b); }
+HD cplxf operator*(double a, cplxf b) { return mkf((float)a * b.re, (float)a * b.im); }
+HD cplxf &operator+=(cplxf &a, cplxf b) { a.re += b.re; a.im += b.im; return a; }
+HD cplxf &operator-=(cplxf &a, cplxf b) { a.re -= b.re; a.im -= b.im; return a; }
+HD float cj(float a) { return a; }
+HD cplxf cj(cplxf a) { return mkf(a.re, -a.im); }
+HD float recip(float a) { return 1.0f / a; }
+HD cplxf recip(cplxf a) { float d = 1.0f / (a.re * a.re + a.im * a.im); return mkf(a.re * d, -a.im * d); }
+HD double abs2(float a) { return (double)a * a; }
+HD double abs2(cplxf a) { return (double)a.re * a.re + (double)a.im * a.im; }
+HD double real_part(double a) { return a; }
+HD double real_part(cplx a) { return a.re; }
+HD double real_part(float a) { return a; }
+HD double real_part(cplxf a) { return a.re; }
+// precision conversion between the Krylov (fp64) and multigrid (fp32) vector types
+HD void convert(double s, double &d) { d = s; }
+HD void convert(double s, float &d) { d = (float)s; }
+HD void convert(float s, double &d) { d = s; }
+HD void convert(float s, float &d) { d = s; }
+HD void convert(cplx s, cplx &d) { d = s; }
+HD void convert(cplx s, cplxf &d) { d = mkf((float)s.re, (float)s.im); }
+HD void convert(cplxf s, cplx &d) { d = mk(s.re, s.im); }
+HD void convert(cplxf s, cplxf &d) { d = s; }
+
 template <typename T> HD T zero_of();
+template <> HD float zero_of<float>() { return 0.0f; }
+template <> HD cplxf zero_of<cplxf>() { return mkf(0.0f, 0.0f); }
 template <> HD double zero_of<double>() { return 0.0; }
 template <> HD cplx zero_of<cplx>() { return mk(0.0, 0.0); }
 template <typename T> HD T from_real(double r);
+template <> HD float from_real<float>(double r) { return (float)r; }
+template <> HD cplxf from_real<cplxf>(double r) { return mkf((float)r, 0.0f); }
 template <> HD double from_real<double>(double r) { return r; }
 template <> HD cplx from_real<cplx>(double r) { return mk(r, 0.0); }
 // conversions between storage types (real <- complex drops the imaginary part)
@@ -53,10 +91,49 @@ template <> __device__ __forceinline__ cplx ldg<cplx>(const cplx *p) {
   return mk(v.x, v.y);
 }
 
+template <> __device__ __forceinline__ float ldg<float>(const float *p) { return __ldg(p); }
+template <> __device__ __forceinline__ cplxf ldg<cplxf>(const cplxf *p) {
+  float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+  return mkf(v.x, v.y);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ cplx warp_sum(cplx v) { return mk(warp_sum(v.re), warp_sum(v.im)); }
+__device__ __forceinline__ cplxf warp_sum(cplxf v) { return mkf(warp_sum(v.re), warp_sum(v.im)); }
+
+// y = a .* b element-wise;  fill
+template <typename T>
+__global__ void __launch_bounds__(256) mul_kernel(size_t total, const T *a, const T *b, T *y) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) y[e] = ldg(a + e) * ldg(b + e);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) fill_kernel(size_t total, T v, T *y) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) y[e] = v;
+}
+
+// dst = (D) src, element-wise over a batched vector
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) convert_kernel(size_t total, const S *src, D *dst) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) {
+    D d;
+    convert(src[e], d);
+    dst[e] = d;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused curl-curl stencil
 // ------------------------------------------------------------------------------------------------
-enum { MODE_APPLY = 0, MODE_RESID = 1, MODE_JACOBI = 2 };
+enum { MODE_APPLY = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_JACOBI_D = 3 };  // _D: stored omega/diag
 
 template <typename T, typename C>
 struct StencilArgs {
@@ -70,11 +147,14 @@ struct StencilArgs {
   const T *cy;       // [B][4][ny]
   const T *sigma;    // [B]
   double omega;      // Jacobi damping
+  const T *dinv;     // [B][2][N] omega / diag(A - sigma) (MODE_JACOBI_D)
 };
 
 template <typename T> struct Tile;
 template <> struct Tile<double> { static constexpr int TX = 8, TY = 64; };
 template <> struct Tile<cplx> { static constexpr int TX = 8, TY = 32; };
+template <> struct Tile<float> { static constexpr int TX = 8, TY = 64; };
+template <> struct Tile<cplxf> { static constexpr int TX = 8, TY = 64; };
 
 // y = (A - sigma) x                       MODE_APPLY
 // y = rhs - (A - sigma) x                 MODE_RESID
@@ -302,7 +382,7 @@ __global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T
   C ie1 = C(), ie0 = C(), im1 = C(), im0 = C(), imm = C(), mx1 = C(), my1 = C(), mx0 = C(), my0 = C();
   C ex1 = C(), ey1 = C(), ex0 = C(), ey0 = C();
   T u0 = zT, t0 = zT, tm = zT;
-  T nr1 = zT, nr2 = zT;
+  T nr1 = zT, nr2 = zT, nd1 = zT, nd2 = zT;
 
   auto load_row = [&](int gi) {
     pv1 = zT; pv2 = zT; pex = C(); pey = C(); pie = C();
@@ -325,12 +405,16 @@ __global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T
     const T a2 = pex * pv1, b2 = pey * pv2;
     const C ie2 = pie, im2 = pim, mx2 = pmx, my2 = pmy, ex2 = pex, ey2 = pey;
     load_row(k + 3);
-    T cr1 = nr1, cr2 = nr2;
+    T cr1 = nr1, cr2 = nr2, cd1 = nd1, cd2 = nd2;
     if (MODE != MODE_APPLY) {
       nr1 = zT; nr2 = zT;
       if (outc && k + 1 >= i0 && k + 1 < iend) {
         const size_t g = (size_t)(k + 1) * ny + gj;
         nr1 = ldg(r1 + g); nr2 = ldg(r1 + N + g);
+        if (MODE == MODE_JACOBI_D) {
+          const T *dv = a.dinv + (size_t)b * 2 * N;
+          nd1 = ldg(dv + g); nd2 = ldg(dv + N + g);
+        }
       }
     }
     // step 1
@@ -361,6 +445,8 @@ __global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T
         y1[g] = o1; y2[g] = o2;
       } else if (MODE == MODE_RESID) {
         y1[g] = cr1 - o1; y2[g] = cr2 - o2;
+      } else if (MODE == MODE_JACOBI_D) {
+        y1[g] = v10 + cd1 * (cr1 - o1); y2[g] = v20 + cd2 * (cr2 - o2);
       } else {
         const T xbm_n = sX[3][xr + 1], xf1_p = sX[1][xr - 1 >= 0 ? xr - 1 : 0];
         const C ier = sIe[sp][c + 2];
@@ -547,19 +633,7 @@ __global__ void __launch_bounds__(256) multidot_partial_kernel(const T *V, size_
     }
 #pragma unroll
     for (int k = 0; k < kDotGroup; ++k) {
-      T v = acc[k];
-      if constexpr (sizeof(T) == 8) {
-        double d = *reinterpret_cast<double *>(&v);
-        for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
-        *reinterpret_cast<double *>(&v) = d;
-      } else {
-        cplx cv = *reinterpret_cast<cplx *>(&v);
-        for (int o = 16; o > 0; o >>= 1) {
-          cv.re += __shfl_down_sync(0xffffffffu, cv.re, o);
-          cv.im += __shfl_down_sync(0xffffffffu, cv.im, o);
-        }
-        *reinterpret_cast<cplx *>(&v) = cv;
-      }
+      T v = warp_sum(acc[k]);
       if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
     }
     __syncthreads();
@@ -637,8 +711,8 @@ __global__ void __launch_bounds__(256) scale_kernel(const T *x, T *y, size_t len
   const int b = blockIdx.y;
   T al = alpha[(size_t)b * astride];
   if (inv_sqrt) {
-    double n2 = *reinterpret_cast<double *>(&al);
-    al = from_real<T>(n2 > 1e-280 ? rsqrt(n2) : 0.0);
+    const double n2 = real_part(al);
+    al = from_real<T>(n2 > 1e-60 ? rsqrt(n2) : 0.0);
   }
   const size_t stride = (size_t)gridDim.x * 256;
   for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < len; e += stride)
@@ -669,7 +743,7 @@ __global__ void pythagoras_kernel(const T *h, int hstride, int nv, T *out, int o
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const T ww = h[(size_t)b * hstride + nv];
-  double acc = *reinterpret_cast<const double *>(&ww);
+  double acc = real_part(ww);
   for (int i = 0; i < nv; ++i) acc -= abs2(h[(size_t)b * hstride + i]);
   out[(size_t)b * ostride] = from_real<T>(acc > 0.0 ? acc : 0.0);
 }
@@ -687,13 +761,13 @@ __global__ void gmres_lsq_kernel(T *H, int kc, int ld, const T *beta2, int bstri
   // g is kept in the unused tail of y? no: use the last column slot of each H column (index ld-1)
   // g[i] lives at Hb[i*ld + ld-1] for i < kc, and g[kc] in a register.
   T b2 = beta2[(size_t)b * bstride];
-  double beta = sqrt(fmax(0.0, *reinterpret_cast<double *>(&b2)));
+  double beta = sqrt(fmax(0.0, real_part(b2)));
   T gnext = from_real<T>(beta);
   for (int j = 0; j < kc; ++j) {
     T *col = Hb + (size_t)j * ld;
     // sub-diagonal entry: sqrt of the stored squared norm
     T n2 = col[j + 1];
-    double sub = sqrt(fmax(0.0, *reinterpret_cast<double *>(&n2)));
+    double sub = sqrt(fmax(0.0, real_part(n2)));
     // apply previous rotations (stored in columns' slots ld-3 (c) and ld-2 (s))
     for (int i = 0; i < j; ++i) {
       const T c = Hb[(size_t)i * ld + ld - 3], sn = Hb[(size_t)i * ld + ld - 2];
@@ -720,7 +794,7 @@ __global__ void gmres_lsq_kernel(T *H, int kc, int ld, const T *beta2, int bstri
     T acc = Hb[(size_t)i * ld + ld - 1];
     for (int j = i + 1; j < kc; ++j) acc -= Hb[(size_t)j * ld + i] * yb[j];
     const T rii = Hb[(size_t)i * ld + i];
-    yb[i] = abs2(rii) > 1e-280 ? recip(rii) * acc : zero_of<T>();
+    yb[i] = abs2(rii) > 1e-60 ? recip(rii) * acc : zero_of<T>();
   }
 }
 

@@ -74,23 +74,32 @@ template <> inline cd to_cd<cplx>(cplx v) { return cd(v.re, v.im); }
 template <typename T> inline T from_cd(cd v);
 template <> inline double from_cd<double>(cd v) { return v.real(); }
 template <> inline cplx from_cd<cplx>(cd v) { return mk(v.real(), v.imag()); }
+template <> inline float from_cd<float>(cd v) { return (float)v.real(); }
+template <> inline cplxf from_cd<cplxf>(cd v) { return mkf((float)v.real(), (float)v.imag()); }
+template <> inline cd to_cd<float>(float v) { return cd(v, 0.0); }
+template <> inline cd to_cd<cplxf>(cplxf v) { return cd(v.re, v.im); }
 
 struct TransferDevStore {
   Transfer1DDev d;
 };
 
 // ------------------------------------------------------------------------------------------------------
-template <typename T, typename C>
+// T / C: Krylov vector and coefficient-field types (fp64).  P / PC: the same for the multigrid preconditioner,
+// either identical (all fp64) or their fp32 twins (mixed precision: the V-cycle moves half the bytes).
+template <typename T, typename C, typename P = T, typename PC = C>
 class BatchSolver {
  public:
+  static constexpr bool kMixed = !std::is_same<T, P>::value;
   struct Level {
     int nx = 0, ny = 0;
     size_t N = 0;
-    C *fields = nullptr;
+    PC *fields = nullptr;
+    C *fields_true = nullptr;  // level 0 only (aliases `fields` when PC == C)
     size_t fbstride = 0;
-    T *cx = nullptr, *cy = nullptr;          // multigrid (phase-limited PML) coefficients
+    P *cx = nullptr, *cy = nullptr;          // multigrid (phase-limited PML) coefficients
     T *cx_true = nullptr, *cy_true = nullptr;  // level 0 only: the reference operator
-    T *x = nullptr, *b = nullptr, *r = nullptr, *tmp = nullptr;
+    P *x = nullptr, *b = nullptr, *r = nullptr, *tmp = nullptr;
+    P *dinv = nullptr;  // omega / diag(A_l - sigma), [B][2][N]
     TransferArgs tr;  // to the next coarser level
   };
 
@@ -145,10 +154,10 @@ class BatchSolver {
     const size_t fB = shared_fields ? 1 : B;
     for (int l = 0; l < L; ++l) {
       size_t Nl = (size_t)plan_.nx[l] * plan_.ny[l];
-      sz.add<C>(fB * nf * Nl);
+      sz.add<C>(fB * nf * Nl * (l == 0 && kMixed ? 2 : 1));
       sz.add<T>((size_t)B * 4 * plan_.nx[l] * (l == 0 ? 2 : 1));
       sz.add<T>((size_t)B * 4 * plan_.ny[l] * (l == 0 ? 2 : 1));
-      for (int q = 0; q < 4; ++q) sz.add<T>((size_t)B * 2 * Nl);
+      for (int q = 0; q < 5; ++q) sz.add<T>((size_t)B * 2 * Nl);
       if (l + 1 < L) {
         size_t ints = 0, dbls = 0;
         transfer_sizes(plan_.trx[l], ints, dbls);
@@ -165,7 +174,7 @@ class BatchSolver {
     sz.add<T>((size_t)B * kDotChunks * pstride());
     sz.add<T>((size_t)B * hstride());
     sz.add<T>((size_t)B * (m + 1) * (m + 1));
-    sz.add<T>((size_t)B * 4);
+    sz.add<T>((size_t)B * 8);
     sz.add<cplx>((size_t)B * k);
     sz.add<cplx>((size_t)B * 6 * N * k);
     sz.add<double>((size_t)B * 2 * std::max(nx, ny) + 64);
@@ -194,21 +203,26 @@ class BatchSolver {
       v.ny = plan_.ny[l];
       v.N = (size_t)v.nx * v.ny;
       v.fbstride = shared_fields ? 0 : nf * v.N;
-      v.fields = arena_.get<C>(fB * nf * v.N);
-      v.cx = arena_.get<T>((size_t)B * 4 * v.nx);
-      v.cy = arena_.get<T>((size_t)B * 4 * v.ny);
+      v.fields = arena_.get<PC>(fB * nf * v.N);
+      if (l == 0) {
+        if constexpr (kMixed) v.fields_true = arena_.get<C>(fB * nf * v.N);
+        else v.fields_true = reinterpret_cast<C *>(v.fields);
+      }
+      v.cx = arena_.get<P>((size_t)B * 4 * v.nx);
+      v.cy = arena_.get<P>((size_t)B * 4 * v.ny);
       if (l == 0) {
         v.cx_true = arena_.get<T>((size_t)B * 4 * v.nx);
         v.cy_true = arena_.get<T>((size_t)B * 4 * v.ny);
       }
-      v.x = arena_.get<T>((size_t)B * 2 * v.N);
-      v.b = arena_.get<T>((size_t)B * 2 * v.N);
-      v.r = arena_.get<T>((size_t)B * 2 * v.N);
-      v.tmp = arena_.get<T>((size_t)B * 2 * v.N);
+      v.x = arena_.get<P>((size_t)B * 2 * v.N);
+      v.b = arena_.get<P>((size_t)B * 2 * v.N);
+      v.r = arena_.get<P>((size_t)B * 2 * v.N);
+      v.tmp = arena_.get<P>((size_t)B * 2 * v.N);
+      v.dinv = arena_.get<P>((size_t)B * 2 * v.N);
     }
     // 1-D coefficients for every problem and level
     for (int l = 0; l < L; ++l) {
-      std::vector<T> hx((size_t)B * 4 * lv[l].nx), hy((size_t)B * 4 * lv[l].ny);
+      std::vector<P> hx((size_t)B * 4 * lv[l].nx), hy((size_t)B * 4 * lv[l].ny);
       std::vector<T> hxt, hyt;
       if (l == 0) {
         hxt.resize(hx.size());
@@ -240,12 +254,12 @@ class BatchSolver {
         }
         std::vector<cd> c;
         axes_b[b][0].coefficients(c);
-        for (size_t i = 0; i < c.size(); ++i) hx[(size_t)b * 4 * lv[l].nx + i] = from_cd<T>(c[i]);
+        for (size_t i = 0; i < c.size(); ++i) hx[(size_t)b * 4 * lv[l].nx + i] = from_cd<P>(c[i]);
         axes_b[b][1].coefficients(c);
-        for (size_t i = 0; i < c.size(); ++i) hy[(size_t)b * 4 * lv[l].ny + i] = from_cd<T>(c[i]);
+        for (size_t i = 0; i < c.size(); ++i) hy[(size_t)b * 4 * lv[l].ny + i] = from_cd<P>(c[i]);
       }
-      CUDA_CHECK(cudaMemcpyAsync(lv[l].cx, hx.data(), hx.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
-      CUDA_CHECK(cudaMemcpyAsync(lv[l].cy, hy.data(), hy.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaMemcpyAsync(lv[l].cx, hx.data(), hx.size() * sizeof(P), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaMemcpyAsync(lv[l].cy, hy.data(), hy.size() * sizeof(P), cudaMemcpyHostToDevice, st_));
       if (l == 0) {
         CUDA_CHECK(cudaMemcpyAsync(lv[0].cx_true, hxt.data(), hxt.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
         CUDA_CHECK(cudaMemcpyAsync(lv[0].cy_true, hyt.data(), hyt.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
@@ -264,7 +278,11 @@ class BatchSolver {
           for (size_t i = 0; i < N; ++i) dst[i] = from_cd<C>(inv ? 1.0 / src[i] : src[i]);
         }
       }
-      CUDA_CHECK(cudaMemcpyAsync(lv[0].fields, hf.data(), hf.size() * sizeof(C), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaMemcpyAsync(lv[0].fields_true, hf.data(), hf.size() * sizeof(C), cudaMemcpyHostToDevice, st_));
+      if constexpr (kMixed) {
+        const size_t tot = hf.size();
+        convert_kernel<C, PC><<<(unsigned)std::min<size_t>((tot + 255) / 256, 4096), 256, 0, st_>>>(tot, lv[0].fields_true, lv[0].fields);
+      }
       CUDA_CHECK(cudaStreamSynchronize(st_));
     }
     // transfer lists + coarse fields
@@ -286,7 +304,7 @@ class BatchSolver {
       dim3 blk(64, 4), grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, (unsigned)fB);
       for (int q = 0; q < nf; ++q) {
         const bool inv = (q == 2 || q == 5);
-        restrict_field_kernel<C><<<grd, blk, 0, st_>>>(t.nxf, t.nyf, t.nxc, t.nyc, *fx[q], *fy[q],
+        restrict_field_kernel<PC><<<grd, blk, 0, st_>>>(t.nxf, t.nyf, t.nxc, t.nyc, *fx[q], *fy[q],
                                                        lv[l].fields + (size_t)q * lv[l].N, shared_fields ? 0 : nf * lv[l].N,
                                                        lv[l + 1].fields + (size_t)q * lv[l + 1].N,
                                                        shared_fields ? 0 : nf * lv[l + 1].N, inv ? 1 : 0);
@@ -304,92 +322,137 @@ class BatchSolver {
     hbuf_ = arena_.get<T>((size_t)B * hstride());
     qbuf_ = arena_.get<T>((size_t)B * (m + 1) * (m + 1));
     sigma_ = arena_.get<T>((size_t)B * 4);
+    sigma_p_ = arena_.get<P>((size_t)B * 4);
     ncomplex_ = arena_.get<cplx>((size_t)B * k);
     fields_out_ = arena_.get<cplx>((size_t)B * 6 * N * k);
     jz_ = arena_.get<double>((size_t)B * 2 * std::max(nx, ny) + 64);
     if (coarse_krylov_) {
       const size_t NL = lv[L - 1].N;
-      cV_ = arena_.get<T>((size_t)(kc_ + 1) * B * 2 * NL);
-      cZ_ = arena_.get<T>((size_t)kc_ * B * 2 * NL);
-      cH_ = arena_.get<T>((size_t)B * kc_ * (kc_ + 4));
-      cH2_ = arena_.get<T>((size_t)B * (kc_ + 1));
-      cy_ = arena_.get<T>((size_t)B * kc_);
-      cbeta_ = arena_.get<T>((size_t)B + 8);
-      cone_ = arena_.get<T>(8);
-      T one = from_real<T>(1.0);
-      CUDA_CHECK(cudaMemcpyAsync(cone_, &one, sizeof(T), cudaMemcpyHostToDevice, st_));
+      cV_ = arena_.get<P>((size_t)(kc_ + 1) * B * 2 * NL);
+      cZ_ = arena_.get<P>((size_t)kc_ * B * 2 * NL);
+      cH_ = arena_.get<P>((size_t)B * kc_ * (kc_ + 4));
+      cH2_ = arena_.get<P>((size_t)B * (kc_ + 1));
+      cy_ = arena_.get<P>((size_t)B * kc_);
+      cbeta_ = arena_.get<P>((size_t)B + 8);
+      cone_ = arena_.get<P>(8);
+      P one = from_real<P>(1.0);
+      CUDA_CHECK(cudaMemcpyAsync(cone_, &one, sizeof(P), cudaMemcpyHostToDevice, st_));
       CUDA_CHECK(cudaStreamSynchronize(st_));
     }
     hhost_.resize((size_t)B * hstride());
     sig_host_.resize(B);
     for (int b = 0; b < B; ++b) sig_host_[b] = ps[b]->sigma;
     set_sigma(sig_host_);
+    // omega / diag(A_l - sigma) on every level: one recomputed-diagonal sweep applied to a vector of ones
+    dinv_ready_ = false;
+    for (int l = 0; l < L; ++l) {
+      const size_t tot = (size_t)B * 2 * lv[l].N;
+      fill_kernel<P><<<(unsigned)std::min<size_t>((tot + 255) / 256, 8192), 256, 0, st_>>>(tot, from_real<P>(1.0), lv[l].tmp);
+      jacobi0(l, lv[l].tmp, lv[l].dinv);
+    }
+    dinv_ready_ = true;
     CUDA_CHECK(cudaStreamSynchronize(st_));
+    CUDA_CHECK(cudaGetLastError());
   }
 
   void set_sigma(const std::vector<cd> &s) {
     std::vector<T> h(B);
     for (int b = 0; b < B; ++b) h[b] = from_cd<T>(s[b]);
+    std::vector<P> hp(B);
+    for (int b = 0; b < B; ++b) hp[b] = from_cd<P>(s[b]);
     CUDA_CHECK(cudaMemcpyAsync(sigma_, h.data(), B * sizeof(T), cudaMemcpyHostToDevice, st_));
+    CUDA_CHECK(cudaMemcpyAsync(sigma_p_, hp.data(), B * sizeof(P), cudaMemcpyHostToDevice, st_));
     CUDA_CHECK(cudaStreamSynchronize(st_));
   }
 
   // -- operator ------------------------------------------------------------------------------------
-  void apply(int l, int mode, const T *x, const T *rhs, T *y, bool true_op = false) {
-    Level &v = lv[l];
-    StencilArgs<T, C> a;
+  template <typename TT, typename CC>
+  void launch_stencil(const Level &v, int mode, const TT *x, const TT *rhs, TT *y, const CC *fields, const TT *cx, const TT *cy,
+                      const TT *sigma, const TT *dinv = nullptr) {
+    StencilArgs<TT, CC> a;
     a.nx = v.nx; a.ny = v.ny; a.x = x; a.rhs = rhs; a.y = y;
-    a.fields = v.fields; a.field_bstride = v.fbstride; a.sigma = sigma_;
-    a.cx = (true_op && l == 0) ? v.cx_true : v.cx;
-    a.cy = (true_op && l == 0) ? v.cy_true : v.cy;
-    stats.launches++;
+    a.fields = fields; a.field_bstride = v.fbstride; a.sigma = sigma; a.cx = cx; a.cy = cy;
     a.omega = opt_.mg_omega;
-    if (l == 0) stats.stencil_applies++;
+    a.dinv = dinv;
+    stats.launches++;
     if (opt_.stencil_variant != 1 && v.nx >= 32 && v.ny >= 2) {
       constexpr int TXR = 32;
       dim3 blk(kMarchCols), grd((v.ny + kMarchOut - 1) / kMarchOut, (v.nx + TXR - 1) / TXR, B);
+      if (mode == MODE_JACOBI && dinv) {  // stored-diagonal sweep: fewer registers and instructions than recomputing it
+        if (has_mu) stencil_march_kernel<TT, CC, MODE_JACOBI_D, true, TXR><<<grd, blk, 0, st_>>>(a);
+        else stencil_march_kernel<TT, CC, MODE_JACOBI_D, false, TXR><<<grd, blk, 0, st_>>>(a);
+        return;
+      }
       if (has_mu) {
-        if (mode == MODE_APPLY) stencil_march_kernel<T, C, MODE_APPLY, true, TXR><<<grd, blk, 0, st_>>>(a);
-        else if (mode == MODE_RESID) stencil_march_kernel<T, C, MODE_RESID, true, TXR><<<grd, blk, 0, st_>>>(a);
-        else stencil_march_kernel<T, C, MODE_JACOBI, true, TXR><<<grd, blk, 0, st_>>>(a);
+        if (mode == MODE_APPLY) stencil_march_kernel<TT, CC, MODE_APPLY, true, TXR><<<grd, blk, 0, st_>>>(a);
+        else if (mode == MODE_RESID) stencil_march_kernel<TT, CC, MODE_RESID, true, TXR><<<grd, blk, 0, st_>>>(a);
+        else stencil_march_kernel<TT, CC, MODE_JACOBI, true, TXR><<<grd, blk, 0, st_>>>(a);
       } else {
-        if (mode == MODE_APPLY) stencil_march_kernel<T, C, MODE_APPLY, false, TXR><<<grd, blk, 0, st_>>>(a);
-        else if (mode == MODE_RESID) stencil_march_kernel<T, C, MODE_RESID, false, TXR><<<grd, blk, 0, st_>>>(a);
-        else stencil_march_kernel<T, C, MODE_JACOBI, false, TXR><<<grd, blk, 0, st_>>>(a);
+        if (mode == MODE_APPLY) stencil_march_kernel<TT, CC, MODE_APPLY, false, TXR><<<grd, blk, 0, st_>>>(a);
+        else if (mode == MODE_RESID) stencil_march_kernel<TT, CC, MODE_RESID, false, TXR><<<grd, blk, 0, st_>>>(a);
+        else stencil_march_kernel<TT, CC, MODE_JACOBI, false, TXR><<<grd, blk, 0, st_>>>(a);
       }
       return;
     }
-    constexpr int TX = Tile<T>::TX, TY = Tile<T>::TY;
+    constexpr int TX = Tile<TT>::TX, TY = Tile<TT>::TY;
     dim3 blk(TY, 256 / TY), grd((v.ny + TY - 1) / TY, (v.nx + TX - 1) / TX, B);
     if (has_mu) {
-      if (mode == MODE_APPLY) stencil_kernel<T, C, MODE_APPLY, true><<<grd, blk, 0, st_>>>(a);
-      else if (mode == MODE_RESID) stencil_kernel<T, C, MODE_RESID, true><<<grd, blk, 0, st_>>>(a);
-      else stencil_kernel<T, C, MODE_JACOBI, true><<<grd, blk, 0, st_>>>(a);
+      if (mode == MODE_APPLY) stencil_kernel<TT, CC, MODE_APPLY, true><<<grd, blk, 0, st_>>>(a);
+      else if (mode == MODE_RESID) stencil_kernel<TT, CC, MODE_RESID, true><<<grd, blk, 0, st_>>>(a);
+      else stencil_kernel<TT, CC, MODE_JACOBI, true><<<grd, blk, 0, st_>>>(a);
     } else {
-      if (mode == MODE_APPLY) stencil_kernel<T, C, MODE_APPLY, false><<<grd, blk, 0, st_>>>(a);
-      else if (mode == MODE_RESID) stencil_kernel<T, C, MODE_RESID, false><<<grd, blk, 0, st_>>>(a);
-      else stencil_kernel<T, C, MODE_JACOBI, false><<<grd, blk, 0, st_>>>(a);
+      if (mode == MODE_APPLY) stencil_kernel<TT, CC, MODE_APPLY, false><<<grd, blk, 0, st_>>>(a);
+      else if (mode == MODE_RESID) stencil_kernel<TT, CC, MODE_RESID, false><<<grd, blk, 0, st_>>>(a);
+      else stencil_kernel<TT, CC, MODE_JACOBI, false><<<grd, blk, 0, st_>>>(a);
     }
   }
-  void jacobi0(int l, const T *rhs, T *y) {
+  // the reference operator (fp64, true PML) on the fine level
+  void apply_true(int mode, const T *x, const T *rhs, T *y) {
+    stats.stencil_applies++;
+    launch_stencil<T, C>(lv[0], mode, x, rhs, y, lv[0].fields_true, lv[0].cx_true, lv[0].cy_true, sigma_);
+  }
+  // the multigrid operator on level l (preconditioner precision, phase-limited PML)
+  void apply(int l, int mode, const P *x, const P *rhs, P *y) {
+    if (l == 0) stats.stencil_applies++;
+    launch_stencil<P, PC>(lv[l], mode, x, rhs, y, lv[l].fields, lv[l].cx, lv[l].cy, sigma_p_, dinv_ready_ ? lv[l].dinv : nullptr);
+  }
+  void jacobi0(int l, const P *rhs, P *y) {
     Level &v = lv[l];
-    StencilArgs<T, C> a;
+    if (dinv_ready_) {
+      const size_t tot = (size_t)B * 2 * v.N;
+      mul_kernel<P><<<(unsigned)std::min<size_t>((tot + 255) / 256, 8192), 256, 0, st_>>>(tot, v.dinv, rhs, y);
+      stats.launches++;
+      return;
+    }
+    StencilArgs<P, PC> a;
     a.nx = v.nx; a.ny = v.ny; a.x = nullptr; a.rhs = rhs; a.y = y;
-    a.fields = v.fields; a.field_bstride = v.fbstride; a.cx = v.cx; a.cy = v.cy; a.sigma = sigma_;
+    a.fields = v.fields; a.field_bstride = v.fbstride; a.cx = v.cx; a.cy = v.cy; a.sigma = sigma_p_;
     a.omega = opt_.mg_omega;
     stats.launches++;
     dim3 blk(64, 4), grd((v.ny + 63) / 64, (v.nx + 3) / 4, B);
-    if (has_mu) jacobi0_kernel<T, C, true><<<grd, blk, 0, st_>>>(a);
-    else jacobi0_kernel<T, C, false><<<grd, blk, 0, st_>>>(a);
+    if (has_mu) jacobi0_kernel<P, PC, true><<<grd, blk, 0, st_>>>(a);
+    else jacobi0_kernel<P, PC, false><<<grd, blk, 0, st_>>>(a);
+  }
+  // z = M^-1 v for Krylov-precision vectors: one V-cycle, converting on the way in and out when mixed
+  void precondition(const T *v, T *z) {
+    if constexpr (!kMixed) {
+      vcycle(0, v, z);
+    } else {
+      const unsigned nb = (unsigned)std::min<size_t>((vstride + 255) / 256, 8192);
+      convert_kernel<T, P><<<nb, 256, 0, st_>>>(vstride, v, lv[0].b);
+      vcycle(0, lv[0].b, nullptr);
+      convert_kernel<P, T><<<nb, 256, 0, st_>>>(vstride, lv[0].x, z);
+      stats.launches += 2;
+    }
   }
 
   // -- multigrid V-cycle: z = M^-1 rin on level l.  Result lands in `out` (or lv[l].x if null). ----
-  void vcycle(int l, const T *rin, T *out) {
+  void vcycle(int l, const P *rin, P *out) {
     Level &v = lv[l];
     const int L = (int)lv.size();
     const int nu = std::max(1, opt_.mg_nu);
-    T *cur = v.x, *oth = v.tmp;
-    auto sweep = [&](T *dst) {  // dst = jacobi(cur)
+    P *cur = v.x, *oth = v.tmp;
+    auto sweep = [&](P *dst) {  // dst = jacobi(cur)
       apply(l, MODE_JACOBI, cur, rin, dst);
     };
     if (l == L - 1 && coarse_krylov_) {
@@ -400,7 +463,7 @@ class BatchSolver {
       const int n_sw = std::max(2, opt_.mg_coarse_iters);
       jacobi0(l, rin, cur);
       for (int s = 1; s < n_sw; ++s) {
-        T *dst = (s == n_sw - 1 && out) ? out : oth;
+        P *dst = (s == n_sw - 1 && out) ? out : oth;
         sweep(dst);
         if (dst != out) std::swap(cur, oth);
       }
@@ -416,17 +479,17 @@ class BatchSolver {
     {
       const TransferArgs &t = v.tr;
       dim3 blk(64, 4), grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, 2 * B);
-      restrict_kernel<T><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+      restrict_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
       stats.launches += 2;
     }
     vcycle(l + 1, lv[l + 1].b, nullptr);
     {
       const TransferArgs &t = v.tr;
       dim3 blk(64, 4), grd((t.nyf + 63) / 64, (t.nxf + 3) / 4, 2 * B);
-      prolong_add_kernel<T><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
+      prolong_add_kernel<P><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
     }
     for (int s = 0; s < nu; ++s) {
-      T *dst = (s == nu - 1 && out) ? out : oth;
+      P *dst = (s == nu - 1 && out) ? out : oth;
       sweep(dst);
       if (dst != out) std::swap(cur, oth);
     }
@@ -435,29 +498,29 @@ class BatchSolver {
 
   // -- coarsest-level Krylov solve (indefinite shifts): GMRES(kc), Jacobi right-preconditioned, CGS2, run entirely
   //    on the device (no host synchronisation; the small least-squares problem is solved by one thread per problem)
-  void coarse_gmres(int l, const T *rin, T *xout) {
+  void coarse_gmres(int l, const P *rin, P *xout) {
     Level &v = lv[l];
     const int kc = kc_;
     const size_t ln = 2 * v.N, vs = (size_t)B * ln;
     const int ld = kc + 4;
-    CUDA_CHECK(cudaMemsetAsync(cH_, 0, (size_t)B * kc * ld * sizeof(T), st_));
+    CUDA_CHECK(cudaMemsetAsync(cH_, 0, (size_t)B * kc * ld * sizeof(P), st_));
     dots(rin, 1, rin, cbeta_, 1, 0, false, ln, vs);
     scale_inv_norm(rin, cV_, cbeta_, 1, ln);
     for (int j = 0; j < kc; ++j) {
-      T *vj = cV_ + (size_t)j * vs, *zj = cZ_ + (size_t)j * vs, *w = cV_ + (size_t)(j + 1) * vs;
+      P *vj = cV_ + (size_t)j * vs, *zj = cZ_ + (size_t)j * vs, *w = cV_ + (size_t)(j + 1) * vs;
       jacobi0(l, vj, zj);
       apply(l, MODE_APPLY, zj, nullptr, w);
-      T *col = cH_ + (size_t)j * ld;  // problem stride kc*ld
+      P *col = cH_ + (size_t)j * ld;  // problem stride kc*ld
       dots(cV_, j + 1, w, col, kc * ld, 0, false, ln, vs);
       axpys(cV_, j + 1, col, kc * ld, -1.0, w, ln, vs);
       dots(cV_, j + 1, w, cH2_, kc + 1, 0, false, ln, vs);
       axpys(cV_, j + 1, cH2_, kc + 1, -1.0, w, ln, vs);
-      add_small_kernel<T><<<B, 64, 0, st_>>>(col, kc * ld, cH2_, kc + 1, j + 1);  // H[:, j] += second-pass coefficients
+      add_small_kernel<P><<<B, 64, 0, st_>>>(col, kc * ld, cH2_, kc + 1, j + 1);  // H[:, j] += second-pass coefficients
       dots(w, 1, w, col, kc * ld, j + 1, false, ln, vs);
       scale_inv_norm(w, w, col + j + 1, kc * ld, ln);
     }
-    gmres_lsq_kernel<T><<<(B + 31) / 32, 32, 0, st_>>>(cH_, kc, ld, cbeta_, 1, cy_, B);
-    CUDA_CHECK(cudaMemsetAsync(xout, 0, vs * sizeof(T), st_));
+    gmres_lsq_kernel<P><<<(B + 31) / 32, 32, 0, st_>>>(cH_, kc, ld, cbeta_, 1, cy_, B);
+    CUDA_CHECK(cudaMemsetAsync(xout, 0, vs * sizeof(P), st_));
     axpys(cZ_, kc, cy_, kc, +1.0, xout, ln, vs);
   }
 
@@ -467,26 +530,30 @@ class BatchSolver {
   int vec_blocks() const { return (int)std::min<size_t>((len + 255) / 256, 1024); }
 
   // dst[b][off + i] (+)= <V_i, w>, i < nv   (vectors of length ln, basis stride vs)
-  void dots(const T *V, int nv, const T *w, T *dst, int dstride, int off, bool accumulate, size_t ln = 0, size_t vs = 0) {
+  template <typename U>
+  void dots(const U *V, int nv, const U *w, U *dst, int dstride, int off, bool accumulate, size_t ln = 0, size_t vs = 0) {
     if (!ln) { ln = len; vs = vstride; }
     const int chunks = (int)std::max<size_t>(1, std::min<size_t>(kDotChunks, (ln + 2047) / 2048));
     stats.launches += 2;
     dim3 grd(chunks, B);
-    multidot_partial_kernel<T><<<grd, 256, 0, st_>>>(V, vs, ln, w, nv, partial_, pstride());
-    multidot_final_kernel<T><<<B, std::max(32, ((nv + 31) / 32) * 32), 0, st_>>>(partial_, chunks, pstride(), nv, dst + off,
+    U *part = reinterpret_cast<U *>(partial_);
+    multidot_partial_kernel<U><<<grd, 256, 0, st_>>>(V, vs, ln, w, nv, part, pstride());
+    multidot_final_kernel<U><<<B, std::max(32, ((nv + 31) / 32) * 32), 0, st_>>>(part, chunks, pstride(), nv, dst + off,
                                                                                 dstride, accumulate ? 1 : 0);
   }
-  void axpys(const T *V, int nv, const T *coef, int cstride, double sign, T *w, size_t ln = 0, size_t vs = 0) {
+  template <typename U>
+  void axpys(const U *V, int nv, const U *coef, int cstride, double sign, U *w, size_t ln = 0, size_t vs = 0) {
     if (!ln) { ln = len; vs = vstride; }
     stats.launches++;
     dim3 grd((unsigned)std::min<size_t>((ln + 255) / 256, 1024), B);
-    multiaxpy_kernel<T><<<grd, 256, nv * sizeof(T), st_>>>(V, vs, ln, coef, cstride, nv, sign, w);
+    multiaxpy_kernel<U><<<grd, 256, nv * sizeof(U), st_>>>(V, vs, ln, coef, cstride, nv, sign, w);
   }
-  void scale_inv_norm(const T *x, T *y, const T *nrm2, int stride, size_t ln = 0) {
+  template <typename U>
+  void scale_inv_norm(const U *x, U *y, const U *nrm2, int stride, size_t ln = 0) {
     if (!ln) ln = len;
     stats.launches++;
     dim3 grd((unsigned)std::min<size_t>((ln + 255) / 256, 1024), B);
-    scale_kernel<T><<<grd, 256, 0, st_>>>(x, y, ln, nrm2, stride, 1);
+    scale_kernel<U><<<grd, 256, 0, st_>>>(x, y, ln, nrm2, stride, 1);
   }
   void copy(const T *src, T *dst) { CUDA_CHECK(cudaMemcpyAsync(dst, src, vstride * sizeof(T), cudaMemcpyDeviceToDevice, st_)); }
   void fetch_h(size_t count) {
@@ -557,7 +624,7 @@ class BatchSolver {
     while (true) {
       // r -> Vg_[0] normalised
       T *r0 = Vg_;
-      if (first) copy(rhs, rhs_); else apply(0, MODE_RESID, xsol, rhs, rhs_, true);
+      if (first) copy(rhs, rhs_); else apply_true(MODE_RESID, xsol, rhs, rhs_);
       dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
       scale_inv_norm(rhs_, r0, hbuf_, hstride());
       fetch_h((size_t)B * hstride());
@@ -581,8 +648,8 @@ class BatchSolver {
       int kk = 0;
       for (; kk < restart && total_it < opt_.gmres_maxit; ++kk) {
         T *vk = Vg_ + (size_t)kk * vstride, *zk = Zg_ + (size_t)kk * vstride, *w = Vg_ + (size_t)(kk + 1) * vstride;
-        vcycle(0, vk, zk);
-        apply(0, MODE_APPLY, zk, nullptr, w, true);
+        precondition(vk, zk);
+        apply_true(MODE_APPLY, zk, nullptr, w);
         orthonormalise(Vg_, kk + 1, w, w, h, nrm, opt_.gmres_cgs2 == 0, &cyc_done);
         ++total_it;
         bool all = true;
@@ -891,7 +958,7 @@ class BatchSolver {
     std::vector<CMat> Hm(B, CMat(k, k));
     for (int j = 0; j < k; ++j) {
       T *wj = Zg_ + (size_t)j * vstride;
-      apply(0, MODE_APPLY, Vout_ + (size_t)j * vstride, nullptr, wj, true);
+      apply_true(MODE_APPLY, Vout_ + (size_t)j * vstride, nullptr, wj);
       dots(Vout_, k, wj, hbuf_, hstride(), 0, false);
       fetch_h((size_t)B * hstride());
       for (int b = 0; b < B; ++b)
@@ -923,7 +990,7 @@ class BatchSolver {
   std::vector<double> eigen_residuals(int q, const std::vector<cd> &lambda) {
     set_sigma(lambda);
     T *x = ritz_ + (size_t)q * vstride;
-    apply(0, MODE_APPLY, x, nullptr, rhs_, true);
+    apply_true(MODE_APPLY, x, nullptr, rhs_);
     dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
     dots(x, 1, x, hbuf_, hstride(), 1, false);
     fetch_h((size_t)B * hstride());
@@ -974,7 +1041,7 @@ class BatchSolver {
     }
     EpilogueArgs<T, C> a;
     a.nx = nx; a.ny = ny; a.num_modes = k; a.vec = Zg_; a.vstride = vstride;
-    a.fields = lv[0].fields; a.field_bstride = lv[0].fbstride; a.cx = lv[0].cx_true; a.cy = lv[0].cy_true;
+    a.fields = lv[0].fields_true; a.field_bstride = lv[0].fbstride; a.cx = lv[0].cx_true; a.cy = lv[0].cy_true;
     a.ncomplex = ncomplex_; a.jz_e = jz_; a.jz_h = jz_ + (size_t)B * jz_len; a.jz_axis = p0.jz_axis; a.jz_len = jz_len;
     a.direction = p0.direction; a.h_scale = 1.0 / eta0(); a.out = fields_out_;
     dim3 blk(64, 4), grd((ny + 63) / 64, (nx + 3) / 4, B * k);
@@ -1069,11 +1136,13 @@ class BatchSolver {
   int mask_x_ = 0, mask_y_ = 0;
   T *Vout_ = nullptr, *Vg_ = nullptr, *Zg_ = nullptr, *xsol_ = nullptr, *rhs_ = nullptr, *ritz_ = nullptr;
   T *partial_ = nullptr, *hbuf_ = nullptr, *qbuf_ = nullptr, *sigma_ = nullptr;
+  P *sigma_p_ = nullptr;
+  bool dinv_ready_ = false;
   cplx *ncomplex_ = nullptr, *fields_out_ = nullptr;
   double *jz_ = nullptr;
   bool coarse_krylov_ = false;
   int kc_ = 16;
-  T *cV_ = nullptr, *cZ_ = nullptr, *cH_ = nullptr, *cH2_ = nullptr, *cy_ = nullptr, *cbeta_ = nullptr, *cone_ = nullptr;
+  P *cV_ = nullptr, *cZ_ = nullptr, *cH_ = nullptr, *cH2_ = nullptr, *cy_ = nullptr, *cbeta_ = nullptr, *cone_ = nullptr;
   std::vector<T> hhost_;
   std::vector<cd> sig_host_;
 };
