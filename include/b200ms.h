@@ -105,6 +105,8 @@ typedef struct {
   double inner_relax_cap; /* loosest inner tolerance allowed (default 1e-4) */
   int gmres_cgs2;        /* 1 (default): CGS2 in the inner FGMRES; 0: second pass only on cancellation (measured: 3x more iterations) */
   int stencil_variant;   /* 0: marching kernel (default), 1: shared-memory tiled kernel (reference implementation) */
+  int use_graph;         /* 1 (default): replay the multigrid V-cycle as one CUDA graph (fp32 multigrid only) */
+  int mg_cycles;         /* V-cycles per preconditioner application (default 1) */
   int mg_precision;      /* 1 (default): multigrid preconditioner in fp32 (Krylov iteration stays fp64); 0: all fp64 */
 } b200ms_options;
 

@@ -169,7 +169,7 @@ class BatchSolver {
     sz.add<T>((size_t)(m + 1) * vstride);        // outer basis
     sz.add<T>((size_t)(restart + 1) * vstride);  // FGMRES V
     sz.add<T>((size_t)restart * vstride);        // FGMRES Z
-    sz.add<T>(vstride * 2);                      // xsol, rhs scratch
+    sz.add<T>(vstride * 4);                      // xsol, rhs scratch, preconditioner scratch
     sz.add<T>((size_t)k * vstride);              // Ritz vectors
     sz.add<T>((size_t)B * kDotChunks * pstride());
     sz.add<T>((size_t)B * hstride());
@@ -317,6 +317,8 @@ class BatchSolver {
     Zg_ = arena_.get<T>((size_t)restart * vstride);
     xsol_ = arena_.get<T>(vstride);
     rhs_ = arena_.get<T>(vstride);
+    pre_a_ = arena_.get<P>(vstride);
+    pre_b_ = arena_.get<P>(vstride);
     ritz_ = arena_.get<T>((size_t)k * vstride);
     partial_ = arena_.get<T>((size_t)B * kDotChunks * pstride());
     hbuf_ = arena_.get<T>((size_t)B * hstride());
@@ -353,6 +355,7 @@ class BatchSolver {
     dinv_ready_ = true;
     CUDA_CHECK(cudaStreamSynchronize(st_));
     CUDA_CHECK(cudaGetLastError());
+    capture_precondition_graph();
   }
 
   void set_sigma(const std::vector<cd> &s) {
@@ -433,17 +436,75 @@ class BatchSolver {
     if (has_mu) jacobi0_kernel<P, PC, true><<<grd, blk, 0, st_>>>(a);
     else jacobi0_kernel<P, PC, false><<<grd, blk, 0, st_>>>(a);
   }
-  // z = M^-1 v for Krylov-precision vectors: one V-cycle, converting on the way in and out when mixed
+  // z = M^-1 v for Krylov-precision vectors: `mg_cycles` multigrid V-cycles (iterated on the multigrid operator's own
+  // residual), converting on the way in and out when the multigrid runs in fp32.  Two cycles per application roughly
+  // halve the FGMRES iteration count, which pays because the Gram-Schmidt cost grows quadratically with it.
   void precondition(const T *v, T *z) {
-    if constexpr (!kMixed) {
-      vcycle(0, v, z);
-    } else {
-      const unsigned nb = (unsigned)std::min<size_t>((vstride + 255) / 256, 8192);
+    const int ncyc = std::max(1, opt_.mg_cycles);
+    const unsigned nb = (unsigned)std::min<size_t>((vstride + 255) / 256, 8192);
+    if constexpr (kMixed) {
       convert_kernel<T, P><<<nb, 256, 0, st_>>>(vstride, v, lv[0].b);
-      vcycle(0, lv[0].b, nullptr);
-      convert_kernel<P, T><<<nb, 256, 0, st_>>>(vstride, lv[0].x, z);
+      if (graph_exec_) {
+        CUDA_CHECK(cudaGraphLaunch(graph_exec_, st_));
+        stats.launches += graph_nodes_;
+        stats.stencil_applies += graph_fine_applies_;
+      } else {
+        precondition_body(lv[0].b, nullptr, ncyc);
+        graph_result_ = ncyc == 1 ? lv[0].x : pre_b_;
+      }
+      convert_kernel<P, T><<<nb, 256, 0, st_>>>(vstride, graph_result_, z);
       stats.launches += 2;
+    } else {
+      precondition_body(v, z, ncyc);
     }
+  }
+  // rin -> M^-1 rin in multigrid precision.  out == nullptr: result in lv[0].x (one cycle) or pre_b_ (several)
+  void precondition_body(const P *rin, P *out, int ncyc) {
+    const unsigned nb = (unsigned)std::min<size_t>((vstride + 255) / 256, 8192);
+    if (ncyc == 1) {
+      vcycle(0, rin, out);
+      return;
+    }
+    P *acc = out ? out : pre_b_;
+    vcycle(0, rin, acc);
+    for (int c = 1; c < ncyc; ++c) {
+      apply(0, MODE_RESID, acc, rin, pre_a_);
+      vcycle(0, pre_a_, nullptr);
+      axpby_kernel<P><<<nb, 256, 0, st_>>>(vstride, 1.0, lv[0].x, 1.0, acc);
+      stats.launches++;
+    }
+  }
+  // Capture the V-cycle(s) into a CUDA graph (mixed precision only: its input and output buffers are fixed).  The
+  // cycle is ~60-250 small launches; replaying it as one graph removes most of the launch latency of the coarse levels.
+  void capture_precondition_graph() {
+    if constexpr (kMixed) {
+      if (!opt_.use_graph) return;
+      const int ncyc = std::max(1, opt_.mg_cycles);
+      const long l0 = stats.launches, a0 = stats.stencil_applies;
+      cudaGraph_t graph = nullptr;
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeRelaxed));
+      precondition_body(lv[0].b, nullptr, ncyc);
+      cudaError_t e = cudaStreamEndCapture(st_, &graph);
+      graph_nodes_ = stats.launches - l0;
+      graph_fine_applies_ = stats.stencil_applies - a0;
+      stats.launches = l0;
+      stats.stencil_applies = a0;
+      graph_result_ = ncyc == 1 ? lv[0].x : pre_b_;
+      if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        graph_exec_ = nullptr;
+        return;
+      }
+      if (cudaGraphInstantiate(&graph_exec_, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        graph_exec_ = nullptr;
+      }
+      cudaGraphDestroy(graph);
+    }
+  }
+  ~BatchSolver() {
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
   }
 
   // -- multigrid V-cycle: z = M^-1 rin on level l.  Result lands in `out` (or lv[l].x if null). ----
@@ -1136,8 +1197,11 @@ class BatchSolver {
   int mask_x_ = 0, mask_y_ = 0;
   T *Vout_ = nullptr, *Vg_ = nullptr, *Zg_ = nullptr, *xsol_ = nullptr, *rhs_ = nullptr, *ritz_ = nullptr;
   T *partial_ = nullptr, *hbuf_ = nullptr, *qbuf_ = nullptr, *sigma_ = nullptr;
-  P *sigma_p_ = nullptr;
+  P *sigma_p_ = nullptr, *pre_a_ = nullptr, *pre_b_ = nullptr;
   bool dinv_ready_ = false;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  P *graph_result_ = nullptr;
+  long graph_nodes_ = 0, graph_fine_applies_ = 0;
   cplx *ncomplex_ = nullptr, *fields_out_ = nullptr;
   double *jz_ = nullptr;
   bool coarse_krylov_ = false;

@@ -18,16 +18,6 @@ def run(name, nrep=1, **opts):
         print(f"{name:16s} {str(opts):70s} |dn| {np.abs(out[0][1]-g['n_tight']).max():.1e} op {i['op_applies']} inner {i['inner_iters']} launches {i['stencil_applies']} res {i['max_residual']:.1e} ms {i['solve_ms']:.0f}", flush=True)
     except Exception as e:
         print(name, opts, "FAILED", e, flush=True)
-base = dict(inner_relax=0.0, gmres_cgs2=1, inner_tol=1e-10)
-for name in ["strip_128_m4", "c2_256_f0", "c3_128", "c4_128", "lossy_48", "c1_64"]:
-    run(name, **base)
-    run(name, inner_relax=1.0, inner_relax_cap=1e-4)
-    run(name, inner_relax=1.0, inner_relax_cap=1e-3)
-    run(name, inner_relax=10.0, inner_relax_cap=1e-3)
-    run(name, inner_relax=1.0, inner_relax_cap=1e-4, mg_nu=1)
-    run(name, inner_relax=1.0, inner_relax_cap=1e-4, mg_nu=2, gmres_restart=4)
-H.set_options(gmres_restart=40)
-for name in ["headline_512_f0"]:
-    run(name, nrep=8, **base)
-    run(name, nrep=8, inner_relax=1.0, inner_relax_cap=1e-4)
-    run(name, nrep=8, inner_relax=10.0, inner_relax_cap=1e-3)
+for name, nrep in [("c1_64", 1), ("strip_128_m4", 1), ("c3_128", 1), ("c4_128", 1), ("lossy_48", 1), ("headline_512_f0", 32), ("c3_512", 2), ("c4_512", 2)]:
+    run(name, nrep=nrep, use_graph=0)
+    run(name, nrep=nrep, use_graph=1)
