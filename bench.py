@@ -171,10 +171,11 @@ def main():
     th.start()
     barrier()
     t0 = time.perf_counter()
-    dev_ms, launches, results, h2d, d2h = 0.0, 0, [], 0, 0
+    dev_ms, lib_ms, launches, results, h2d, d2h = 0.0, 0.0, 0, [], 0, 0
     for s in range(args.steps):
         out, info = compute_modes_batch(step_problems(args.warmup + s), handle=h, return_info=True)
         dev_ms += info[0]["solve_ms"]
+        lib_ms += info[0]["total_ms"]
         launches += int(info[0]["stencil_applies"])
         results.append(np.array([o[1] for o in out]))
         d2h = sum(o[0].nbytes + o[1].nbytes for o in out)
@@ -214,7 +215,7 @@ def main():
             "config": {"workload": f"headline Si strip {args.n}x{args.n}, num_modes=4, {fps} freqs/step/GPU of the 256-pt sweep 1.5-1.6um",
                        "l2": "inputs larger than L2 (per-step working set > 10 GB)", "parallelism": f"freq-shard x{world}"},
             "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "lib_wall_ms_per_step": lib_ms / args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "clocks": _clock_summary(samples),
         }
         print(json.dumps(line), flush=True)

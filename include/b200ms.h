@@ -103,7 +103,8 @@ typedef struct {
   double mg_pml_phase;   /* multigrid operator: clamp |arg| of the PML stretch to this (default pi/4; <=0: off) */
   double inner_relax;    /* inexact shift-invert: inner tol = clamp(inner_relax * inner_tol / ritz_residual); 0 = off (default 1.0) */
   double inner_relax_cap; /* loosest inner tolerance allowed (default 1e-4) */
-  int gmres_cgs2;        /* 1 (default): CGS2 in the inner FGMRES; 0: second pass only on cancellation (measured: 3x more iterations) */
+  int gmres_cgs2;        /* inner FGMRES Gram-Schmidt: 1 always two passes (CGS2); 0 one pass (+ a second on cancellation; measured 3x more
+                            iterations at tol 1e-10); 2 (default) one pass while all residuals are > 3e-6, CGS2 below */
   int stencil_variant;   /* 0: marching kernel (default), 1: shared-memory tiled kernel (reference implementation) */
   int use_graph;         /* 1 (default): replay the multigrid V-cycle as one CUDA graph (fp32 multigrid only) */
   int mg_cycles;         /* V-cycles per preconditioner application (default 1) */

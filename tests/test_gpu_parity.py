@@ -139,6 +139,23 @@ def test_relative_mode_solver_matches_reference():
         compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, solver_basis_fields=g["basis"][..., :2])
 
 
+def test_edge_shapes_and_mode_counts():
+    """Tiny and odd-sized grids, one mode, many modes (ncv grows with k like scipy's max(2k+1, 20))."""
+    rng = np.random.default_rng(7)
+    for (nx, ny, k) in [(10, 10, 2), (33, 47, 1), (61, 29, 3), (40, 40, 11)]:
+        x = np.linspace(-1.0, 1.0, nx + 1)
+        y = np.linspace(-0.8, 0.8, ny + 1)
+        xm, ym = 0.5 * (x[:-1] + x[1:]), 0.5 * (y[:-1] + y[1:])
+        base = 2.0 + 9.0 * np.exp(-((xm[:, None] / 0.3) ** 2) - (ym[None, :] / 0.2) ** 2) + 0.05 * rng.random((nx, ny))
+        eps = [np.zeros((nx, ny), complex) for _ in range(9)]
+        eps[0], eps[4], eps[8] = base + 0j, base + 0j, base + 0j
+        spec = W.ModeSpecLike(num_modes=k)
+        f, n, s = compute_modes(eps, [x, y], W.C_0 / 1.55, spec)
+        f0, n0, s0 = R.compute_modes(eps, [x, y], W.C_0 / 1.55, spec, tol=1e-12)
+        assert f.shape == (2, 3, nx, ny, 1, k) and s == s0
+        assert np.abs(n - n0).max() < 1e-8, (nx, ny, k, np.abs(n - n0).max())
+
+
 def test_unsupported_paths_fail_loudly():
     wl = W.angled(32)
     with pytest.raises(NotImplementedError):

@@ -711,7 +711,13 @@ class BatchSolver {
         T *vk = Vg_ + (size_t)kk * vstride, *zk = Zg_ + (size_t)kk * vstride, *w = Vg_ + (size_t)(kk + 1) * vstride;
         precondition(vk, zk);
         apply_true(MODE_APPLY, zk, nullptr, w);
-        orthonormalise(Vg_, kk + 1, w, w, h, nrm, opt_.gmres_cgs2 == 0, &cyc_done);
+        // classical Gram-Schmidt loses orthogonality like eps * kappa^2 with kappa ~ 1 / (relative residual): one pass
+        // is enough while every active problem is still above ~1e-6, two passes (CGS2) below that
+        double minres = 1.0;
+        for (int b = 0; b < B; ++b)
+          if (!cyc_done[b]) minres = std::min(minres, res[b]);
+        const bool one_pass = opt_.gmres_cgs2 == 0 || (opt_.gmres_cgs2 == 2 && minres > 3e-6);
+        orthonormalise(Vg_, kk + 1, w, w, h, nrm, one_pass, &cyc_done);
         ++total_it;
         bool all = true;
         for (int b = 0; b < B; ++b) {

@@ -18,6 +18,6 @@ def run(name, nrep=1, **opts):
         print(f"{name:16s} {str(opts):70s} |dn| {np.abs(out[0][1]-g['n_tight']).max():.1e} op {i['op_applies']} inner {i['inner_iters']} launches {i['stencil_applies']} res {i['max_residual']:.1e} ms {i['solve_ms']:.0f}", flush=True)
     except Exception as e:
         print(name, opts, "FAILED", e, flush=True)
-for name, nrep in [("c1_64", 1), ("strip_128_m4", 1), ("c3_128", 1), ("c4_128", 1), ("lossy_48", 1), ("headline_512_f0", 32), ("c3_512", 2), ("c4_512", 2)]:
-    run(name, nrep=nrep, use_graph=0)
-    run(name, nrep=nrep, use_graph=1)
+for name, nrep in [("c1_64", 1), ("strip_128_m4", 1), ("c3_128", 1), ("c4_128", 1), ("headline_512_f0", 32), ("c3_512", 2)]:
+    run(name, nrep=nrep, gmres_cgs2=1)
+    run(name, nrep=nrep, gmres_cgs2=2)
