@@ -23,6 +23,8 @@
 #ifndef B200MS_H
 #define B200MS_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -118,6 +120,11 @@ int b200ms_create(int device, b200ms_handle **out);
 int b200ms_destroy(b200ms_handle *h);
 int b200ms_set_options(b200ms_handle *h, const b200ms_options *opt);
 const char *b200ms_last_error(b200ms_handle *h);
+
+/* Page-locked host memory for result buffers (optional): fields written into memory from b200ms_host_alloc are copied
+ * device->host at full PCIe/C2C speed instead of through the driver's pageable staging path. */
+void *b200ms_host_alloc(size_t bytes);
+void b200ms_host_free(void *ptr);
 
 /* Solve nprob independent eigenproblems.  Problems with identical (nx, ny, arithmetic) are batched on
  * the device.  Returns B200MS_OK if every problem succeeded, else the first failing status (each

@@ -53,7 +53,7 @@ class Options(C.Structure):
 
 EXPORTS = [
     "b200ms_version", "b200ms_default_options", "b200ms_create", "b200ms_destroy", "b200ms_set_options",
-    "b200ms_last_error", "b200ms_solve_batch", "b200ms_bench_stencil", "b200ms_debug_schur", "b200ms_debug_setup",
+    "b200ms_last_error", "b200ms_host_alloc", "b200ms_host_free", "b200ms_solve_batch", "b200ms_bench_stencil", "b200ms_debug_schur", "b200ms_debug_setup",
     "b200ms_debug_hierarchy", "b200ms_debug_apply", "b200ms_debug_vcycle", "b200ms_debug_solve",
 ]  # fmt: skip
 
@@ -80,6 +80,10 @@ def lib():
             L.b200ms_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
             L.b200ms_last_error.argtypes = [C.c_void_p]
             L.b200ms_last_error.restype = C.c_char_p
+            L.b200ms_host_alloc.argtypes = [C.c_size_t]
+            L.b200ms_host_alloc.restype = C.c_void_p
+            L.b200ms_host_free.argtypes = [C.c_void_p]
+            L.b200ms_host_free.restype = None
             L.b200ms_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Problem), C.POINTER(Result)]
             L.b200ms_bench_stencil.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
             L.b200ms_debug_schur.argtypes = [C.c_int, _dp, _dp, _dp]
@@ -154,6 +158,49 @@ class PackedProblem:
         self.num_modes = p.num_modes
 
 
+class PinnedPool:
+    """Recycling pool of page-locked host buffers for the field results (D2H at full link speed, no first-touch page
+    faults).  A buffer returns to the pool when the numpy array built on it (and every view of it) is garbage
+    collected; at most ``max_cached`` bytes are kept, the rest is freed."""
+
+    def __init__(self, max_cached=8 << 30):
+        self.free = {}
+        self.cached = 0
+        self.max_cached = max_cached
+        self._lock = threading.Lock()
+
+    def empty(self, shape, dtype=np.complex128):
+        import weakref
+
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        with self._lock:
+            lst = self.free.get(nbytes)
+            ptr = lst.pop() if lst else None
+            if ptr is not None:
+                self.cached -= nbytes
+        if ptr is None:
+            ptr = lib().b200ms_host_alloc(nbytes)
+            if not ptr:
+                return np.empty(shape, dtype=dtype)  # pinned allocation failed: ordinary pageable memory still works
+        raw = (C.c_char * nbytes).from_address(ptr)
+        weakref.finalize(raw, self._release, ptr, nbytes)
+        return np.frombuffer(raw, dtype=dtype).reshape(shape)
+
+    def _release(self, ptr, nbytes):
+        with self._lock:
+            if self.cached + nbytes <= self.max_cached:
+                self.free.setdefault(nbytes, []).append(ptr)
+                self.cached += nbytes
+                return
+        try:
+            lib().b200ms_host_free(ptr)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+_pool = PinnedPool()
+
+
 class Handle:
     """One solver handle == one GPU (``b200ms_create`` / ``b200ms_destroy``)."""
 
@@ -201,7 +248,7 @@ class Handle:
             ncs.append(nc)
             results[i].n_complex = _ptr(nc.view(np.float64))
             if want_fields:
-                f = np.empty((2, 3, p.nx, p.ny, 1, p.num_modes), dtype=np.complex128)
+                f = _pool.empty((2, 3, p.nx, p.ny, 1, p.num_modes))
                 fields.append(f)
                 results[i].fields = _ptr(f.view(np.float64))
             else:

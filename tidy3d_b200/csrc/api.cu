@@ -86,6 +86,18 @@ extern "C" int b200ms_destroy(b200ms_handle *h) {
   return B200MS_OK;
 }
 
+extern "C" void *b200ms_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void b200ms_host_free(void *ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
 extern "C" int b200ms_set_options(b200ms_handle *h, const b200ms_options *opt) {
   if (!h || !opt) return B200MS_ERR_ARG;
   h->opt = *opt;
