@@ -76,6 +76,17 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _ref_freq(a):
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import restatement as R
+    from tidy3d_b200 import workloads as W
+
+    n, freq = a
+    wl = W.headline(nf=1, n=n)
+    _, nc, _ = R.compute_modes(wl.eps_cross, wl.coords, freq, wl.mode_spec)
+    return nc
+
+
 def _ref_one(a):
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from oracle import restatement as R
@@ -153,7 +164,8 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = roof["apply"][0]
-    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 464.8e6,  # dram read+write bytes per launch, ncu --set full, profiles/r01_stencil_apply_ncu.txt
+               
                 "kernel": "stencil_march_kernel<double,double,MODE_APPLY> (fp64 operator apply y=(A-sigma)x, 56 B/cell)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "apply_ms": roof["apply"][1], "bytes_per_launch": roof["apply"][2],
@@ -165,19 +177,25 @@ def main():
         return
 
     for s in range(args.warmup):
-        compute_modes_batch(step_problems(s), handle=h)
+        compute_modes_batch(step_problems(s), handle=h)  # results dropped immediately
     stop, samples = threading.Event(), []
     th = threading.Thread(target=_clock_sampler, args=(stop, samples), daemon=True)
     th.start()
     barrier()
     t0 = time.perf_counter()
     dev_ms, lib_ms, launches, results, h2d, d2h = 0.0, 0.0, 0, [], 0, 0
+    first_step_n = None
+    out = None
     for s in range(args.steps):
+        out = None  # drop the previous step's results: their pinned buffers return to the pool
         out, info = compute_modes_batch(step_problems(args.warmup + s), handle=h, return_info=True)
         dev_ms += info[0]["solve_ms"]
         lib_ms += info[0]["total_ms"]
         launches += int(info[0]["stencil_applies"])
         results.append(np.array([o[1] for o in out]))
+        if s == 0:
+            first_step_n = results[0].copy()
+            first_step_freqs = [p["freq"] for p in step_problems(args.warmup)]
         d2h = sum(o[0].nbytes + o[1].nbytes for o in out)
         h2d = 9 * 16 * args.n * args.n  # the shared cross-section is uploaded once per step
     barrier()
@@ -198,16 +216,22 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            from oracle import restatement as R
+            # reference algorithm (scipy ARPACK + SuperLU through the oracle restatement) on the host cores, on a
+            # bounded sample of the same workload: one frequency of the sweep per worker process
+            from concurrent.futures import ProcessPoolExecutor
 
+            cores = os.cpu_count() or 1
+            workers = max(1, min(cores, 8))
+            idx = np.linspace(0, fps - 1, workers).round().astype(int)
             tc = time.time()
-            smallwl = W.headline(nf=256, n=args.n)
-            os.environ.setdefault("OMP_NUM_THREADS", "1")
-            _, nref, _ = R.compute_modes(smallwl.eps_cross, smallwl.coords, my[0], smallwl.mode_spec)
+            with ProcessPoolExecutor(workers) as ex:
+                ncpu = list(ex.map(_ref_freq, [(args.n, float(first_step_freqs[i])) for i in idx]))
             tcpu = time.time() - tc
-            cpu = {"value": 1.0 / tcpu, "unit": "solves/s", "cores": 1, "kind": "port",
-                   "sample": f"1 of the 256 frequencies ({args.n}x{args.n}, 4 modes) with scipy eigs (ARPACK+SuperLU) on one core: {tcpu:.1f} s",
-                   "max_abs_dn_vs_gpu": None}
+            dn = max(float(np.abs(np.asarray(ncpu[j]) - first_step_n[i]).max()) for j, i in enumerate(idx))
+            cpu = {"value": workers / tcpu, "unit": "solves/s", "cores": workers, "kind": "port",
+                   "sample": f"{workers} of the 256 frequencies ({args.n}x{args.n}, 4 modes), one per worker process, scipy eigs "
+                             f"(ARPACK+SuperLU) via oracle/restatement.py: {tcpu:.1f} s wall",
+                   "host_cores_total": cores, "max_abs_dn_gpu_vs_cpu": dn}
         line = {
             "metric": "mode-solves/sec (512x512, 4 modes, 256 freqs)", "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,

@@ -322,15 +322,11 @@ __global__ void __launch_bounds__(256) stencil_kernel(StencilArgs<T, C> a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kMarchCols = 128, kMarchOut = 126;
 
-// resident CTAs per SM the register allocator should aim for (occupancy is what hides the HBM latency here: a
-// two-deep software prefetch at 89 registers measured slower than one-deep at 72)
-template <typename T, int MODE> struct MarchBlocks { static constexpr int value = 3; };
-template <int MODE> struct MarchBlocks<double, MODE> { static constexpr int value = MODE == MODE_JACOBI ? 4 : 8; };
-template <int MODE> struct MarchBlocks<float, MODE> { static constexpr int value = 8; };
-template <int MODE> struct MarchBlocks<cplxf, MODE> { static constexpr int value = 4; };
-
+// Measured alternatives (bench.py --stencil-only, 32 x 512^2): a two-deep software prefetch (89 registers) ran the fp64
+// apply at 126 us and forcing 8 CTAs/SM through __launch_bounds__ (64 registers, small spills) at 131 us, against
+// 108 us for this one-deep version at 72 registers; occupancy and register pressure trade off right here.
 template <typename T, typename C, int MODE, bool HAS_MU, int TXR>
-__global__ void __launch_bounds__(kMarchCols, MarchBlocks<T, MODE>::value) stencil_march_kernel(StencilArgs<T, C> a) {
+__global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T, C> a) {
   constexpr bool JAC = (MODE == MODE_JACOBI);
   __shared__ T sB[2][kMarchCols + 2], sV[2][kMarchCols + 2], sU[2][kMarchCols + 2], sTt[2][kMarchCols + 2];
   __shared__ C sIe[JAC ? 2 : 1][JAC ? kMarchCols + 2 : 1];
