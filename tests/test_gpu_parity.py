@@ -93,6 +93,20 @@ def test_frequency_batch_equals_single_solves():
     assert (np.diff(ns[:, 0].real) < 0).all()  # n_eff falls with wavelength along the sweep
 
 
+def test_c5_planes_batch_distinct_cross_sections():
+    """BASELINE config 5 in miniature: several mode planes (different core widths) x frequencies in ONE batch, so
+    the problems of a device batch carry different coefficient fields (no sharing)."""
+    planes = W.c5_planes(n_planes=3, n=64, nf=2)
+    probs = [dict(eps_cross=p.eps_cross, coords=p.coords, freq=f, mode_spec=p.mode_spec) for p in planes for f in p.freqs]
+    out = compute_modes_batch(probs)
+    assert len(out) == 6
+    for pr, (f, n, s) in zip(probs, out):
+        _, n0, _ = R.compute_modes(pr["eps_cross"], pr["coords"], pr["freq"], pr["mode_spec"], tol=1e-12)
+        assert np.abs(n - n0).max() < 1e-8
+    widths_n1 = [out[2 * i][1][0].real for i in range(3)]
+    assert widths_n1[0] < widths_n1[1] < widths_n1[2]  # wider core -> larger fundamental n_eff
+
+
 def test_mixed_batch_groups_and_ragged_inputs():
     """One call with different grid sizes, arithmetic kinds and mode counts; and an empty batch."""
     assert compute_modes_batch([]) == []
