@@ -12,7 +12,8 @@ from tidy3d_b200 import workloads as W
 pytestmark = pytest.mark.gpu
 
 SMALL = ["c1_64", "c1_64_minus", "c1_64_sym_pmc_pec", "lossy_48", "nonuniform_56", "slab1d_x1", "slab1d_y1",
-         "c3_96", "c4_96", "c4_96_axis0", "strip_128_m4", "c3_128", "c4_128"]  # fmt: skip
+         "c3_96", "c4_96", "c4_96_axis0", "strip_128_m4", "c3_128", "c4_128",
+         "angled_64", "angled_48_minus", "angled_phi_48", "offdiag_48"]  # fmt: skip
 LARGE = ["c2_256_f0", "headline_512_f0", "c3_512", "c4_512"]
 
 
@@ -171,9 +172,11 @@ def test_edge_shapes_and_mode_counts():
 
 
 def test_unsupported_paths_fail_loudly():
-    wl = W.angled(32)
+    wl = W.c1()
     with pytest.raises(NotImplementedError):
-        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec)
+        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, mu_cross=wl.eps_cross)
+    with pytest.raises(NotImplementedError):
+        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, split_curl_scaling=wl.eps_cross[:3])
 
 
 def test_full_size_properties_headline_batch():

@@ -77,7 +77,7 @@ def test_host_setup_matches_oracle(built_lib, name):
     rc, sigma, flags, tgt, kn, cx, cy, f, pk = _setup(built_lib, wl, kw)
     st = R.setup(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, kw.get("symmetry", (0, 0)))
     assert bool(flags[1]) == st["tensorial"]
-    assert rc == (3 if st["tensorial"] else 0)
+    assert rc == 0
     dt = R.solver_dtype(st, "double")
     assert bool(flags[0]) == np.issubdtype(dt, np.complexfloating)
     assert abs(tgt - st["target"]) < 1e-14 and abs(kn - st["knorm"]) < 1e-14
@@ -85,9 +85,8 @@ def test_host_setup_matches_oracle(built_lib, name):
     rel = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)  # noqa: E731
     assert rel(cx, np.concatenate(st["coef"][0])) < 1e-13
     assert rel(cy, np.concatenate(st["coef"][1])) < 1e-13
-    if not st["tensorial"]:
-        e, m = st["eps"], st["mu"]
-        assert rel(f, np.stack([e[0, 0], e[1, 1], e[2, 2], m[0, 0], m[1, 1], m[2, 2]])) < 1e-13
+    e, m = st["eps"], st["mu"]
+    assert rel(f, np.stack([e[0, 0], e[1, 1], e[2, 2], m[0, 0], m[1, 1], m[2, 2]])) < 1e-13
 
 
 def test_hierarchy_plan(built_lib):

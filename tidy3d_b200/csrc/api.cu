@@ -109,10 +109,11 @@ extern "C" const char *b200ms_last_error(b200ms_handle *h) { return h ? h->err.c
 namespace {
 
 struct GroupKey {
-  int nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel;
+  int nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens;
+  double theta, phi;
   bool operator<(const GroupKey &o) const {
-    return std::tie(nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel) <
-           std::tie(o.nx, o.ny, o.k, o.kind, o.has_mu, o.sx, o.sy, o.jz_axis, o.dir, o.rel);
+    return std::tie(nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens, theta, phi) <
+           std::tie(o.nx, o.ny, o.k, o.kind, o.has_mu, o.sx, o.sy, o.jz_axis, o.dir, o.rel, o.tens, o.theta, o.phi);
   }
 };
 struct MediumKey {
@@ -172,10 +173,14 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
         ll[q] = rel_vals[(size_t)b * k + q];
       } else {
         cd th = eig.theta[(size_t)b * k + q];
-        ll[q] = ps[b]->sigma + (std::abs(th) > 0 ? 1.0 / th : cd(0, 0));
+        ll[q] = (S.tensor_ ? ps[b]->sigma_t : ps[b]->sigma) + (std::abs(th) > 0 ? 1.0 / th : cd(0, 0));
       }
-      nn[q] = std::sqrt(-ll[q]);
-      if (nn[q].real() < 0) nn[q] = -nn[q];
+      if (S.tensor_) {
+        nn[q] = ll[q];  // the first-order operator's eigenvalue is n_eff + i k_eff itself (solver.py:879-880)
+      } else {
+        nn[q] = std::sqrt(-ll[q]);
+        if (nn[q].real() < 0) nn[q] = -nn[q];
+      }
     }
     std::vector<int> o(k);
     for (int q = 0; q < k; ++q) o[q] = q;
@@ -222,7 +227,7 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
       const size_t cnt = (size_t)12 * S.N * k;
       for (size_t i = 0; i < cnt; ++i) r.fields[i] = (double)(float)r.fields[i];
     }
-    r.eps_spec = B200MS_SPEC_DIAGONAL;
+    r.eps_spec = ps[b]->eps_spec;
     r.converged = eig.nconv[b];
     r.outer_iters = S.stats.restarts;
     r.op_applies = S.stats.op_applies;
@@ -291,7 +296,7 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
       }
       const ProblemSetup &s = setups[i];
       GroupKey key{s.nx, s.ny, s.num_modes, kind_of(s), s.has_mu ? 1 : 0, prob[i].symmetry[0], prob[i].symmetry[1],
-                   s.jz_axis, s.direction, s.relative ? 1 : 0};
+                   s.jz_axis, s.direction, s.relative ? 1 : 0, s.tensorial ? (s.eps_complex ? 2 : 1) : 0, prob[i].angle_theta, prob[i].angle_phi};
       groups[key].push_back(i);
     }
     size_t free_b = 0, total_b = 0;

@@ -65,6 +65,10 @@ struct ProblemSetup {
   std::vector<double> dlf[2], dlb[2];
   double target_raw = 0;     // target before the knorm division and nudge (solver.py:204-210)
   bool eps_complex = false, mu_complex = false;
+  // tensorial path (solver.py:594-721): 18 derived coefficient fields, see tensor_fields() below
+  std::shared_ptr<std::vector<cd>> ft[18];
+  cd sigma_t;                // shift of the first-order operator: target n_eff (solver.py:684)
+  double jac_a = 0, jac_b = 0;  // J[0][2], J[1][2] of the angled transform (transforms.py:107-108)
   std::vector<double> jz_e, jz_h;  // bend back-transform E_z *= jz_e[ix or iy], H_z *= jz_h (solver.py:254-259)
   int jz_axis = -1;          // axis along which jz varies (-1: none)
   double max_k2 = 0;         // max over cells of Re(eps) - target^2 (positive => indefinite region)
@@ -93,6 +97,33 @@ inline void sfactors(double omega, const std::vector<double> &dlf, const std::ve
     else if (i > n - npml)
       sb[i] = s_value(dlb[n - 1], double(i - (n - npml)) / npml, omega, sp_max);
   }
+}
+
+// eps' = J eps J^T / det J and mu' = J J^T / det J (mu = identity) at one cell, for J = [[1,0,a],[0,1,b],[0,0,d]]
+// (angled transform followed by the bend, solver.py:142-172; d differs between E and H sites for a bend)
+inline void transformed_tensors(const cd *eps, size_t n, size_t c, double a, double b, double d_e, double d_h, cd e[9], cd m[9]) {
+  cd raw[9];
+  for (int k = 0; k < 9; ++k) raw[k] = eps[(size_t)k * n + c];
+  const double Je[3][3] = {{1, 0, a}, {0, 1, b}, {0, 0, d_e}}, Jh[3][3] = {{1, 0, a}, {0, 1, b}, {0, 0, d_h}};
+  cd tmp[9];
+  for (int i = 0; i < 3; ++i)
+    for (int p2 = 0; p2 < 3; ++p2) {
+      cd acc = 0.0;
+      for (int j = 0; j < 3; ++j) acc += Je[i][j] * raw[3 * j + p2];
+      tmp[3 * i + p2] = acc;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int p2 = 0; p2 < 3; ++p2) {
+      cd acc = 0.0;
+      for (int j = 0; j < 3; ++j) acc += tmp[3 * i + j] * Je[p2][j];
+      e[3 * i + p2] = acc / d_e;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int p2 = 0; p2 < 3; ++p2) {
+      double acc = 0.0;
+      for (int j = 0; j < 3; ++j) acc += Jh[i][j] * Jh[p2][j];
+      m[3 * i + p2] = acc / d_h;
+    }
 }
 
 // Frequency-dependent part of the set-up: PML stretch and the k0-scaled lengths of both axes.  Needs s.k0,
@@ -213,6 +244,9 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
   }
   if (angled) {
     s.tensorial = true;  // J has off-diagonals (transforms.py:74-111) -> solver.py:594
+    s.jac_a = -std::tan(p.angle_theta) * std::cos(p.angle_phi);
+    s.jac_b = -std::tan(p.angle_theta) * std::sin(p.angle_phi);
+    s.has_mu = true;
   }
 
   // eps' = J eps J^T / det J with J = diag(1,1,d) (solver.py:165-172); mu' likewise from identity
@@ -229,18 +263,14 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
         d_e = de[t];
         d_h = dh[t];
       }
-      cd e[9];
-      for (int k = 0; k < 9; ++k) e[k] = eps[(size_t)k * n + c];
-      // J e J^T / det: rows/cols 2 scaled by d, everything / d
-      const double sc[3] = {1.0, 1.0, d_e};
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) e[3 * a + b] *= sc[a] * sc[b] / d_e;
+      cd e[9], m[9];
+      transformed_tensors(eps, n, c, s.jac_a, s.jac_b, d_e, d_h, e, m);
       (*F[0])[c] = e[0];
       (*F[1])[c] = e[4];
       (*F[2])[c] = e[8];
-      (*F[3])[c] = 1.0 / d_h;
-      (*F[4])[c] = 1.0 / d_h;
-      (*F[5])[c] = d_h;
+      (*F[3])[c] = m[0];
+      (*F[4])[c] = m[4];
+      (*F[5])[c] = m[8];
     }
 
   // grid steps, solver.py:187-190
@@ -293,16 +323,20 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
         im2 += (*F[k])[c].imag() * (*F[k])[c].imag();
         all2 += std::norm((*F[k])[c]);
       }
-      const double sc[3] = {1.0, 1.0, d_e};
+      const double d_h2 = bend ? dh[norm_axis == 0 ? ix : iy] : 1.0;
+      cd et[9], mt[9];
+      transformed_tensors(eps, n, c, s.jac_a, s.jac_b, d_e, d_h2, et, mt);
       for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) {
           if (a == b) continue;
-          cd v = eps[(size_t)(3 * a + b) * n + c] * (sc[a] * sc[b] / d_e);
+          cd v = et[3 * a + b];
           if (is_pec(v)) v = pec_model;
-          double av = std::abs(v);
+          double av = std::max(std::abs(v), std::abs(mt[3 * a + b]));
           if (av > off_max) off_max = av;
           im2 += v.imag() * v.imag();
           all2 += std::norm(v);
+          mu_i2 += mt[3 * a + b].imag() * mt[3 * a + b].imag();
+          mu_a2 += std::norm(mt[3 * a + b]);
         }
       for (int k = 3; k < 6; ++k) {
         mu_i2 += (*F[k])[c].imag() * (*F[k])[c].imag();
@@ -318,11 +352,44 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
   s.is_complex = s.coef_complex || der_complex;
   s.relative = p.basis_e != nullptr;
   if (s.relative) s.is_complex = true;  // the supplied basis is complex (solver.py:771-775)
+  s.eps_complex = eps_complex;
+  s.mu_complex = mu_complex;
+  s.sigma_t = cd(s.target, 0.0);
   if (s.tensorial) {
-    s.is_complex = true;
+    s.has_mu = true;      // the tensorial kernels always carry the six diagonal-part fields
+    s.is_complex = true;  // solver.py:395-396: the tensorial matrix is always complex
     s.eps_spec = eps_complex ? B200MS_SPEC_TENSORIAL_COMPLEX : B200MS_SPEC_TENSORIAL_REAL;
-    s.status = B200MS_ERR_UNSUPPORTED;
-    s.error = "tensorial permittivity (angled / off-diagonal eps, solver.py:594) is not built yet";
+    if (s.relative) {
+      s.status = B200MS_ERR_UNSUPPORTED;  // solver.py:357-361
+      s.error = "Tensorial eps not yet supported in relative mode solver (with basis fields provided).";
+    }
+    // derived coefficient fields of the 4N first-order operator (solver.py:604-653), PEC model applied entry-wise
+    for (int k = 0; k < 18; ++k) s.ft[k] = std::make_shared<std::vector<cd>>(n);
+    for (int ix = 0; ix < nx; ++ix)
+      for (int iy = 0; iy < ny; ++iy) {
+        const size_t c = (size_t)ix * ny + iy;
+        const double d_e = bend ? de[norm_axis == 0 ? ix : iy] : 1.0, d_h2 = bend ? dh[norm_axis == 0 ? ix : iy] : 1.0;
+        cd et[9], mt[9];
+        transformed_tensors(eps, n, c, s.jac_a, s.jac_b, d_e, d_h2, et, mt);
+        for (int q = 0; q < 9; ++q)
+          if (is_pec(et[q])) et[q] = pec_model;
+        const cd *tt[2] = {et, mt};
+        for (int w = 0; w < 2; ++w) {
+          const cd *t = tt[w];
+          const cd izz = 1.0 / t[8];
+          cd *dst[9];
+          for (int q = 0; q < 9; ++q) dst[q] = &(*s.ft[9 * w + q])[c];
+          *dst[0] = t[6] * izz;                    // t_zx / t_zz
+          *dst[1] = t[7] * izz;                    // t_zy / t_zz
+          *dst[2] = izz;                           // 1 / t_zz
+          *dst[3] = t[5] * izz;                    // t_yz / t_zz
+          *dst[4] = t[2] * izz;                    // t_xz / t_zz
+          *dst[5] = t[0] - t[2] * t[6] * izz;      // S_xx = t_xx - t_xz t_zx / t_zz
+          *dst[6] = t[1] - t[2] * t[7] * izz;      // S_xy
+          *dst[7] = t[3] - t[5] * t[6] * izz;      // S_yx
+          *dst[8] = t[4] - t[5] * t[7] * izz;      // S_yy
+        }
+      }
   }
   if (s.relative && p.num_modes > 20) {
     s.status = B200MS_ERR_UNSUPPORTED;

@@ -802,6 +802,210 @@ __global__ void gmres_lsq_kernel(T *H, int kc, int ld, const T *beta2, int bstri
 }
 
 // ------------------------------------------------------------------------------------------------
+// tensorial path (angled waveguides / off-diagonal eps): the 4N first-order operator of solver.py:604-666,
+//   mat = msign * (-i) * M,   M [Ex;Ey;Hx;Hy] = [r1;r2;r3;r4]
+// written with U = Ez and Tt = Hz of solver.py:708-711:
+//   K = Dxb Hy - Dyb Hx,  G = Dxf Ey - Dyf Ex
+//   U = K/ezz - (ezx/ezz) Ex - (ezy/ezz) Ey,   Tt = G/mzz - (mzx/mzz) Hx - (mzy/mzz) Hy
+//   r1 = Dxf U + (myz/mzz) G + Sm_yx Hx + Sm_yy Hy      r3 = Dxb Tt + (eyz/ezz) K + Se_yx Ex + Se_yy Ey
+//   r2 = Dyf U - (mxz/mzz) G - Sm_xx Hx - Sm_xy Hy      r4 = Dyb Tt - (exz/ezz) K - Se_xx Ex - Se_xy Ey
+// with S_ab = t_ab - t_az t_zb / t_zz.  Coefficient fields ft[18]: for eps (0..8) and mu (9..17):
+//   t_zx/t_zz, t_zy/t_zz, 1/t_zz, t_yz/t_zz, t_xz/t_zz, S_xx, S_xy, S_yx, S_yy.
+// Vector layout [B][4][N].  A plain one-thread-per-cell kernel (neighbours through L1); this path is correctness
+// first, the diagonal path is the tuned one.
+// ------------------------------------------------------------------------------------------------
+template <typename C>
+struct TensorArgs {
+  int nx, ny;
+  const cplx *w;
+  const cplx *rhs;   // optional: y = rhs - (mat - sigma) w
+  cplx *y;
+  const C *ft;       // [fb][18][N]
+  size_t ft_bstride;
+  const cplx *cx, *cy;  // [B][4][n] reference-operator difference coefficients
+  const cplx *sigma;    // [B]
+  double msign;
+};
+
+template <typename C>
+struct TensorCell {
+  const cplx *ex, *ey, *hx, *hy;
+  const C *ft;
+  const cplx *cx, *cy;
+  int nx, ny;
+  size_t N;
+  __device__ __forceinline__ cplx ld(const cplx *p, int i, int j) const {
+    return (i >= 0 && i < nx && j >= 0 && j < ny) ? ldg(p + (size_t)i * ny + j) : mk(0.0, 0.0);
+  }
+  __device__ __forceinline__ cplx CX(int w, int i) const { return (i >= 0 && i < nx) ? ldg(cx + (size_t)w * nx + i) : mk(0.0, 0.0); }
+  __device__ __forceinline__ cplx CY(int w, int j) const { return (j >= 0 && j < ny) ? ldg(cy + (size_t)w * ny + j) : mk(0.0, 0.0); }
+  __device__ __forceinline__ C F(int k, int i, int j) const { return ldg(ft + (size_t)k * N + (size_t)i * ny + j); }
+  __device__ __forceinline__ cplx K(int i, int j) const {
+    return CX(2, i) * ld(hy, i, j) + CX(3, i) * ld(hy, i - 1, j) - CY(2, j) * ld(hx, i, j) - CY(3, j) * ld(hx, i, j - 1);
+  }
+  __device__ __forceinline__ cplx G(int i, int j) const {
+    return CX(0, i) * ld(ey, i, j) + CX(1, i) * ld(ey, i + 1, j) - CY(0, j) * ld(ex, i, j) - CY(1, j) * ld(ex, i, j + 1);
+  }
+  __device__ __forceinline__ cplx U(int i, int j) const {
+    if (i < 0 || j < 0 || i >= nx || j >= ny) return mk(0.0, 0.0);
+    return F(2, i, j) * K(i, j) - F(0, i, j) * ld(ex, i, j) - F(1, i, j) * ld(ey, i, j);
+  }
+  __device__ __forceinline__ cplx Tt(int i, int j) const {
+    if (i < 0 || j < 0 || i >= nx || j >= ny) return mk(0.0, 0.0);
+    return F(11, i, j) * G(i, j) - F(9, i, j) * ld(hx, i, j) - F(10, i, j) * ld(hy, i, j);
+  }
+};
+
+template <typename C>
+__global__ void __launch_bounds__(256) tensor_apply_kernel(TensorArgs<C> a) {
+  const int nx = a.nx, ny = a.ny;
+  const size_t N = (size_t)nx * ny;
+  const int j = blockIdx.x * 64 + threadIdx.x, i = blockIdx.y * 4 + threadIdx.y, b = blockIdx.z;
+  if (i >= nx || j >= ny) return;
+  const cplx *wb = a.w + (size_t)b * 4 * N;
+  TensorCell<C> t{wb, wb + N, wb + 2 * N, wb + 3 * N, a.ft + a.ft_bstride * b, a.cx + (size_t)b * 4 * nx, a.cy + (size_t)b * 4 * ny, nx, ny, N};
+  const size_t g = (size_t)i * ny + j;
+  const cplx ex = ldg(t.ex + g), ey = ldg(t.ey + g), hx = ldg(t.hx + g), hy = ldg(t.hy + g);
+  const cplx u00 = t.U(i, j), u10 = t.U(i + 1, j), u01 = t.U(i, j + 1);
+  const cplx t00 = t.Tt(i, j), tm0 = t.Tt(i - 1, j), t0m = t.Tt(i, j - 1);
+  const cplx kk = t.K(i, j), gg = t.G(i, j);
+  cplx r1 = t.CX(0, i) * u00 + t.CX(1, i) * u10 + t.F(12, i, j) * gg + t.F(16, i, j) * hx + t.F(17, i, j) * hy;
+  cplx r2 = t.CY(0, j) * u00 + t.CY(1, j) * u01 - t.F(13, i, j) * gg - t.F(14, i, j) * hx - t.F(15, i, j) * hy;
+  cplx r3 = t.CX(2, i) * t00 + t.CX(3, i) * tm0 + t.F(3, i, j) * kk + t.F(7, i, j) * ex + t.F(8, i, j) * ey;
+  cplx r4 = t.CY(2, j) * t00 + t.CY(3, j) * t0m - t.F(4, i, j) * kk - t.F(5, i, j) * ex - t.F(6, i, j) * ey;
+  const cplx mi = mk(0.0, -a.msign);  // msign * (-i)
+  const cplx sg = ldg(a.sigma + b);
+  cplx o1 = mi * r1 - sg * ex, o2 = mi * r2 - sg * ey, o3 = mi * r3 - sg * hx, o4 = mi * r4 - sg * hy;
+  cplx *yb = a.y + (size_t)b * 4 * N;
+  if (a.rhs) {
+    const cplx *rb = a.rhs + (size_t)b * 4 * N;
+    o1 = ldg(rb + g) - o1; o2 = ldg(rb + N + g) - o2; o3 = ldg(rb + 2 * N + g) - o3; o4 = ldg(rb + 3 * N + g) - o4;
+  }
+  yb[g] = o1; yb[N + g] = o2; yb[2 * N + g] = o3; yb[3 * N + g] = o4;
+}
+
+// Diagonal-part blocks of the first-order operator, M_d = [[0, P], [Q, 0]] (solver.py:479-489):
+//   which = 0:  out = P h,  P h = [Dxf u + myy hy ; Dyf u - mxx hx],  u = (Dxb hy - Dyb hx) / ezz
+//   which = 1:  out = Q e,  Q e = [Dxb t + eyy ey ; Dyb t - exx ex],  t = (Dxf ey - Dyf ex) / mzz
+// in/out are two-component fields with arbitrary batch strides (they are halves of 4N Krylov vectors).
+template <typename C>
+__global__ void __launch_bounds__(256) pq_kernel(int which, int nx, int ny, const cplx *in, size_t in_bstride, cplx *out,
+                                                 size_t out_bstride, const C *fields, size_t f_bstride, const cplx *cxs,
+                                                 const cplx *cys) {
+  const size_t N = (size_t)nx * ny;
+  const int j = blockIdx.x * 64 + threadIdx.x, i = blockIdx.y * 4 + threadIdx.y, b = blockIdx.z;
+  if (i >= nx || j >= ny) return;
+  const cplx *a1 = in + in_bstride * b, *a2 = a1 + N;
+  const C *fb = fields + f_bstride * b;
+  const C *exx = fb, *eyy = fb + N, *iez = fb + 2 * N, *mxx = fb + 3 * N, *myy = fb + 4 * N, *imz = fb + 5 * N;
+  const cplx *cx = cxs + (size_t)b * 4 * nx, *cy = cys + (size_t)b * 4 * ny;
+  const cplx z = mk(0.0, 0.0);
+  auto ld = [&](const cplx *p, int ii, int jj) { return (ii >= 0 && ii < nx && jj >= 0 && jj < ny) ? ldg(p + (size_t)ii * ny + jj) : z; };
+  auto CX = [&](int w, int ii) { return (ii >= 0 && ii < nx) ? ldg(cx + (size_t)w * nx + ii) : z; };
+  auto CY = [&](int w, int jj) { return (jj >= 0 && jj < ny) ? ldg(cy + (size_t)w * ny + jj) : z; };
+  const size_t g = (size_t)i * ny + j;
+  cplx o1, o2;
+  if (which == 0) {  // a1 = hx, a2 = hy
+    auto U = [&](int ii, int jj) {
+      if (ii < 0 || jj < 0 || ii >= nx || jj >= ny) return z;
+      cplx kd = CX(2, ii) * ld(a2, ii, jj) + CX(3, ii) * ld(a2, ii - 1, jj) - CY(2, jj) * ld(a1, ii, jj) - CY(3, jj) * ld(a1, ii, jj - 1);
+      return ldg(iez + (size_t)ii * ny + jj) * kd;
+    };
+    const cplx u00 = U(i, j);
+    o1 = CX(0, i) * u00 + CX(1, i) * U(i + 1, j) + ldg(myy + g) * ldg(a2 + g);
+    o2 = CY(0, j) * u00 + CY(1, j) * U(i, j + 1) - ldg(mxx + g) * ldg(a1 + g);
+  } else {  // a1 = ex, a2 = ey
+    auto T = [&](int ii, int jj) {
+      if (ii < 0 || jj < 0 || ii >= nx || jj >= ny) return z;
+      cplx gd = CX(0, ii) * ld(a2, ii, jj) + CX(1, ii) * ld(a2, ii + 1, jj) - CY(0, jj) * ld(a1, ii, jj) - CY(1, jj) * ld(a1, ii, jj + 1);
+      return ldg(imz + (size_t)ii * ny + jj) * gd;
+    };
+    const cplx t00 = T(i, j);
+    o1 = CX(2, i) * t00 + CX(3, i) * T(i - 1, j) + ldg(eyy + g) * ldg(a2 + g);
+    o2 = CY(2, j) * t00 + CY(3, j) * T(i, j - 1) - ldg(exx + g) * ldg(a1 + g);
+  }
+  cplx *ob = out + out_bstride * b;
+  ob[g] = o1;
+  ob[N + g] = o2;
+}
+
+// out[b][e] = ca[b] * x[b][e] + cb[b] * y[b][e]  (per-problem complex scalars, strided batches; y may be null)
+__global__ void __launch_bounds__(256) lin2_kernel(size_t len, const cplx *ca, const cplx *x, size_t x_bstride, const cplx *cb,
+                                                   const cplx *y, size_t y_bstride, cplx *out, size_t out_bstride) {
+  const int b = blockIdx.y;
+  const cplx a = ca[b], bb = cb ? cb[b] : mk(0.0, 0.0);
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < len; e += stride) {
+    cplx v = a * ldg(x + x_bstride * b + e);
+    if (y) v = v + bb * ldg(y + y_bstride * b + e);
+    out[out_bstride * b + e] = v;
+  }
+}
+
+// strided precision conversion: dst[b][e] = (D) src[b][e]
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) convert_strided_kernel(size_t len, const S *src, size_t src_bstride, D *dst, size_t dst_bstride) {
+  const int b = blockIdx.y;
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < len; e += stride) {
+    D d;
+    convert(src[src_bstride * b + e], d);
+    dst[dst_bstride * b + e] = d;
+  }
+}
+
+// tensorial epilogue (solver.py:701-719, 254-269): six components from w = [Ex;Ey;Hx;Hy], Ez = U, Hz = Tt
+template <typename C>
+struct TensorEpilogueArgs {
+  int nx, ny, num_modes;
+  const cplx *vec;   // mode m of problem b at vec + m*vstride + b*4N
+  size_t vstride;
+  const C *ft;
+  size_t ft_bstride;
+  const cplx *cx, *cy;
+  const double *jz_e, *jz_h;  // bend scale of the z components or null
+  int jz_axis, jz_len;
+  double jac_a, jac_b;        // angled transform J[0][2], J[1][2]
+  int conj_flip;              // tensorial_real with direction "-": E = conj(E), H = -conj(H) (solver.py:378-380)
+  double h_scale;
+  cplx *out;
+};
+template <typename C>
+__global__ void __launch_bounds__(256) tensor_epilogue_kernel(TensorEpilogueArgs<C> a) {
+  const int nx = a.nx, ny = a.ny, M = a.num_modes;
+  const size_t N = (size_t)nx * ny;
+  const int j = blockIdx.x * 64 + threadIdx.x, i = blockIdx.y * 4 + threadIdx.y;
+  const int m = blockIdx.z % M, b = blockIdx.z / M;
+  if (i >= nx || j >= ny) return;
+  const cplx *wb = a.vec + (size_t)m * a.vstride + (size_t)b * 4 * N;
+  TensorCell<C> t{wb, wb + N, wb + 2 * N, wb + 3 * N, a.ft + a.ft_bstride * b, a.cx + (size_t)b * 4 * nx, a.cy + (size_t)b * 4 * ny, nx, ny, N};
+  const size_t g = (size_t)i * ny + j;
+  const cplx hs = mk(0.0, -a.h_scale);
+  cplx Ex = ldg(t.ex + g), Ey = ldg(t.ey + g), Ez = t.U(i, j);
+  cplx Hx = hs * ldg(t.hx + g), Hy = hs * ldg(t.hy + g), Hz = hs * t.Tt(i, j);
+  if (a.conj_flip) {
+    Ex = cj(Ex); Ey = cj(Ey); Ez = cj(Ez);
+    Hx = -cj(Hx); Hy = -cj(Hy); Hz = -cj(Hz);
+  }
+  double de = 1.0, dh = 1.0;
+  if (a.jz_axis >= 0) {
+    const int q = a.jz_axis == 0 ? i : j;
+    de = a.jz_e[(size_t)b * a.jz_len + q];
+    dh = a.jz_h[(size_t)b * a.jz_len + q];
+  }
+  // E = J^T E' with J = [[1,0,a],[0,1,b],[0,0,d]]
+  Ez = a.jac_a * Ex + a.jac_b * Ey + de * Ez;
+  Hz = a.jac_a * Hx + a.jac_b * Hy + dh * Hz;
+  cplx *o = a.out + (size_t)b * 6 * N * M;
+  o[(0 * N + g) * M + m] = Ex;
+  o[(1 * N + g) * M + m] = Ey;
+  o[(2 * N + g) * M + m] = Ez;
+  o[(3 * N + g) * M + m] = Hx;
+  o[(4 * N + g) * M + m] = Hy;
+  o[(5 * N + g) * M + m] = Hz;
+}
+
+// ------------------------------------------------------------------------------------------------
 // epilogue: eigenvector -> six field components in the reference layout (solver.py:556-589,254-269)
 // ------------------------------------------------------------------------------------------------
 template <typename T, typename C>

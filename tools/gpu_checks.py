@@ -126,5 +126,7 @@ if __name__ == "__main__":
                 components(name, fac(), kw)
             except Exception as e:  # noqa: BLE001
                 print(f"== {name}: FAILED {type(e).__name__}: {e}")
+    if "tensor" in which:
+        full(["angled_48_minus", "offdiag_48", "angled_phi_48", "angled_64"])
     if "full" in which:
         full(["c1_64", "c1_64_minus", "c1_64_sym_pmc_pec", "strip_128_m4", "lossy_48", "c3_96", "c4_96", "nonuniform_56", "slab1d_x1", "slab1d_y1", "c4_96_axis0"])

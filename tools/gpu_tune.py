@@ -18,6 +18,10 @@ def run(name, nrep=1, **opts):
         print(f"{name:16s} {str(opts):70s} |dn| {np.abs(out[0][1]-g['n_tight']).max():.1e} op {i['op_applies']} inner {i['inner_iters']} launches {i['stencil_applies']} res {i['max_residual']:.1e} ms {i['solve_ms']:.0f}", flush=True)
     except Exception as e:
         print(name, opts, "FAILED", e, flush=True)
-for name, nrep in [("c1_64", 1), ("strip_128_m4", 1), ("c3_128", 1), ("c4_128", 1), ("headline_512_f0", 32), ("c3_512", 2)]:
-    run(name, nrep=nrep, gmres_cgs2=1)
-    run(name, nrep=nrep, gmres_cgs2=2)
+for name in ["angled_phi_48", "angled_64"]:
+    run(name)
+    run(name, inner_relax=0.0)
+    run(name, inner_relax=0.0, eig_tol=1e-11)
+    run(name, inner_relax=0.0, eig_tol=1e-11, inner_tol=1e-12)
+    run(name, inner_relax=1.0, eig_tol=1e-11, inner_tol=1e-12)
+    H.set_options(inner_relax=1.0, eig_tol=1e-9, inner_tol=1e-10)
