@@ -347,7 +347,14 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
             _trim(mat)
         v0 = _cast(initial_vector(st["nx"], st["ny"], 2), dtype)
         sigma = _cast(np.array([-(st["target"] ** 2)]), dtype)[0]
-        if basis_vecs is None:
+        has_pec = bool(np.any(np.abs(np.stack([e[0, 0], e[1, 1], e[2, 2]])) >= 0.9 * abs(PEC_VAL)))
+        if basis_vecs is None and has_pec:
+            # solver.py:467-468, 510-514, 565-566: right-Jacobi preconditioned generalized problem
+            # (mat D^-1) y = lambda D^-1 y, x = D^-1 y -- the same eigenpairs of mat
+            precon = sp.diags(1 / mat.diagonal()).tocsr()
+            vals, vecs = spl.eigs(mat @ precon, k=m_modes, sigma=sigma, tol=tol, v0=v0, M=precon)
+            vecs = precon @ vecs
+        elif basis_vecs is None:
             vals, vecs = eigs(mat, sigma, v0)
         else:  # solver_eigs_relative, solver.py:750-776: dense Rayleigh-Ritz in the span of the basis
             import scipy.linalg as sl

@@ -53,6 +53,22 @@ def _offdiag(n=48):
     return wl
 
 
+def _pec_block(n=40):
+    """Dielectric strip next to a PEC block (pec_val entries -> lossy-metal model + right-Jacobi preconditioned
+    generalized problem in the reference, solver.py:327-333, 467-468, 510-514, 565-566)."""
+    wl = W.si_strip(n, 2)
+    c = wl.coords[0]
+    ctr = 0.5 * (c[:-1] + c[1:])
+    metal = (np.abs(ctr - 0.9)[:, None] <= 0.25) & (np.abs(ctr)[None, :] <= 0.4)
+    for k in (0, 4, 8):
+        e = wl.eps_cross[k].copy()
+        e[metal] = -1e8
+        wl.eps_cross[k] = e
+    wl.mode_spec.target_neff = 2.4
+    wl.name = f"pec_block_{n}"
+    return wl
+
+
 # name: (factory, kwargs for compute_modes, store full fields?)
 CASES = {
     "c1_64": (W.c1, {}, True),
@@ -72,6 +88,7 @@ CASES = {
     "angled_48_minus": (lambda: W.angled(48), {"direction": "-"}, True),
     "angled_phi_48": (lambda: W.angled(48, theta=0.3, phi=0.7), {}, True),
     "offdiag_48": (_offdiag, {}, True),
+    "pec_block_40": (_pec_block, {}, True),
     "c2_256_f0": (lambda: W.c2(1), {}, False),
     "headline_512_f0": (lambda: W.headline(1), {}, False),
     "c3_512": (W.c3, {}, False),

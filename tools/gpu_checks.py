@@ -126,6 +126,21 @@ if __name__ == "__main__":
                 components(name, fac(), kw)
             except Exception as e:  # noqa: BLE001
                 print(f"== {name}: FAILED {type(e).__name__}: {e}")
+    if "rand" in which:
+        # the reference's own smoke test test_compute_modes (tests/test_plugins/test_mode_solver.py:170-181)
+        rs = np.random.default_rng(0)
+        eps_cross = rs.random((10, 10, 9))
+        coords = np.arange(11)
+        ms = W.ModeSpecLike(num_modes=3, target_neff=2.0, precision="single")
+        ec = [eps_cross[..., i].astype(complex) for i in range(9)]
+        try:
+            f0, n0, s0 = R.compute_modes(ec, [coords, coords], 1.0, ms, direction="-")
+            print("oracle", n0, s0)
+            out = compute_modes_batch([dict(eps_cross=ec, coords=[coords, coords], freq=1.0, mode_spec=ms, direction="-")], return_info=True)
+            print("gpu   ", out[0][0][1], out[0][0][2], out[1][0])
+        except Exception as e:  # noqa: BLE001
+            print("rand case FAILED", type(e).__name__, e)
+        full(["pec_block_40"])
     if "tensor" in which:
         full(["angled_48_minus", "offdiag_48", "angled_phi_48", "angled_64"])
     if "full" in which:
