@@ -58,13 +58,27 @@ def reference_arm(args, rank, world):
     from concurrent.futures import ProcessPoolExecutor
 
     cores = os.cpu_count() or 1
+    # Each worker holds a SuperLU factorisation of the 524288 x 524288 operator (several GB); an unbounded pool of 128
+    # workers took the GPU box down once (cgroup memory), so the pool is bounded by the container's memory limit at
+    # 8 GB per worker and by 16 workers.
+    limit = None
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v.isdigit():
+                limit = int(v)
+                break
+        except OSError:
+            pass
     try:
         import psutil
 
-        mem_cap = max(1, int(psutil.virtual_memory().available / (6 << 30)))  # ~6 GB per SuperLU factorisation
+        avail = psutil.virtual_memory().available
     except Exception:  # noqa: BLE001
-        mem_cap = 16
-    workers = max(1, min(cores, args.ref_workers or cores, mem_cap, 256))
+        avail = 64 << 30
+    budget = min(avail, limit) if limit else avail
+    mem_cap = max(1, int(0.5 * budget / (8 << 30)))
+    workers = max(1, min(cores, args.ref_workers or cores, mem_cap, 16))
     idx = np.linspace(0, 255, workers).round().astype(int)
     from tidy3d_b200 import workloads as W
 
