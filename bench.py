@@ -77,7 +77,13 @@ def reference_arm(args, rank, world):
     except Exception:  # noqa: BLE001
         avail = 64 << 30
     budget = min(avail, limit) if limit else avail
-    mem_cap = max(1, int(0.5 * budget / (8 << 30)))
+    mem_cap = max(1, int(0.6 * budget / (10 << 30)))
+    try:  # CPU quota of the container (cgroup v2 cpu.max = "quota period"); the B200 box: 16 CPUs of 128, 200 GiB
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            cores = max(1, min(cores, int(int(q) / int(per))))
+    except (OSError, ValueError):
+        pass
     workers = max(1, min(cores, args.ref_workers or cores, mem_cap, 16))
     idx = np.linspace(0, 255, workers).round().astype(int)
     from tidy3d_b200 import workloads as W
@@ -236,6 +242,12 @@ def main():
             from concurrent.futures import ProcessPoolExecutor
 
             cores = os.cpu_count() or 1
+            try:
+                q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+                if q != "max":
+                    cores = max(1, min(cores, int(int(q) / int(per))))
+            except (OSError, ValueError):
+                pass
             workers = max(1, min(cores, 8))
             idx = np.linspace(0, fps - 1, workers).round().astype(int)
             tc = time.time()
