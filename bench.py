@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- mode-solves/sec on the BASELINE.json headline workload (512x512, 4 modes, 256 freqs).
 
-A "step" is one pass of the hot path over one batch of `--freqs-per-step` frequency points (a contiguous
+A "step" is one pass of the hot path over one batch of `--freqs-per-step` (default 64) frequency points (a contiguous
 slice of the 256-point sweep C_0/linspace(1.5,1.6,256)); the sweep is sharded contiguously over ranks
 (weak scaling: every GPU gets `--freqs-per-step` problems per step, no data-path collective; the only
 collective is the final gather of n_complex).  `value` = mode-solves/s with the cross-section already resident
@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=512)
-    ap.add_argument("--freqs-per-step", type=int, default=32)
+    ap.add_argument("--freqs-per-step", type=int, default=64)
     ap.add_argument("--ref-workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stencil-only", action="store_true")
@@ -155,6 +155,7 @@ def main():
     from tidy3d_b200.solver import compute_modes_batch, get_handle
 
     h = get_handle(local)
+    h.set_options(max_batch=max(32, args.freqs_per_step))
     wl = W.headline(nf=256, n=args.n)
     fps = args.freqs_per_step
     # contiguous shard of the sweep per rank (independent problems, no exchange)
@@ -192,7 +193,7 @@ def main():
                 "apply_ms": roof["apply"][1], "bytes_per_launch": roof["apply"][2],
                 "smoother_kernel": "stencil_march_kernel<float,float,MODE_JACOBI_D> (fp32 stored-diagonal sweep, 44 B/cell)",
                 "smoother_GBps": roof["jacobi"][0], "smoother_ms": roof["jacobi"][1], "smoother_bytes_per_launch": roof["jacobi"][2],
-                "working_set": "32 problems x 512^2: vectors+coeffs 0.5 GB >> 126 MB L2"}
+                "working_set": f"{fps} problems x {args.n}^2: vectors + coefficient fields >> 126 MB L2"}
     if args.stencil_only:
         print(json.dumps(roofline))
         return

@@ -98,7 +98,7 @@ typedef struct {
   int mg_nu;             /* Jacobi pre/post sweeps (default 2) */
   int mg_min_size;       /* stop coarsening below this many cells per axis (default 12) */
   int mg_coarse_iters;   /* Krylov iterations on the coarsest level (default 16) */
-  int max_batch;         /* problems solved concurrently on the device (default 32) */
+  int max_batch;         /* problems solved concurrently on the device (default 64: 5120 CTAs of the fp64 apply = 4.94 waves on 148 SMs) */
   double mg_omega;       /* Jacobi damping (default 0.8) */
   double mg_ppw;         /* indefinite problems: keep >= this many cells per local wavelength (default 4) */
   int verbose;

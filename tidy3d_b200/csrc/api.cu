@@ -39,7 +39,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->mg_nu = 2;
   o->mg_min_size = 12;
   o->mg_coarse_iters = 16;
-  o->max_batch = 32;
+  o->max_batch = 64;
   o->mg_omega = 0.8;
   o->mg_ppw = 4.0;
   o->verbose = 0;
