@@ -186,7 +186,10 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = roof["apply"][0]
-    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 464.8e6,  # dram read+write bytes per launch, ncu --set full, profiles/r01_stencil_apply_ncu.txt
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                # dram read+write bytes per launch from one ncu --set full capture (profiles/r01_stencil_apply_b64_ncu.txt:
+                # 955.3 MB at 64 x 512^2 = 56.94 B per cell), scaled to this launch's cell count
+                "traffic": 56.94 * fps * args.n * args.n,
                
                 "kernel": "stencil_march_kernel<double,double,MODE_APPLY> (fp64 operator apply y=(A-sigma)x, 56 B/cell)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
