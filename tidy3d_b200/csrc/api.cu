@@ -48,6 +48,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->mg_precision = 1;
   o->mg_cycles = 1;
   o->use_graph = 1;
+  o->mg_nu_growth = 0;
   o->gmres_cgs2 = 2;
   o->inner_relax = 1.0;
   o->inner_relax_cap = 1e-4;

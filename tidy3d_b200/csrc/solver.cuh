@@ -618,7 +618,7 @@ class BatchSolver {
   void vcycle(int l, const P *rin, P *out) {
     Level &v = lv[l];
     const int L = (int)lv.size();
-    const int nu = std::max(1, opt_.mg_nu);
+    const int nu = std::max(1, opt_.mg_nu + l * opt_.mg_nu_growth);  // optional variable V-cycle: more sweeps on coarser levels
     P *cur = v.x, *oth = v.tmp;
     auto sweep = [&](P *dst) {  // dst = jacobi(cur)
       apply(l, MODE_JACOBI, cur, rin, dst);

@@ -18,10 +18,10 @@ def run(name, nrep=1, **opts):
         print(f"{name:16s} {str(opts):70s} |dn| {np.abs(out[0][1]-g['n_tight']).max():.1e} op {i['op_applies']} inner {i['inner_iters']} launches {i['stencil_applies']} res {i['max_residual']:.1e} ms {i['solve_ms']:.0f}", flush=True)
     except Exception as e:
         print(name, opts, "FAILED", e, flush=True)
-for name in ["angled_phi_48", "angled_64"]:
-    run(name)
-    run(name, inner_relax=0.0)
-    run(name, inner_relax=0.0, eig_tol=1e-11)
-    run(name, inner_relax=0.0, eig_tol=1e-11, inner_tol=1e-12)
-    run(name, inner_relax=1.0, eig_tol=1e-11, inner_tol=1e-12)
-    H.set_options(inner_relax=1.0, eig_tol=1e-9, inner_tol=1e-10)
+for name, nrep in [("headline_512_f0", 32), ("c3_512", 2), ("strip_128_m4", 1)]:
+    run(name, nrep=nrep, mg_nu_growth=0)
+    run(name, nrep=nrep, mg_nu_growth=1)
+    run(name, nrep=nrep, mg_nu_growth=2)
+    run(name, nrep=nrep, mg_nu_growth=0, mg_omega=0.9)
+    run(name, nrep=nrep, mg_nu_growth=0, mg_omega=0.7)
+    H.set_options(mg_omega=0.8, mg_nu_growth=0)
