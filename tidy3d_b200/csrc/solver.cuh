@@ -79,10 +79,6 @@ template <> inline cplxf from_cd<cplxf>(cd v) { return mkf((float)v.real(), (flo
 template <> inline cd to_cd<float>(float v) { return cd(v, 0.0); }
 template <> inline cd to_cd<cplxf>(cplxf v) { return cd(v.re, v.im); }
 
-struct TransferDevStore {
-  Transfer1DDev d;
-};
-
 // ------------------------------------------------------------------------------------------------------
 // T / C: Krylov vector and coefficient-field types (fp64).  P / PC: the same for the multigrid preconditioner,
 // either identical (all fp64) or their fp32 twins (mixed precision: the V-cycle moves half the bytes).
