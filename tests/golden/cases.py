@@ -69,6 +69,26 @@ def _pec_block(n=40):
     return wl
 
 
+def _lossy_angled(n=40):
+    """Lossy core + angled waveguide: the tensorial_complex branch (solver.py:382-384, 669-670)."""
+    wl = W.angled(n, theta=0.25, phi=0.4, num_modes=3)
+    wl.eps_cross = [e * (1 + 0.02j) for e in wl.eps_cross]
+    wl.name = f"lossy_angled_{n}"
+    return wl
+
+
+def _angle_bend(n=44):
+    """Angle + bend + PML + a PEC/PMC symmetry pair, after the reference's test_mode_solver_angle_bend
+    (tests/test_plugins/test_mode_solver.py:606-645)."""
+    wl = W.angled(n, theta=np.pi / 6, phi=np.pi, num_modes=3)
+    wl.mode_spec.bend_radius = 3.0
+    wl.mode_spec.bend_axis = 0
+    wl.mode_spec.num_pml = (0, 6)
+    wl.mode_spec.target_neff = 2.6
+    wl.name = f"angle_bend_{n}"
+    return wl
+
+
 # name: (factory, kwargs for compute_modes, store full fields?)
 CASES = {
     "c1_64": (W.c1, {}, True),
@@ -89,6 +109,9 @@ CASES = {
     "angled_phi_48": (lambda: W.angled(48, theta=0.3, phi=0.7), {}, True),
     "offdiag_48": (_offdiag, {}, True),
     "pec_block_40": (_pec_block, {}, True),
+    "lossy_angled_40": (_lossy_angled, {}, True),
+    "lossy_angled_40_minus": (_lossy_angled, {"direction": "-"}, True),
+    "angle_bend_44": (_angle_bend, {"symmetry": (-1, 0)}, True),
     "c2_256_f0": (lambda: W.c2(1), {}, False),
     "headline_512_f0": (lambda: W.headline(1), {}, False),
     "c3_512": (W.c3, {}, False),

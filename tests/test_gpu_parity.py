@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 SMALL = ["c1_64", "c1_64_minus", "c1_64_sym_pmc_pec", "lossy_48", "nonuniform_56", "slab1d_x1", "slab1d_y1",
          "c3_96", "c4_96", "c4_96_axis0", "strip_128_m4", "c3_128", "c4_128",
-         "angled_64", "angled_48_minus", "angled_phi_48", "offdiag_48", "pec_block_40"]  # fmt: skip
+         "angled_64", "angled_48_minus", "angled_phi_48", "offdiag_48", "pec_block_40", "lossy_angled_40", "lossy_angled_40_minus", "angle_bend_44"]  # fmt: skip
 LARGE = ["c2_256_f0", "headline_512_f0", "c3_512", "c4_512"]
 
 
