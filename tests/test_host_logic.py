@@ -22,6 +22,29 @@ def test_abi_exports_every_declared_symbol(built_lib):
     assert L.b200ms_version() == 100
 
 
+def test_ctypes_structs_mirror_the_header(built_lib):
+    """Field order of the three ABI structs in include/b200ms.h == the ctypes mirrors (a silent mismatch would
+    scramble options or results)."""
+    import os
+
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "b200ms.h")).read()
+
+    def fields(struct_name):
+        body = hdr[: hdr.index("} " + struct_name + ";")]
+        body = body[body.rindex("typedef struct {") :]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            m = re.search(r"(?:const\s+)?(?:double|int)\s*\*?\s*([a-z_0-9,\s\*\[\]]+)$", decl.strip())
+            if m:
+                for part in m.group(1).split(","):
+                    names.append(re.sub(r"[\*\s]|\[\d+\]", "", part))
+        return names
+
+    for name, cls in (("b200ms_problem", built_lib.Problem), ("b200ms_result", built_lib.Result), ("b200ms_options", built_lib.Options)):
+        assert fields(name) == [f[0] for f in cls._fields_], name
+
+
 def test_no_cpu_fallback_without_gpu(built_lib):
     import torch
 
