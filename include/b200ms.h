@@ -64,6 +64,8 @@ typedef struct {
                             each component C-order with y fastest (solver.py:890-901) */
   const double *coords_x; /* nx+1 */
   const double *coords_y; /* ny+1 */
+  const double *mu;      /* NULL (identity), or the relative permeability `mu_cross` (solver.py:62-66, 128-136) in the same
+                            9*nx*ny complex128 layout as eps */
   const double *basis_e; /* NULL, or the in-plane E part of `solver_basis_fields` (solver.py:219-236, 750-776):
                             2*nx*ny*num_modes complex128 (re,im) laid out [Ex|Ey][ix][iy][mode]; the modes are then
                             computed as linear combinations of this basis (relative mode solver) */

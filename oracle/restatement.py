@@ -307,9 +307,17 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
                   symmetry=(0, 0), direction="+", solver_basis_fields=None, tol=FP_EPS, info=None):  # fmt: skip
     """Restatement of ``compute_modes`` (solver.py:33-269, 941).  ``tol`` defaults to the
     reference's ARPACK tolerance (solver.py:20); tests pass 1e-12 for a tight oracle.
-    ``split_curl_scaling`` is not restated."""
-    if split_curl_scaling is not None:
-        raise NotImplementedError("oracle: split-curl not restated")
+    the PEC incidence-matrix variant of ``mu_cross`` / ``split_curl_scaling`` (solver.py:441-449) is not restated."""
+    if split_curl_scaling is not None:  # solver.py:122-124
+        eps_cross = [np.array(eps_cross[i], dtype=complex, copy=True) for i in range(9)]
+        for comp, idx in enumerate((0, 4, 8)):
+            sc = np.asarray(split_curl_scaling[comp])
+            outside = ~np.isclose(sc, 0)
+            eps_cross[idx][outside] /= sc[outside]
+    if (split_curl_scaling is not None or mu_cross is not None) and any(
+        np.any(np.abs(np.asarray(eps_cross[i])) >= 0.9 * abs(PEC_VAL)) for i in (0, 4, 8)
+    ):
+        raise NotImplementedError("oracle: incidence matrices for PEC cells (solver.py:441-449) not restated")
     st = setup(eps_cross, coords, freq, mode_spec, symmetry, mu_cross)
     n, m_modes = st["n"], mode_spec.num_modes
     basis_vecs = None
@@ -408,6 +416,10 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
 
     # back to the original axes, E = J^T E' (solver.py:254-259)
     efield = np.einsum("ijn,inm->jnm", st["jac_e"], efield)
+    if split_curl_scaling is not None:  # solver.py:904-919
+        sc = np.asarray(split_curl_scaling).reshape(3, -1)
+        outside = ~np.isclose(sc, 0)
+        efield = efield / np.where(outside, sc, 1.0)[:, :, None] * outside[:, :, None]
     hfield = np.einsum("ijn,inm->jnm", st["jac_h"], hfield)
     shape = (3, st["nx"], st["ny"], 1, m_modes)
     fields = np.stack((efield.reshape(shape), hfield.reshape(shape)))

@@ -89,6 +89,24 @@ def _angle_bend(n=44):
     return wl
 
 
+def _mu_and_split(n=40):
+    """Magnetic cladding (mu_cross) and a split-curl scaling profile: the two optional inputs of compute_modes
+    (solver.py:62-72) that the reference's own ModeSolver never passes."""
+    wl = W.si_strip(n, 2)
+    c = wl.coords[0]
+    ctr = 0.5 * (c[:-1] + c[1:])
+    X, Y = np.meshgrid(ctr, ctr, indexing="ij")
+    mu = [np.zeros((n, n), complex) for _ in range(9)]
+    mu[0] = 1.0 + 0.3 * (Y < -0.5) + 0j
+    mu[4] = 1.0 + 0.2 * (Y < -0.5) + 0j
+    mu[8] = 1.0 + 0.1 * (Y < -0.5) + 0j
+    split = np.stack([1.0 + 0.1 * np.exp(-(X**2 + Y**2)), 1.0 + 0.05 * np.exp(-(X**2 + Y**2)), 1.0 - 0.05 * np.exp(-(X**2 + Y**2))])
+    wl.extra["mu_cross"] = mu
+    wl.extra["split_curl_scaling"] = split
+    wl.name = f"mu_split_{n}"
+    return wl
+
+
 # name: (factory, kwargs for compute_modes, store full fields?)
 CASES = {
     "c1_64": (W.c1, {}, True),
@@ -109,6 +127,8 @@ CASES = {
     "angled_phi_48": (lambda: W.angled(48, theta=0.3, phi=0.7), {}, True),
     "offdiag_48": (_offdiag, {}, True),
     "pec_block_40": (_pec_block, {}, True),
+    "mu_cross_40": (_mu_and_split, {"mu_cross": "extra"}, True),
+    "split_curl_40": (_mu_and_split, {"split_curl_scaling": "extra"}, True),
     "lossy_angled_40": (_lossy_angled, {}, True),
     "lossy_angled_40_minus": (_lossy_angled, {"direction": "-"}, True),
     "angle_bend_44": (_angle_bend, {"symmetry": (-1, 0)}, True),
@@ -131,3 +151,8 @@ def _axis0(wl):
     wl.mode_spec.bend_axis = 0
     wl.name += "_axis0"
     return wl
+
+
+def resolve_kwargs(wl, kw):
+    """Replace the marker "extra" by the array stored on the workload (mu_cross / split_curl_scaling cases)."""
+    return {k: (wl.extra[k] if isinstance(v, str) and v == "extra" else v) for k, v in kw.items()}

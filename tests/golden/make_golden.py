@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import ref_shim  # noqa: E402
-from tests.golden.cases import CASES  # noqa: E402
+from tests.golden.cases import CASES, resolve_kwargs  # noqa: E402
 
 
 def signature(fields):
@@ -29,6 +29,7 @@ def signature(fields):
 def run(name):
     factory, kw, store = CASES[name]
     wl = factory()
+    kw = resolve_kwargs(wl, kw)
     ref = ref_shim.load()
     out = {}
     for tag, tol in (("ref", None), ("tight", 1e-12)):

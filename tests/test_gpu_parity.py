@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import restatement as R
-from tests.golden.cases import CASES
+from tests.golden.cases import CASES, resolve_kwargs
 from tests.helpers import N_TOL, OVERLAP_MIN, load_golden, mode_overlaps
 from tidy3d_b200 import compute_modes, compute_modes_batch
 from tidy3d_b200 import workloads as W
@@ -13,13 +13,15 @@ pytestmark = pytest.mark.gpu
 
 SMALL = ["c1_64", "c1_64_minus", "c1_64_sym_pmc_pec", "lossy_48", "nonuniform_56", "slab1d_x1", "slab1d_y1",
          "c3_96", "c4_96", "c4_96_axis0", "strip_128_m4", "c3_128", "c4_128",
-         "angled_64", "angled_48_minus", "angled_phi_48", "offdiag_48", "pec_block_40", "lossy_angled_40", "lossy_angled_40_minus", "angle_bend_44"]  # fmt: skip
+         "angled_64", "angled_48_minus", "angled_phi_48", "offdiag_48", "pec_block_40", "lossy_angled_40", "lossy_angled_40_minus", "angle_bend_44",
+         "mu_cross_40", "split_curl_40"]  # fmt: skip
 LARGE = ["c2_256_f0", "headline_512_f0", "c3_512", "c4_512"]
 
 
 def _solve(name, **opts):
     fac, kw, _ = CASES[name]
     wl = fac()
+    kw = resolve_kwargs(wl, kw)
     out, info = compute_modes_batch(
         [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], return_info=True
     )
@@ -172,11 +174,12 @@ def test_edge_shapes_and_mode_counts():
 
 
 def test_unsupported_paths_fail_loudly():
-    wl = W.c1()
+    """PEC cells together with mu_cross / split_curl_scaling (incidence matrices, solver.py:441-449) are not built."""
+    fac, kw, _ = CASES["pec_block_40"]
+    wl = fac()
+    ones = np.ones((3,) + wl.eps_cross[0].shape)
     with pytest.raises(NotImplementedError):
-        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, mu_cross=wl.eps_cross)
-    with pytest.raises(NotImplementedError):
-        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, split_curl_scaling=wl.eps_cross[:3])
+        compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, split_curl_scaling=ones)
 
 
 def test_full_size_properties_headline_batch():

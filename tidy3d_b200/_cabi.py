@@ -30,7 +30,7 @@ class Problem(C.Structure):
         ("symmetry", C.c_int * 2), ("bend_axis", C.c_int), ("direction", C.c_int), ("precision", C.c_int),
         ("freq", C.c_double), ("target_neff", C.c_double), ("bend_radius", C.c_double),
         ("angle_theta", C.c_double), ("angle_phi", C.c_double),
-        ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp), ("basis_e", _dp),
+        ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp), ("mu", _dp), ("basis_e", _dp),
     ]  # fmt: skip
 
 
@@ -103,7 +103,8 @@ def _ptr(a):
 class PackedProblem:
     """Owns the contiguous arrays a ``Problem`` struct points to."""
 
-    def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None, basis_fields=None):
+    def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None, basis_fields=None,
+                 mu_cross=None):
         if eps_packed is not None:
             eps = eps_packed
         else:
@@ -142,6 +143,18 @@ class PackedProblem:
         p.angle_theta = float(getattr(mode_spec, "angle_theta", 0.0))
         p.angle_phi = float(getattr(mode_spec, "angle_phi", 0.0))
         p.eps, p.coords_x, p.coords_y = _ptr(self.eps.view(np.float64)), _ptr(self.cx), _ptr(self.cy)
+        self.mu = None
+        if mu_cross is not None:
+            if isinstance(mu_cross, np.ndarray):
+                mcomps = [mu_cross[i] for i in range(9)]
+            else:
+                if len(mu_cross) != 9:
+                    raise ValueError("Wrong input to mode solver pemittivity/permeability!")
+                mcomps = list(mu_cross)
+            self.mu = np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.complex128) for c in mcomps]))
+            if self.mu.shape != self.eps.shape:
+                raise ValueError("Wrong input to mode solver pemittivity/permeability!")
+            p.mu = _ptr(self.mu.view(np.float64))
         self.basis = None
         if basis_fields is not None:
             try:  # solver.py:222-230

@@ -118,12 +118,12 @@ struct GroupKey {
   }
 };
 struct MediumKey {
-  const double *eps, *cx, *cy;
+  const double *eps, *mu, *cx, *cy;
   int nx, ny, k, p0, p1, s0, s1, bend_axis, dir;
   double bend_radius, target, theta, phi;
   bool operator==(const MediumKey &o) const {
     auto same = [](double a, double b) { return (std::isnan(a) && std::isnan(b)) || a == b; };
-    return eps == o.eps && cx == o.cx && cy == o.cy && nx == o.nx && ny == o.ny && k == o.k && p0 == o.p0 && p1 == o.p1 &&
+    return eps == o.eps && mu == o.mu && cx == o.cx && cy == o.cy && nx == o.nx && ny == o.ny && k == o.k && p0 == o.p0 && p1 == o.p1 &&
            s0 == o.s0 && s1 == o.s1 && bend_axis == o.bend_axis && dir == o.dir && same(bend_radius, o.bend_radius) &&
            same(target, o.target) && theta == o.theta && phi == o.phi;
   }
@@ -140,7 +140,7 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
   for (int b = 0; b < B; ++b) {
     ps[b] = &setups[ids[b]];
     const b200ms_problem &p = prob[ids[b]], &p0 = prob[ids[0]];
-    if (p.eps != p0.eps || p.coords_x != p0.coords_x || p.coords_y != p0.coords_y ||
+    if (p.eps != p0.eps || p.mu != p0.mu || p.coords_x != p0.coords_x || p.coords_y != p0.coords_y ||
         !((std::isnan(p.bend_radius) && std::isnan(p0.bend_radius)) || p.bend_radius == p0.bend_radius) ||
         p.bend_axis != p0.bend_axis)
       share = false;
@@ -275,7 +275,7 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
         res[i].status = B200MS_ERR_ARG;
       } else {
         // a sweep over one cross-section sets the medium up once (pointer equality == identical content)
-        MediumKey mk{prob[i].eps, prob[i].coords_x, prob[i].coords_y, prob[i].nx, prob[i].ny, prob[i].num_modes,
+        MediumKey mk{prob[i].eps, prob[i].mu, prob[i].coords_x, prob[i].coords_y, prob[i].nx, prob[i].ny, prob[i].num_modes,
                      prob[i].num_pml[0], prob[i].num_pml[1], prob[i].symmetry[0], prob[i].symmetry[1], prob[i].bend_axis,
                      prob[i].direction, prob[i].bend_radius, prob[i].target_neff, prob[i].angle_theta, prob[i].angle_phi};
         auto it = std::find_if(seen.begin(), seen.end(), [&](const std::pair<MediumKey, int> &e) { return e.first == mk; });

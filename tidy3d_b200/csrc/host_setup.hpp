@@ -101,7 +101,8 @@ inline void sfactors(double omega, const std::vector<double> &dlf, const std::ve
 
 // eps' = J eps J^T / det J and mu' = J J^T / det J (mu = identity) at one cell, for J = [[1,0,a],[0,1,b],[0,0,d]]
 // (angled transform followed by the bend, solver.py:142-172; d differs between E and H sites for a bend)
-inline void transformed_tensors(const cd *eps, size_t n, size_t c, double a, double b, double d_e, double d_h, cd e[9], cd m[9]) {
+inline void transformed_tensors(const cd *eps, const cd *mu, size_t n, size_t c, double a, double b, double d_e, double d_h, cd e[9],
+                                cd m[9]) {
   cd raw[9];
   for (int k = 0; k < 9; ++k) raw[k] = eps[(size_t)k * n + c];
   const double Je[3][3] = {{1, 0, a}, {0, 1, b}, {0, 0, d_e}}, Jh[3][3] = {{1, 0, a}, {0, 1, b}, {0, 0, d_h}};
@@ -118,10 +119,26 @@ inline void transformed_tensors(const cd *eps, size_t n, size_t c, double a, dou
       for (int j = 0; j < 3; ++j) acc += tmp[3 * i + j] * Je[p2][j];
       e[3 * i + p2] = acc / d_e;
     }
+  if (!mu) {
+    for (int i = 0; i < 3; ++i)
+      for (int p2 = 0; p2 < 3; ++p2) {
+        double acc = 0.0;
+        for (int j = 0; j < 3; ++j) acc += Jh[i][j] * Jh[p2][j];
+        m[3 * i + p2] = acc / d_h;
+      }
+    return;
+  }
+  for (int k = 0; k < 9; ++k) raw[k] = mu[(size_t)k * n + c];
   for (int i = 0; i < 3; ++i)
     for (int p2 = 0; p2 < 3; ++p2) {
-      double acc = 0.0;
-      for (int j = 0; j < 3; ++j) acc += Jh[i][j] * Jh[p2][j];
+      cd acc = 0.0;
+      for (int j = 0; j < 3; ++j) acc += Jh[i][j] * raw[3 * j + p2];
+      tmp[3 * i + p2] = acc;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int p2 = 0; p2 < 3; ++p2) {
+      cd acc = 0.0;
+      for (int j = 0; j < 3; ++j) acc += tmp[3 * i + j] * Jh[p2][j];
       m[3 * i + p2] = acc / d_h;
     }
 }
@@ -188,6 +205,8 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
   }
   const size_t n = (size_t)nx * ny;
   const cd *eps = reinterpret_cast<const cd *>(p.eps);
+  const cd *mu_in = reinterpret_cast<const cd *>(p.mu);
+  if (mu_in) s.has_mu = true;
   const double omega = 2.0 * M_PI * p.freq;
   s.k0 = omega / kC0;
   const bool bend = !std::isnan(p.bend_radius);
@@ -264,7 +283,7 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
         d_h = dh[t];
       }
       cd e[9], m[9];
-      transformed_tensors(eps, n, c, s.jac_a, s.jac_b, d_e, d_h, e, m);
+      transformed_tensors(eps, mu_in, n, c, s.jac_a, s.jac_b, d_e, d_h, e, m);
       (*F[0])[c] = e[0];
       (*F[1])[c] = e[4];
       (*F[2])[c] = e[8];
@@ -325,7 +344,7 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
       }
       const double d_h2 = bend ? dh[norm_axis == 0 ? ix : iy] : 1.0;
       cd et[9], mt[9];
-      transformed_tensors(eps, n, c, s.jac_a, s.jac_b, d_e, d_h2, et, mt);
+      transformed_tensors(eps, mu_in, n, c, s.jac_a, s.jac_b, d_e, d_h2, et, mt);
       for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) {
           if (a == b) continue;
@@ -370,7 +389,7 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
         const size_t c = (size_t)ix * ny + iy;
         const double d_e = bend ? de[norm_axis == 0 ? ix : iy] : 1.0, d_h2 = bend ? dh[norm_axis == 0 ? ix : iy] : 1.0;
         cd et[9], mt[9];
-        transformed_tensors(eps, n, c, s.jac_a, s.jac_b, d_e, d_h2, et, mt);
+        transformed_tensors(eps, mu_in, n, c, s.jac_a, s.jac_b, d_e, d_h2, et, mt);
         for (int q = 0; q < 9; ++q)
           if (is_pec(et[q])) et[q] = pec_model;
         const cd *tt[2] = {et, mt};

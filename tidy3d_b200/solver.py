@@ -6,8 +6,8 @@
     fields, n_complex, eps_spec = compute_modes(eps_cross, coords, freq, mode_spec, symmetry=..., direction=...)
 
 ``fields`` has shape ``(2, 3, Nx, Ny, 1, num_modes)`` (E/H, component, x, y, 1, mode), ``n_complex`` is
-``n_eff + 1j*k_eff`` sorted by descending ``n_eff`` and ``eps_spec`` is ``"diagonal"`` (tensorial cross-sections
-raise ``NotImplementedError`` for now).  ``compute_modes_batch`` is the batched entry point that corresponds to the
+``n_eff + 1j*k_eff`` sorted by descending ``n_eff`` and ``eps_spec`` is ``"diagonal"``, ``"tensorial_real"`` or
+``"tensorial_complex"``.  ``compute_modes_batch`` is the batched entry point that corresponds to the
 frequency loop of ``ModeSolver._solve_all_freqs`` (tidy3d/plugins/mode/mode_solver.py:655-672): all problems are
 solved concurrently on the GPU.
 """
@@ -47,9 +47,41 @@ def _raise_for(rc: int, handle, where=""):
         raise RuntimeError(f"tidy3d_b200: error {rc}: {msg}")
 
 
-def _check_unsupported(mu_cross, split_curl_scaling, solver_basis_fields):
-    if mu_cross is not None or split_curl_scaling is not None:
-        raise NotImplementedError("tidy3d_b200: mu_cross / split_curl_scaling (solver.py:93) are not built yet")
+PEC_VAL = -1e8  # tidy3d/constants.py
+
+
+def _has_pec(eps_cross) -> bool:
+    return any(bool(np.any(np.abs(np.asarray(eps_cross[i])) >= 0.9 * abs(PEC_VAL))) for i in (0, 4, 8))
+
+
+def _check_unsupported(eps_cross, mu_cross, split_curl_scaling):
+    """``mu_cross`` / ``split_curl_scaling`` switch the reference to its incidence-matrix formulation (solver.py:93,
+    441-449, 474-477, 506-508), which only differs from the plain one when PEC-valued cells are present: that
+    combination is not built."""
+    if (mu_cross is not None or split_curl_scaling is not None) and _has_pec(eps_cross):
+        raise NotImplementedError(
+            "tidy3d_b200: mu_cross / split_curl_scaling together with PEC-valued permittivity (incidence matrices, "
+            "solver.py:441-449) is not built"
+        )
+
+
+def _apply_split_curl(eps_cross, split):
+    """solver.py:122-124: eps_rr -> eps_rr / scaling_r outside PEC (scaling == 0 marks PEC)."""
+    eps = [np.array(eps_cross[i], dtype=np.complex128, copy=True) for i in range(9)]
+    for comp, idx in enumerate((0, 4, 8)):
+        sc = np.asarray(split[comp])
+        outside = ~np.isclose(sc, 0)
+        eps[idx][outside] /= sc[outside]
+    return eps
+
+
+def _undo_split_curl(fields, split):
+    """solver.py:904-919 applied to the packed (2,3,Nx,Ny,1,M) array: E -> E / scaling, zero inside PEC."""
+    split = np.asarray(split)
+    outside = ~np.isclose(split, 0)
+    scale = np.where(outside, split, 1.0)
+    fields[0] = fields[0] / scale[:, :, :, None, None] * outside[:, :, :, None, None]
+    return fields
 
 
 def compute_modes_batch(
@@ -62,16 +94,21 @@ def compute_modes_batch(
     Returns a list of ``(fields, n_complex, eps_spec)`` tuples (``fields`` is None when ``want_fields=False``),
     plus a list of per-problem info dicts when ``return_info``.
     """
-    h = handle or get_handle(device)
     packed, cache = [], {}
     for p in problems:
-        _check_unsupported(p.get("mu_cross"), p.get("split_curl_scaling"), p.get("solver_basis_fields"))
+        split = p.get("split_curl_scaling")
+        _check_unsupported(p["eps_cross"], p.get("mu_cross"), split)
+        if split is not None and p.get("solver_basis_fields") is not None:
+            raise RuntimeError("Split curl not yet implemented for relative mode solver.")  # solver.py:938
         key = id(p["eps_cross"])
+        eps_in = _apply_split_curl(p["eps_cross"], split) if split is not None else p["eps_cross"]
         pk = _cabi.PackedProblem(
-            p["eps_cross"], p["coords"], p["freq"], p["mode_spec"], p.get("symmetry", (0, 0)), p.get("direction", "+"),
-            eps_packed=cache.get(key), basis_fields=p.get("solver_basis_fields"),
+            eps_in, p["coords"], p["freq"], p["mode_spec"], p.get("symmetry", (0, 0)), p.get("direction", "+"),
+            eps_packed=None if split is not None else cache.get(key), basis_fields=p.get("solver_basis_fields"),
+            mu_cross=p.get("mu_cross"),
         )  # fmt: skip
-        cache[key] = pk.eps
+        if split is None:
+            cache[key] = pk.eps
         if key in cache and len(packed) and packed[-1].eps is pk.eps:
             # share the coordinate arrays too so the library can detect identical cross-sections
             prev = packed[-1]
@@ -79,6 +116,7 @@ def compute_modes_batch(
                 pk.cx, pk.cy = prev.cx, prev.cy
                 pk.struct.coords_x, pk.struct.coords_y = prev.struct.coords_x, prev.struct.coords_y
         packed.append(pk)
+    h = handle or get_handle(device)  # after input validation: argument errors do not need a GPU
     rc, fields, ncs, results = h.solve_batch(packed, want_fields)
     if rc != _cabi.OK:
         bad = [i for i in range(len(packed)) if results[i].status != _cabi.OK]
@@ -86,6 +124,8 @@ def compute_modes_batch(
     out, infos = [], []
     for i, pk in enumerate(packed):
         f = fields[i] if want_fields else None
+        if f is not None and problems[i].get("split_curl_scaling") is not None:
+            f = _undo_split_curl(f, problems[i]["split_curl_scaling"])
         if f is not None and pk.struct.precision == 1:
             f = f.astype(np.complex64)  # solver.py:265-267
         out.append((f, ncs[i], _cabi.SPEC_NAMES[results[i].eps_spec]))
@@ -110,8 +150,7 @@ def compute_modes(
     solver_basis_fields=None,
 ) -> Tuple[np.ndarray, np.ndarray, str]:
     """Drop-in for ``tidy3d.plugins.mode.solver.compute_modes`` (solver.py:941)."""
-    _check_unsupported(mu_cross, split_curl_scaling, solver_basis_fields)
     return compute_modes_batch(
         [dict(eps_cross=eps_cross, coords=coords, freq=freq, mode_spec=mode_spec, symmetry=symmetry, direction=direction,
-              solver_basis_fields=solver_basis_fields)]
+              solver_basis_fields=solver_basis_fields, mu_cross=mu_cross, split_curl_scaling=split_curl_scaling)]
     )[0]
