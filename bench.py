@@ -147,7 +147,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__ as g
 
-    g.build()
+    if rank == 0:
+        g.build()  # no-op when the in-tree library is up to date; never let N ranks rebuild the same file at once
+    if world > 1:
+        dist.barrier()
     import ctypes as C
 
     from tidy3d_b200 import _cabi
