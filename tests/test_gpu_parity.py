@@ -125,6 +125,16 @@ def test_mixed_batch_groups_and_ragged_inputs():
         assert np.abs(n - nref).max() < 1e-8
 
 
+def test_n_complex_only_mode():
+    """want_fields=False: only n_complex is produced (no epilogue kernel, no field transfer)."""
+    wl = W.c1()
+    probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=f, mode_spec=wl.mode_spec) for f in (wl.freqs[0], 1.02 * wl.freqs[0])]
+    out = compute_modes_batch(probs, want_fields=False)
+    assert out[0][0] is None and out[0][2] == "diagonal"
+    assert np.abs(out[0][1] - load_golden("c1_64")["n_tight"]).max() < 1e-8
+    assert out[1][1][0].real > out[0][1][0].real  # higher frequency -> larger n_eff
+
+
 def test_direction_and_precision_contract():
     wl = W.c1()
     fp, n_p, _ = compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, direction="+")
