@@ -48,6 +48,12 @@ def _clock_summary(samples):
             "reasons": reasons, "samples": len(samples)}
 
 
+def bench_config(args, world):
+    """The `config` object shared by both arms (the driver compares them)."""
+    return {"workload": f"headline Si strip {args.n}x{args.n}, num_modes=4, {args.freqs_per_step} freqs/step/GPU of the 256-pt sweep 1.5-1.6um",
+            "l2": "inputs larger than L2 (per-step working set > 10 GB)", "parallelism": f"freq-shard x{world}"}
+
+
 def reference_arm(args, rank, world):
     """CPU arm: the reference algorithm (oracle restatement == the reference's scipy ARPACK + SuperLU call,
     solver.py:744; the reference is pure Python and not installable here) on all host cores, on a bounded
@@ -99,7 +105,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": "mode-solves/sec (512x512, 4 modes, 256 freqs)", "value": val, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 0, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"headline Si strip {args.n}x{args.n}, num_modes=4, sweep 1.5-1.6um (256 freqs)"},
+        "config": bench_config(args, world),
         "cpu_baseline": {"value": val, "unit": "solves/s", "cores": workers, "kind": "port",
                          "sample": f"{len(idx)} of the 256 frequencies in one concurrent round ({-(-len(idx) // steps)} per step), one "
                                    f"per worker process, scipy eigs (ARPACK+SuperLU, tol=fp_eps) via oracle/restatement.py, {dt:.1f} s wall"},
@@ -270,8 +276,7 @@ def main():
             "metric": "mode-solves/sec (512x512, 4 modes, 256 freqs)", "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"headline Si strip {args.n}x{args.n}, num_modes=4, {fps} freqs/step/GPU of the 256-pt sweep 1.5-1.6um",
-                       "l2": "inputs larger than L2 (per-step working set > 10 GB)", "parallelism": f"freq-shard x{world}"},
+            "config": bench_config(args, world),
             "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "lib_wall_ms_per_step": lib_ms / args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "clocks": _clock_summary(samples),
