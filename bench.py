@@ -65,8 +65,8 @@ def reference_arm(args, rank, world):
 
     cores = os.cpu_count() or 1
     # Each worker holds a SuperLU factorisation of the 524288 x 524288 operator (several GB); an unbounded pool of 128
-    # workers took the GPU box down once (cgroup memory), so the pool is bounded by the container's memory limit at
-    # 8 GB per worker and by 16 workers.
+    # workers took the GPU box down once (cgroup memory limit 200 GiB), so the pool is bounded by the container's memory
+    # limit at 4 GB per worker, by its CPU quota and by 16 workers.
     limit = None
     for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
         try:
@@ -83,7 +83,7 @@ def reference_arm(args, rank, world):
     except Exception:  # noqa: BLE001
         avail = 64 << 30
     budget = min(avail, limit) if limit else avail
-    mem_cap = max(1, int(0.6 * budget / (10 << 30)))
+    mem_cap = max(1, int(0.6 * budget / (4 << 30)))  # measured peak RSS of one 512x512 solve: 2.5 GB
     try:  # CPU quota of the container (cgroup v2 cpu.max = "quota period"); the B200 box: 16 CPUs of 128, 200 GiB
         q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
         if q != "max":
