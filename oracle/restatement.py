@@ -307,17 +307,15 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
                   symmetry=(0, 0), direction="+", solver_basis_fields=None, tol=FP_EPS, info=None):  # fmt: skip
     """Restatement of ``compute_modes`` (solver.py:33-269, 941).  ``tol`` defaults to the
     reference's ARPACK tolerance (solver.py:20); tests pass 1e-12 for a tight oracle.
-    the PEC incidence-matrix variant of ``mu_cross`` / ``split_curl_scaling`` (solver.py:441-449) is not restated."""
+    the incidence-matrix variant used with ``mu_cross`` / ``split_curl_scaling`` (solver.py:441-449) is restated too
+    (the product does not build it yet)."""
     if split_curl_scaling is not None:  # solver.py:122-124
         eps_cross = [np.array(eps_cross[i], dtype=complex, copy=True) for i in range(9)]
         for comp, idx in enumerate((0, 4, 8)):
             sc = np.asarray(split_curl_scaling[comp])
             outside = ~np.isclose(sc, 0)
             eps_cross[idx][outside] /= sc[outside]
-    if (split_curl_scaling is not None or mu_cross is not None) and any(
-        np.any(np.abs(np.asarray(eps_cross[i])) >= 0.9 * abs(PEC_VAL)) for i in (0, 4, 8)
-    ):
-        raise NotImplementedError("oracle: incidence matrices for PEC cells (solver.py:441-449) not restated")
+    incidence = split_curl_scaling is not None or mu_cross is not None  # solver.py:93
     st = setup(eps_cross, coords, freq, mode_spec, symmetry, mu_cross)
     n, m_modes = st["n"], mode_spec.num_modes
     basis_vecs = None
@@ -349,12 +347,32 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
 
     if not st["tensorial"]:
         spec = "diagonal"
-        _, qmat, mat = assemble_diagonal(st)
+        keep = None
+        if incidence:
+            # solver.py:441-449, 474-477: unknowns on PEC-valued cells are removed (incidence matrices) and 1/eps_zz is
+            # zeroed there; identity when no cell is PEC
+            thr = 0.9 * abs(PEC_VAL)
+            st = dict(st)
+            e = st["eps"] = st["eps"].copy()
+            zz_pec = np.abs(e[2, 2]) >= thr
+            keep = np.concatenate((np.abs(e[0, 0]) < thr, np.abs(e[1, 1]) < thr))
+            ezz_inv = np.where(zz_pec, 0.0, 1.0 / e[2, 2])
+            dxf_, dxb_, dyf_, dyb_ = d_matrices(st)
+            iez_, imz_ = _dg(ezz_inv), _dg(1 / st["mu"][2, 2])
+            m_ = st["mu"]
+            pmat = sp.bmat([[-dxf_ @ iez_ @ dyb_, dxf_ @ iez_ @ dxb_ + _dg(m_[1, 1])], [-dyf_ @ iez_ @ dyb_ - _dg(m_[0, 0]), dyf_ @ iez_ @ dxb_]], format="csr")
+            qmat = sp.bmat([[-dxb_ @ imz_ @ dyf_, dxb_ @ imz_ @ dxf_ + _dg(e[1, 1])], [-dyb_ @ imz_ @ dyf_ - _dg(e[0, 0]), dyb_ @ imz_ @ dxf_]], format="csr")
+            mat = (pmat @ qmat).tocsr()
+        else:
+            _, qmat, mat = assemble_diagonal(st)
         mat = _cast(mat, dtype)
         if mode_spec.precision == "single":
             _trim(mat)
         v0 = _cast(initial_vector(st["nx"], st["ny"], 2), dtype)
         sigma = _cast(np.array([-(st["target"] ** 2)]), dtype)[0]
+        if keep is not None and not keep.all():  # solver.py:506-508
+            mat = mat[keep][:, keep].tocsr()
+            v0 = v0[keep]
         has_pec = bool(np.any(np.abs(np.stack([e[0, 0], e[1, 1], e[2, 2]])) >= 0.9 * abs(PEC_VAL)))
         if basis_vecs is None and has_pec:
             # solver.py:467-468, 510-514, 565-566: right-Jacobi preconditioned generalized problem
@@ -372,6 +390,10 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
             vecs = qb @ coeffs
         if vals.size == 0:
             raise RuntimeError("Could not find any eigenmodes for this waveguide.")
+        if keep is not None and not keep.all():  # solver.py:568-569: back to the full set of unknowns (zeros on PEC cells)
+            full = np.zeros((keep.size, vecs.shape[1]), dtype=vecs.dtype)
+            full[keep] = vecs
+            vecs = full
         root = np.emath.sqrt(-vals + 0j)  # solver.py:884
         neff, keff = root.real, root.imag
         order = np.argsort(neff)[::-1]
@@ -381,7 +403,7 @@ def compute_modes(eps_cross, coords, freq, mode_spec, mu_cross=None, split_curl_
         hx = hq[:n] / (1j * neff - keff)
         hy = hq[n:] / (1j * neff - keff)
         hz = (dxf @ ey - dyf @ ex) / m[2, 2][:, None]
-        ez = (dxb @ hy - dyb @ hx) / e[2, 2][:, None]
+        ez = (dxb @ hy - dyb @ hx) * (ezz_inv[:, None] if incidence else 1 / e[2, 2][:, None])
         efield = np.stack((ex, ey, ez))
         hfield = np.stack((hx, hy, hz)) * (-1j / ETA_0)
         if direction == "-":  # solver.py:370-373

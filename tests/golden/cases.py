@@ -107,6 +107,15 @@ def _mu_and_split(n=40):
     return wl
 
 
+def _pec_split(n=40):
+    """PEC block + split-curl scaling: the reference's incidence-matrix formulation (solver.py:441-449, 474-477,
+    506-508).  Oracle-only fixture: the product raises NotImplementedError for this combination."""
+    wl = _pec_block(n)
+    wl.extra["split_curl_scaling"] = np.ones((3, n, n))
+    wl.name = f"pec_split_{n}"
+    return wl
+
+
 # name: (factory, kwargs for compute_modes, store full fields?)
 CASES = {
     "c1_64": (W.c1, {}, True),
@@ -129,6 +138,7 @@ CASES = {
     "pec_block_40": (_pec_block, {}, True),
     "mu_cross_40": (_mu_and_split, {"mu_cross": "extra"}, True),
     "split_curl_40": (_mu_and_split, {"split_curl_scaling": "extra"}, True),
+    "pec_split_40": (_pec_split, {"split_curl_scaling": "extra"}, True),
     "lossy_angled_40": (_lossy_angled, {}, True),
     "lossy_angled_40_minus": (_lossy_angled, {"direction": "-"}, True),
     "angle_bend_44": (_angle_bend, {"symmetry": (-1, 0)}, True),

@@ -10,7 +10,7 @@ from tests.helpers import load_golden, mode_overlaps, signature
 
 FAST = ["c1_64", "c1_64_minus", "c1_64_sym_pmc_pec", "lossy_48", "nonuniform_56", "slab1d_x1", "slab1d_y1",
         "angled_48_minus", "angled_phi_48", "offdiag_48", "c3_96", "c4_96", "c4_96_axis0", "strip_128_m4", "pec_block_40", "lossy_angled_40", "lossy_angled_40_minus", "angle_bend_44",
-        "mu_cross_40", "split_curl_40"]  # fmt: skip
+        "mu_cross_40", "split_curl_40", "pec_split_40"]  # fmt: skip
 
 
 @pytest.mark.parametrize("name", FAST)
