@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200MS_VERSION 100
+#define B200MS_VERSION 200
 
 /* return codes */
 enum {
@@ -55,7 +55,8 @@ typedef struct {
   int symmetry[2];       /* 0 none, +1 PMC, -1 PEC at the min wall (solver.py:184,197) */
   int bend_axis;         /* mode_spec.bend_axis, ignored when bend_radius is NaN */
   int direction;         /* +1 "+", -1 "-" */
-  int precision;         /* 0 double, 1 single (single: fields are rounded to complex64 precision) */
+  int precision;         /* mode_spec.precision: 0 double, 1 single.  single: result.fields is a complex64 buffer (solver.py:265-267);
+                            the eigenproblem itself is always solved to the handle's tolerances */
   double freq;           /* Hz */
   double target_neff;    /* NaN == None */
   double bend_radius;    /* NaN == None */
@@ -72,8 +73,9 @@ typedef struct {
 } b200ms_problem;
 
 typedef struct {
-  double *fields;        /* caller-allocated 2*3*nx*ny*1*num_modes complex128 (re,im), reference layout
-                            [E/H][comp][ix][iy][0][mode]; may be NULL to skip fields */
+  double *fields;        /* caller-allocated 2*3*nx*ny*1*num_modes complex128 (re,im) -- complex64 when precision == 1 --, reference
+                            layout [E/H][comp][ix][iy][0][mode]; HOST or DEVICE memory (unified addressing; a device buffer
+                            keeps the fields in HBM for an NCCL gather or on-device post-processing); NULL skips the fields */
   double *n_complex;     /* caller-allocated num_modes complex128 (re,im): n_eff + i k_eff */
   int eps_spec;          /* out: B200MS_SPEC_* */
   int status;            /* out: per-problem B200MS_* code */
@@ -91,8 +93,9 @@ typedef struct {
 
 /* Tunables (all have defaults). */
 typedef struct {
-  double eig_tol;        /* relative Ritz residual tolerance (default 1e-9; reference ARPACK tol is 1.19e-7) */
-  double inner_tol;      /* relative residual of the shift-invert solves (default 1e-10) */
+  double eig_tol;        /* relative Ritz residual tolerance; default 1.19e-7 = the reference's ARPACK tol (solver.py:20,745);
+                            the "tight" setting used by the parity tests is 1e-9 */
+  double inner_tol;      /* relative residual of the shift-invert solves before relaxation (default 1e-8; tight 1e-10) */
   int ncv;               /* Krylov subspace size, 0 = max(2k+1, 20) like scipy (solver.py:744) */
   int max_restarts;      /* default 100 */
   int gmres_restart;     /* default 40 */
@@ -114,7 +117,27 @@ typedef struct {
   int use_graph;         /* 1 (default): replay the multigrid V-cycle as one CUDA graph (fp32 multigrid only) */
   int mg_cycles;         /* V-cycles per preconditioner application (default 1) */
   int mg_precision;      /* 1 (default): multigrid preconditioner in fp32 (Krylov iteration stays fp64); 0: all fp64 */
+  int inner_mode;        /* 1 (default): device-resident FGMRES cycles (fused Gram-Schmidt kernels, device least-squares, one or
+                            two host read-backs per cycle); 0: the round-1 host-driven FGMRES */
+  int inner_ir;          /* 1 (default): run the FGMRES cycles in the multigrid precision (fp32) inside an fp64 iterative
+                            refinement (needs mg_precision == 1; diagonal path); 0: fp64 cycles */
+  double ir_floor;       /* smallest residual reduction asked of one fp32 cycle (default 2e-5) */
+  double ir_trust;       /* solves whose tolerance is >= this accept the fp32 residual estimate without an fp64 check (3e-5) */
 } b200ms_options;
+
+/* Counters of the most recent b200ms_solve_batch call on a handle (all its device batches together). */
+typedef struct {
+  double device_ms;      /* sum over device batches of the CUDA-event window "operator resident in HBM -> results in HBM" */
+  double setup_ms;       /* host wall time spent on upload + problem set-up + hierarchy build */
+  double download_ms;    /* host wall time spent delivering the fields */
+  double total_ms;       /* host wall time of the whole call */
+  long long launches;    /* kernels launched (CUDA-graph nodes counted individually) */
+  long long inner_iters; /* sum over problems of the FGMRES iterations each went through */
+  long long op_applies;  /* sum over problems of shift-invert applications */
+  long long host_syncs;  /* stream synchronisations inside the inner solves, summed over device batches */
+  int device_batches;    /* how many device batches the call was split into */
+  int nprob;
+} b200ms_stats;
 
 int b200ms_version(void);
 void b200ms_default_options(b200ms_options *opt);
@@ -123,6 +146,7 @@ int b200ms_create(int device, b200ms_handle **out);
 int b200ms_destroy(b200ms_handle *h);
 int b200ms_set_options(b200ms_handle *h, const b200ms_options *opt);
 const char *b200ms_last_error(b200ms_handle *h);
+int b200ms_get_stats(b200ms_handle *h, b200ms_stats *out);
 
 /* Page-locked host memory for result buffers (optional): fields written into memory from b200ms_host_alloc are copied
  * device->host at full PCIe/C2C speed instead of through the driver's pageable staging path. */
@@ -137,7 +161,8 @@ int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_problem *prob, 
 /* Benchmark / roofline hook: run one of the two hot stencil kernels `nrep` times on `nbatch` device-resident copies
  * of the operator of `prob` and return the mean kernel time (CUDA events on the library stream).
  * mode 0: y = (A - sigma) x, the fp64 operator apply of the Krylov iteration; mode 1: the production smoother sweep
- * (stored-diagonal Jacobi in the multigrid precision).  x (2*nx*ny complex128 (re,im)) may be NULL (random); y may be
+ * (stored-diagonal Jacobi in the multigrid precision); mode 2: one fused CGS2 Gram-Schmidt step of the inner solver against
+ * four basis vectors in the multigrid precision (gs_dots, gs_update_dots, gs_update_norm, gs_scale: 19 vector passes).  x (2*nx*ny complex128 (re,im)) may be NULL (random); y may be
  * NULL.  bytes_per_apply returns the algorithmic bytes of one launch: N*(4*s_v + nf*s_c) per problem for
  * the apply, N*(8*s_v + nf*s_c) for the sweep. */
 int b200ms_bench_stencil(b200ms_handle *h, const b200ms_problem *prob, int nbatch, int mode, int nrep,

@@ -27,3 +27,22 @@ def built_lib():
 @pytest.fixture(scope="session")
 def gpu_handle(built_lib):
     return built_lib.Handle()
+
+
+def _gpu_usable():
+    try:
+        import torch
+
+        return bool(torch.cuda.is_available())
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not failed) on a host without a CUDA device."""
+    if _gpu_usable():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this host (run under gpurun)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

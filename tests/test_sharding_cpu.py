@@ -17,7 +17,8 @@ def _fake_solve(problems):
         m = p["mode_spec"].num_modes
         nx, ny = p["eps_cross"][0].shape
         n = (p["freq"] * 1e-14 + np.arange(m)) * (1 + 0.5j)
-        f = np.full((2, 3, nx, ny, 1, m), p["freq"] * 1e-14, dtype=np.complex128) * (1 + np.arange(m))
+        dt = np.complex64 if p["mode_spec"].precision == "single" else np.complex128
+        f = (np.full((2, 3, nx, ny, 1, m), p["freq"] * 1e-14, dtype=np.complex128) * (1 + np.arange(m))).astype(dt)
         out.append((f, n, "diagonal"))
     return out
 
@@ -32,13 +33,23 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     wl = W.si_strip(8, 3, W.sweep_freqs(7))
     wl2 = W.si_strip(6, 2, W.sweep_freqs(4))
+    wl2.mode_spec.precision = "single"  # complex64 fields: the gather must preserve the dtype
     probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=f, mode_spec=wl.mode_spec) for f in wl.freqs]
     probs += [dict(eps_cross=wl2.eps_cross, coords=wl2.coords, freq=f, mode_spec=wl2.mode_spec) for f in wl2.freqs]
     n_all, fields = solve_sharded(probs, solve_fn=_fake_solve, gather_fields=True)
     ref = _fake_solve(probs)
     ok = len(n_all) == len(probs)
     ok &= all(np.array_equal(a, r[1]) for a, r in zip(n_all, ref))
-    ok &= all(np.array_equal(fields[i], ref[i][0]) for i in range(len(probs)))
+    ok &= all(np.array_equal(fields[i], ref[i][0]) and fields[i].dtype == ref[i][0].dtype for i in range(len(probs)))
+    # gather to rank 0 only (what the bench does on NCCL): rank 0 holds everything, rank 1 its own shard
+    info = {}
+    n_all, fields = solve_sharded(probs, solve_fn=_fake_solve, gather_fields=True, dst=0, info=info)
+    ok &= all(np.array_equal(a, r[1]) for a, r in zip(n_all, ref))
+    if rank == 0:
+        ok &= all(np.array_equal(fields[i], ref[i][0]) for i in range(len(probs)))
+        ok &= info["field_gather_bytes"] > 0
+    else:
+        ok &= sorted(fields) == list(partition(len(probs), world, rank))
     ok &= list(partition(11, 2, 0)) == list(range(0, 6)) and list(partition(11, 2, 1)) == list(range(6, 11))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()

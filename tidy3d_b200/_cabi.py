@@ -48,11 +48,20 @@ class Options(C.Structure):
         ("gmres_restart", C.c_int), ("gmres_maxit", C.c_int), ("mg_nu", C.c_int), ("mg_min_size", C.c_int),
         ("mg_coarse_iters", C.c_int), ("max_batch", C.c_int), ("mg_omega", C.c_double), ("mg_ppw", C.c_double),
         ("verbose", C.c_int), ("mg_pml_phase", C.c_double), ("inner_relax", C.c_double), ("inner_relax_cap", C.c_double), ("gmres_cgs2", C.c_int), ("stencil_variant", C.c_int), ("mg_nu_growth", C.c_int), ("use_graph", C.c_int), ("mg_cycles", C.c_int), ("mg_precision", C.c_int),
+        ("inner_mode", C.c_int), ("inner_ir", C.c_int), ("ir_floor", C.c_double), ("ir_trust", C.c_double),
+    ]  # fmt: skip
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("device_ms", C.c_double), ("setup_ms", C.c_double), ("download_ms", C.c_double), ("total_ms", C.c_double),
+        ("launches", C.c_longlong), ("inner_iters", C.c_longlong), ("op_applies", C.c_longlong), ("host_syncs", C.c_longlong),
+        ("device_batches", C.c_int), ("nprob", C.c_int),
     ]  # fmt: skip
 
 
 EXPORTS = [
-    "b200ms_version", "b200ms_default_options", "b200ms_create", "b200ms_destroy", "b200ms_set_options",
+    "b200ms_version", "b200ms_get_stats", "b200ms_default_options", "b200ms_create", "b200ms_destroy", "b200ms_set_options",
     "b200ms_last_error", "b200ms_host_alloc", "b200ms_host_free", "b200ms_solve_batch", "b200ms_bench_stencil", "b200ms_debug_schur", "b200ms_debug_setup",
     "b200ms_debug_hierarchy", "b200ms_debug_apply", "b200ms_debug_vcycle", "b200ms_debug_solve",
 ]  # fmt: skip
@@ -80,6 +89,7 @@ def lib():
             L.b200ms_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
             L.b200ms_last_error.argtypes = [C.c_void_p]
             L.b200ms_last_error.restype = C.c_char_p
+            L.b200ms_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
             L.b200ms_host_alloc.argtypes = [C.c_size_t]
             L.b200ms_host_alloc.restype = C.c_void_p
             L.b200ms_host_free.argtypes = [C.c_void_p]
@@ -104,9 +114,14 @@ class PackedProblem:
     """Owns the contiguous arrays a ``Problem`` struct points to."""
 
     def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None, basis_fields=None,
-                 mu_cross=None):
+                 mu_cross=None, target_override=None):
         if eps_packed is not None:
             eps = eps_packed
+        elif isinstance(eps_cross, np.ndarray) and eps_cross.dtype == np.complex128 and eps_cross.flags.c_contiguous and eps_cross.ndim == 3:
+            # what ModeSolver._solver_eps returns (mode_solver.py:647-653): used in place, no host copy
+            if eps_cross.shape[0] != 9:
+                raise ValueError("Wrong input to mode solver pemittivity/permeability!")
+            eps = eps_cross
         else:
             if isinstance(eps_cross, np.ndarray):
                 if eps_cross.shape[0] != 9:
@@ -138,7 +153,7 @@ class PackedProblem:
         p.direction = -1 if direction == "-" else 1
         p.precision = 1 if getattr(mode_spec, "precision", "single") == "single" else 0
         p.freq = float(freq)
-        tn = getattr(mode_spec, "target_neff", None)
+        tn = getattr(mode_spec, "target_neff", None) if target_override is None else target_override
         p.target_neff = math.nan if tn is None else float(tn)
         p.angle_theta = float(getattr(mode_spec, "angle_theta", 0.0))
         p.angle_phi = float(getattr(mode_spec, "angle_phi", 0.0))
@@ -219,6 +234,7 @@ class Handle:
 
     def __init__(self, device: int = -1, **options):
         self._h = C.c_void_p()
+        self.lock = threading.Lock()
         rc = lib().b200ms_create(device, C.byref(self._h))
         if rc != OK:
             raise RuntimeError(
@@ -239,6 +255,12 @@ class Handle:
     def last_error(self) -> str:
         return lib().b200ms_last_error(self._h).decode()
 
+    def last_stats(self) -> dict:
+        """Counters of the most recent solve_batch call on this handle (b200ms_get_stats)."""
+        st = Stats()
+        lib().b200ms_get_stats(self._h, C.byref(st))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}
+
     def close(self):
         if self._h:
             lib().b200ms_destroy(self._h)
@@ -250,8 +272,12 @@ class Handle:
         except Exception:
             pass
 
-    def solve_batch(self, packed, want_fields=True):
-        """packed: list of PackedProblem.  Returns (fields list | None, n_complex list, Result structs)."""
+    def solve_batch(self, packed, want_fields=True, fields_ptrs=None):
+        """packed: list of PackedProblem.  Returns (rc, fields list | None, n_complex list, Result structs).
+
+        ``fields_ptrs``: optional list of raw addresses (host or DEVICE memory, e.g. ``tensor.data_ptr()``) the library
+        writes the fields of each problem to, instead of freshly allocated pinned host arrays; then ``fields`` is None.
+        Fields are complex128, or complex64 for ``precision == "single"`` problems (solver.py:265-267)."""
         n = len(packed)
         probs = (Problem * n)(*[p.struct for p in packed])
         results = (Result * n)()
@@ -260,11 +286,14 @@ class Handle:
             nc = np.zeros(p.num_modes, dtype=np.complex128)
             ncs.append(nc)
             results[i].n_complex = _ptr(nc.view(np.float64))
-            if want_fields:
-                f = _pool.empty((2, 3, p.nx, p.ny, 1, p.num_modes))
+            if fields_ptrs is not None:
+                results[i].fields = C.cast(C.c_void_p(int(fields_ptrs[i])), _dp)
+            elif want_fields:
+                dt = np.complex64 if p.struct.precision == 1 else np.complex128
+                f = _pool.empty((2, 3, p.nx, p.ny, 1, p.num_modes), dtype=dt)
                 fields.append(f)
-                results[i].fields = _ptr(f.view(np.float64))
+                results[i].fields = C.cast(C.c_void_p(f.ctypes.data), _dp)
             else:
                 results[i].fields = None
         rc = lib().b200ms_solve_batch(self._h, n, probs, results)
-        return rc, (fields if want_fields else None), ncs, results
+        return rc, (fields if (want_fields and fields_ptrs is None) else None), ncs, results

@@ -25,13 +25,14 @@ struct b200ms_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned char *flush_buf = nullptr;
   size_t flush_bytes = 0;
+  b200ms_stats stats;
 };
 
 extern "C" int b200ms_version(void) { return B200MS_VERSION; }
 
 extern "C" void b200ms_default_options(b200ms_options *o) {
-  o->eig_tol = 1e-9;
-  o->inner_tol = 1e-10;
+  o->eig_tol = kFpEps;   // the reference's ARPACK tolerance (TOL_EIGS = fp_eps, solver.py:20)
+  o->inner_tol = 1e-8;
   o->ncv = 0;
   o->max_restarts = 100;
   o->gmres_restart = 40;
@@ -52,6 +53,10 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->gmres_cgs2 = 2;
   o->inner_relax = 1.0;
   o->inner_relax_cap = 1e-4;
+  o->inner_mode = 1;
+  o->inner_ir = 1;
+  o->ir_floor = 2e-5;
+  o->ir_trust = 3e-5;
 }
 
 extern "C" int b200ms_create(int device, b200ms_handle **out) {
@@ -107,14 +112,20 @@ extern "C" int b200ms_set_options(b200ms_handle *h, const b200ms_options *opt) {
 
 extern "C" const char *b200ms_last_error(b200ms_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
+extern "C" int b200ms_get_stats(b200ms_handle *h, b200ms_stats *out) {
+  if (!h || !out) return B200MS_ERR_ARG;
+  *out = h->stats;
+  return B200MS_OK;
+}
+
 namespace {
 
 struct GroupKey {
-  int nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens;
+  int nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens, prec;
   double theta, phi;
   bool operator<(const GroupKey &o) const {
-    return std::tie(nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens, theta, phi) <
-           std::tie(o.nx, o.ny, o.k, o.kind, o.has_mu, o.sx, o.sy, o.jz_axis, o.dir, o.rel, o.tens, o.theta, o.phi);
+    return std::tie(nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens, prec, theta, phi) <
+           std::tie(o.nx, o.ny, o.k, o.kind, o.has_mu, o.sx, o.sy, o.jz_axis, o.dir, o.rel, o.tens, o.prec, o.theta, o.phi);
   }
 };
 struct MediumKey {
@@ -147,7 +158,9 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
   }
   BatchSolver<T, C, P, PC> S(h->arena, h->stream, h->opt);
   auto wall0 = std::chrono::steady_clock::now();
+  S.single_out_ = prob[ids[0]].precision == 1;
   S.build(ps, share);
+  h->stats.setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));  // inputs are resident in HBM from here on
   const bool real_arith = std::is_same<T, double>::value;
   const bool relative = ps[0]->relative;
@@ -215,7 +228,15 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
   CUDA_CHECK(cudaEventSynchronize(h->ev1));
   float ms = 0.f;
   CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  auto dl0 = std::chrono::steady_clock::now();
   if (want_fields) S.copy_fields_out(dst.data());
+  h->stats.download_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dl0).count();
+  h->stats.device_ms += ms;
+  h->stats.launches += S.stats.launches;
+  h->stats.inner_iters += (long long)S.stats.inner_iters * B;
+  h->stats.op_applies += (long long)S.stats.op_applies * B;
+  h->stats.host_syncs += S.stats.host_syncs;
+  h->stats.device_batches += 1;
   const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   for (int b = 0; b < B; ++b) {
     b200ms_result &r = res[ids[b]];
@@ -223,10 +244,6 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
       cd n = nsorted[(size_t)b * k + q] * ps[b]->knorm;  // solver.py:262-263
       r.n_complex[2 * q] = n.real();
       r.n_complex[2 * q + 1] = n.imag();
-    }
-    if (prob[ids[b]].precision == 1 && r.fields) {  // solver.py:265-267: complex64 output precision
-      const size_t cnt = (size_t)12 * S.N * k;
-      for (size_t i = 0; i < cnt; ++i) r.fields[i] = (double)(float)r.fields[i];
     }
     r.eps_spec = ps[b]->eps_spec;
     r.converged = eig.nconv[b];
@@ -263,8 +280,12 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
   if (!h || nprob < 0 || (nprob > 0 && (!prob || !res))) return B200MS_ERR_ARG;
   if (cudaSetDevice(h->device) != cudaSuccess) return B200MS_ERR_CUDA;
   h->err.clear();
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  h->stats.nprob = nprob;
+  const auto call0 = std::chrono::steady_clock::now();
   int first_err = B200MS_OK;
   try {
+    const auto su0 = std::chrono::steady_clock::now();
     std::vector<ProblemSetup> setups(nprob);
     std::map<GroupKey, std::vector<int>> groups;
     std::vector<std::pair<MediumKey, int>> seen;
@@ -298,9 +319,11 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
       }
       const ProblemSetup &s = setups[i];
       GroupKey key{s.nx, s.ny, s.num_modes, kind_of(s), s.has_mu ? 1 : 0, prob[i].symmetry[0], prob[i].symmetry[1],
-                   s.jz_axis, s.direction, s.relative ? 1 : 0, s.tensorial ? (s.eps_complex ? 2 : 1) : 0, prob[i].angle_theta, prob[i].angle_phi};
+                   s.jz_axis, s.direction, s.relative ? 1 : 0, s.tensorial ? (s.eps_complex ? 2 : 1) : 0, prob[i].precision == 1 ? 1 : 0,
+                   prob[i].angle_theta, prob[i].angle_phi};
       groups[key].push_back(i);
     }
+    h->stats.setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - su0).count();
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
     free_b += h->arena.cap;
@@ -336,6 +359,7 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
     h->err = e.what();
     return B200MS_ERR_CUDA;
   }
+  h->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - call0).count();
   return first_err;
 }
 
@@ -371,8 +395,15 @@ static void bench_group(b200ms_handle *h, const ProblemSetup &s, int nbatch, int
     h->flush_bytes = (size_t)256 << 20;
     CUDA_CHECK(cudaMalloc(&h->flush_buf, h->flush_bytes));
   }
+  // mode 2: one fused CGS2 step in the multigrid precision against 4 basis vectors (slots 0..3 of the FGMRES basis)
+  P *gsV = reinterpret_cast<P *>(S.gmres_v()), *gsW = gsV + 4 * S.vstride;
+  if (mode == 2)
+    for (int q = 0; q < 5; ++q)
+      for (int b = 0; b < nbatch; ++b)
+        CUDA_CHECK(cudaMemcpyAsync(gsV + (size_t)q * S.vstride + (size_t)b * len, hp.data(), len * sizeof(P), cudaMemcpyHostToDevice, h->stream));
   auto run = [&]() {
-    if (mode == 1) S.apply(0, MODE_JACOBI, px, prhs, py);
+    if (mode == 2) S.template gs_cgs2<P>(gsV, S.vstride, len, 4, gsW, gsW, nullptr, reinterpret_cast<P *>(S.hessenberg()), (size_t)S.restart * (S.restart + 4));
+    else if (mode == 1) S.apply(0, MODE_JACOBI, px, prhs, py);
     else S.apply_true(MODE_APPLY, dx, drhs, dy);
   };
   for (int w = 0; w < 3; ++w) run();
@@ -402,7 +433,9 @@ static void bench_group(b200ms_handle *h, const ProblemSetup &s, int nbatch, int
   // algorithmic bytes: apply = read v (2) + write Av (2) + nf coefficient fields per cell;
   // smoother sweep = read x, rhs, omega/diag (6) + write x' (2) + nf coefficient fields per cell
   const double ncell = (double)S.N * nbatch;
-  if (bytes_out)
+  if (bytes_out && mode == 2)  // dots: 4+1 vectors; update+dots: 4 + r/w w; update+norm: 4 + r/w w; scale: r + w
+    *bytes_out = (double)len * nbatch * sizeof(P) * 19.0;
+  else if (bytes_out)
     *bytes_out = mode == 1 ? ncell * (8.0 * sizeof(P) + (double)S.nf * sizeof(PC)) : ncell * (4.0 * sizeof(T) + (double)S.nf * sizeof(C));
   if (y) {
     for (size_t e = 0; e < len; ++e) {

@@ -83,6 +83,16 @@ template <> HD double cast_to<double>(cplx v) { return v.re; }
 template <> HD cplx cast_to<cplx>(cplx v) { return v; }
 HD cplx to_cplx(double v) { return mk(v, 0.0); }
 HD cplx to_cplx(cplx v) { return v; }
+// any of the four vector scalar types <-> double-complex (small dense work is always done in cplx)
+HD cplx to_cplx_any(double v) { return mk(v, 0.0); }
+HD cplx to_cplx_any(float v) { return mk((double)v, 0.0); }
+HD cplx to_cplx_any(cplx v) { return v; }
+HD cplx to_cplx_any(cplxf v) { return mk((double)v.re, (double)v.im); }
+template <typename U> HD U from_cplx_any(cplx v);
+template <> HD double from_cplx_any<double>(cplx v) { return v.re; }
+template <> HD float from_cplx_any<float>(cplx v) { return (float)v.re; }
+template <> HD cplx from_cplx_any<cplx>(cplx v) { return v; }
+template <> HD cplxf from_cplx_any<cplxf>(cplx v) { return mkf((float)v.re, (float)v.im); }
 
 template <typename T> __device__ __forceinline__ T ldg(const T *p) { return *p; }
 template <> __device__ __forceinline__ double ldg<double>(const double *p) { return __ldg(p); }
@@ -954,6 +964,21 @@ __global__ void __launch_bounds__(256) convert_strided_kernel(size_t len, const 
   }
 }
 
+// six components of mode m at cell g into the reference layout [2][3][nx][ny][1][M], complex128 or complex64
+__device__ __forceinline__ void store_fields(cplx *out, int single, size_t base, size_t N, size_t g, int M, int m, cplx Ex, cplx Ey,
+                                             cplx Ez, cplx Hx, cplx Hy, cplx Hz) {
+  const cplx v[6] = {Ex, Ey, Ez, Hx, Hy, Hz};
+  if (single) {
+    cplxf *o = reinterpret_cast<cplxf *>(out) + base;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) o[((size_t)c * N + g) * M + m] = mkf((float)v[c].re, (float)v[c].im);
+  } else {
+    cplx *o = out + base;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) o[((size_t)c * N + g) * M + m] = v[c];
+  }
+}
+
 // tensorial epilogue (solver.py:701-719, 254-269): six components from w = [Ex;Ey;Hx;Hy], Ez = U, Hz = Tt
 template <typename C>
 struct TensorEpilogueArgs {
@@ -969,6 +994,7 @@ struct TensorEpilogueArgs {
   int conj_flip;              // tensorial_real with direction "-": E = conj(E), H = -conj(H) (solver.py:378-380)
   double h_scale;
   cplx *out;
+  int single;                 // write complex64 (precision = "single", solver.py:265-267)
 };
 template <typename C>
 __global__ void __launch_bounds__(256) tensor_epilogue_kernel(TensorEpilogueArgs<C> a) {
@@ -996,13 +1022,7 @@ __global__ void __launch_bounds__(256) tensor_epilogue_kernel(TensorEpilogueArgs
   // E = J^T E' with J = [[1,0,a],[0,1,b],[0,0,d]]
   Ez = a.jac_a * Ex + a.jac_b * Ey + de * Ez;
   Hz = a.jac_a * Hx + a.jac_b * Hy + dh * Hz;
-  cplx *o = a.out + (size_t)b * 6 * N * M;
-  o[(0 * N + g) * M + m] = Ex;
-  o[(1 * N + g) * M + m] = Ey;
-  o[(2 * N + g) * M + m] = Ez;
-  o[(3 * N + g) * M + m] = Hx;
-  o[(4 * N + g) * M + m] = Hy;
-  o[(5 * N + g) * M + m] = Hz;
+  store_fields(a.out, a.single, (size_t)b * 6 * N * M, N, g, M, m, Ex, Ey, Ez, Hx, Hy, Hz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1022,6 +1042,7 @@ struct EpilogueArgs {
   int direction;
   double h_scale;    // 1 / ETA_0
   cplx *out;         // [B][2][3][nx][ny][M]
+  int single;        // write complex64 (precision = "single", solver.py:265-267)
 };
 
 // E = (Ex, Ey, u / (i n)),  H = (-i/eta0) * (q1/(i n), q2/(i n), t)
@@ -1072,13 +1093,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(EpilogueArgs<T, C> a) {
     Ez = a.jz_e[(size_t)b * a.jz_len + t] * Ez;
     Hz = a.jz_h[(size_t)b * a.jz_len + t] * Hz;
   }
-  cplx *o = a.out + (size_t)b * 6 * N * M;
-  o[(0 * N + g) * M + m] = Ex;
-  o[(1 * N + g) * M + m] = Ey;
-  o[(2 * N + g) * M + m] = Ez;
-  o[(3 * N + g) * M + m] = Hx;
-  o[(4 * N + g) * M + m] = Hy;
-  o[(5 * N + g) * M + m] = Hz;
+  store_fields(a.out, a.single, (size_t)b * 6 * N * M, N, g, M, m, Ex, Ey, Ez, Hx, Hy, Hz);
 }
 
 }  // namespace b200ms

@@ -15,6 +15,7 @@
 #include "dense.hpp"
 #include "host_setup.hpp"
 #include "kernels.cuh"
+#include "krylov_kernels.cuh"
 
 namespace b200ms {
 
@@ -66,6 +67,8 @@ struct SolveStats {
   int op_applies = 0, inner_iters = 0, restarts = 0;
   long stencil_applies = 0, launches = 0;
   int inner_failures = 0;  // shift-invert solves that stopped above 1e4 x inner_tol
+  long host_syncs = 0;     // stream synchronisations inside the inner solves
+  int inner_cycles = 0;    // FGMRES cycles (iterative-refinement steps)
 };
 
 template <typename T> inline cd to_cd(T v);
@@ -104,6 +107,7 @@ class BatchSolver {
   int B = 0, nx = 0, ny = 0, k = 0, m = 0, restart = 0, nf = 3;
   size_t N = 0, len = 0, vstride = 0, lenE = 0, vsE = 0;
   bool tensor_ = false;
+  bool single_out_ = false;  // fields are delivered as complex64 (mode_spec.precision == "single")
   double msign_ = 1.0;
   bool has_mu = false, shared_fields = false;
   std::vector<Level> lv;
@@ -131,6 +135,7 @@ class BatchSolver {
     m = std::min(ncv, (int)std::min<size_t>(len - 1, 1 << 20));
     if (m < k + 2) m = std::min<int>(k + 2, (int)len);
     restart = std::max(2, opt_.gmres_restart);
+    if (opt_.inner_mode != 0) restart = std::min(restart, kGsMaxCoef - 4);
     mask_x_ = (!p0.ax[0].pmc && nx > 1) ? 1 : 0;
     mask_y_ = (!p0.ax[1].pmc && ny > 1) ? 1 : 0;
 
@@ -177,6 +182,15 @@ class BatchSolver {
     sz.add<T>((size_t)B * hstride());
     sz.add<T>((size_t)B * (m + 1) * (m + 1));
     sz.add<T>((size_t)B * 8);
+    sz.add<P>((size_t)B * 4 * nx);
+    sz.add<P>((size_t)B * 4 * ny);
+    sz.add<T>((size_t)B * restart * (restart + 4));
+    sz.add<T>((size_t)B * restart);
+    sz.add<T>((size_t)3 * B * kDotChunks * pstride());
+    sz.add<cplx>((size_t)B * ((size_t)(restart + 1) * restart + 3 * restart + 2));
+    sz.add<double>((size_t)4 * B + 64);
+    sz.add<int>((size_t)B + 64);
+    sz.add<unsigned char>((size_t)B + 64);
     sz.add<cplx>((size_t)B * k);
     sz.add<cplx>((size_t)B * 6 * N * k);
     sz.add<double>((size_t)B * 2 * std::max(nx, ny) + 64);
@@ -332,6 +346,23 @@ class BatchSolver {
     qbuf_ = arena_.get<T>((size_t)B * (m + 1) * (m + 1));
     sigma_ = arena_.get<T>((size_t)B * 4);
     sigma_p_ = arena_.get<P>((size_t)B * 4);
+    cx_true_p_ = arena_.get<P>((size_t)B * 4 * nx);
+    cy_true_p_ = arena_.get<P>((size_t)B * 4 * ny);
+    {
+      const size_t tx = (size_t)B * 4 * nx, ty = (size_t)B * 4 * ny;
+      convert_kernel<T, P><<<(unsigned)std::min<size_t>((tx + 255) / 256, 1024), 256, 0, st_>>>(tx, lv[0].cx_true, cx_true_p_);
+      convert_kernel<T, P><<<(unsigned)std::min<size_t>((ty + 255) / 256, 1024), 256, 0, st_>>>(ty, lv[0].cy_true, cy_true_p_);
+    }
+    Hd_ = arena_.get<T>((size_t)B * restart * (restart + 4));
+    ydev_ = arena_.get<T>((size_t)B * restart);
+    gpart_ = arena_.get<T>((size_t)3 * B * kDotChunks * pstride());
+    lsq_work_ = arena_.get<cplx>((size_t)B * ((size_t)(restart + 1) * restart + 3 * restart + 2));
+    tol_dev_ = arena_.get<double>((size_t)4 * B + 64);
+    res_dev_ = tol_dev_ + B;
+    n2_dev_ = tol_dev_ + 2 * B;
+    bn2_dev_ = tol_dev_ + 3 * B;
+    jused_dev_ = arena_.get<int>((size_t)B + 64);
+    skip_dev_ = arena_.get<unsigned char>((size_t)B + 64);
     ncomplex_ = arena_.get<cplx>((size_t)B * k);
     fields_out_ = arena_.get<cplx>((size_t)B * 6 * N * k);
     jz_ = arena_.get<double>((size_t)B * 2 * std::max(nx, ny) + 64);
@@ -884,6 +915,288 @@ class BatchSolver {
     return worst;
   }
 
+
+  // =====================================================================================================
+  // Round-2 inner solver: device-resident FGMRES cycles (Gram-Schmidt coefficients never visit the host, the
+  // least-squares problem is solved by one thread per problem, the host reads back only (estimate, columns used)
+  // once or twice per cycle), run in the multigrid precision (fp32) inside an fp64 iterative refinement:
+  //   r = b - (A - sigma) x  (fp64)  ->  d = FGMRES_fp32(r / ||r||)  ->  x += ||r|| d  (fp64)
+  // Each fp32 cycle needs only ~1e-4 of reduction, so its Krylov basis is short, its Gram-Schmidt bytes are halved and
+  // no fp64<->fp32 conversion surrounds the V-cycle.  Falls back to fp64 cycles when refinement stagnates.
+  // =====================================================================================================
+  template <typename U>
+  static bool vec_ok(size_t ln) { return ln % PackTraits<U>::EPV == 0; }
+  int gs_chunks(size_t ln) const {
+    const size_t packs = std::max<size_t>(1, ln / 2);
+    return (int)std::max<size_t>(1, std::min<size_t>({(size_t)kDotChunks, packs / 1024 + 1, (size_t)(1184 + B - 1) / B}));
+  }
+  template <typename U>
+  U *gpart(int region) { return reinterpret_cast<U *>(gpart_) + (size_t)region * B * kDotChunks * pstride(); }
+
+  // partial[b][chunk][poff + i] = <V_i, w>, i < nv (groups of kGsGroup)
+  template <typename U>
+  void k_dots(const U *V, size_t vs, size_t ln, const U *w, int nv, U *part, int poff, int nch) {
+    dim3 grd(nch, B);
+    for (int g0 = 0; g0 < nv; g0 += kGsGroup) {
+      const int ng = std::min(kGsGroup, nv - g0);
+      stats.launches++;
+#define B200_DOTS(EPV, NG) gs_dots_kernel<U, EPV, NG><<<grd, 256, 0, st_>>>(V, vs, ln, w, g0, ng, part, pstride(), poff + g0)
+      if (vec_ok<U>(ln)) {
+        constexpr int E = PackTraits<U>::EPV;
+        if (ng == 1) B200_DOTS(E, 1); else if (ng == 2) B200_DOTS(E, 2); else if (ng <= 4) B200_DOTS(E, 4); else B200_DOTS(E, 8);
+      } else {
+        if (ng == 1) B200_DOTS(1, 1); else if (ng == 2) B200_DOTS(1, 2); else if (ng <= 4) B200_DOTS(1, 4); else B200_DOTS(1, 8);
+      }
+#undef B200_DOTS
+    }
+  }
+  template <typename U>
+  void k_update_dots(const U *V, size_t vs, size_t ln, U *w, int nv, const U *pin, int nch, U *pout, U *hexp, size_t hstride, int acc) {
+    dim3 grd(nch, B);
+    stats.launches++;
+    if (vec_ok<U>(ln)) gs_update_dots_kernel<U, PackTraits<U>::EPV><<<grd, 256, 0, st_>>>(V, vs, ln, w, nv, pin, nch, pstride(), 0, pout, 0, hexp, hstride, 0, acc);
+    else gs_update_dots_kernel<U, 1><<<grd, 256, 0, st_>>>(V, vs, ln, w, nv, pin, nch, pstride(), 0, pout, 0, hexp, hstride, 0, acc);
+  }
+  template <typename U>
+  void k_update_norm(const U *V, size_t vs, size_t ln, U *w, int nv, const U *pin, int nch, U *pout, int do_norm, U *hexp, size_t hstride, int acc) {
+    dim3 grd(nch, B);
+    stats.launches++;
+    if (vec_ok<U>(ln)) gs_update_norm_kernel<U, PackTraits<U>::EPV><<<grd, 256, 0, st_>>>(V, vs, ln, w, nv, pin, nch, pstride(), 0, pout, 0, do_norm, hexp, hstride, 0, acc);
+    else gs_update_norm_kernel<U, 1><<<grd, 256, 0, st_>>>(V, vs, ln, w, nv, pin, nch, pstride(), 0, pout, 0, do_norm, hexp, hstride, 0, acc);
+  }
+  template <typename U>
+  void k_scale(const U *w, U *y, U *y2, size_t ln, const U *pin, int nch, U *hexp, size_t hstride, int hoff) {
+    dim3 grd((unsigned)std::min<size_t>((ln / 4 + 255) / 256 + 1, 2048), B);
+    stats.launches++;
+    if (vec_ok<U>(ln)) gs_scale_kernel<U, PackTraits<U>::EPV><<<grd, 256, 0, st_>>>(w, y, y2, ln, pin, nch, pstride(), 0, hexp, hstride, hoff);
+    else gs_scale_kernel<U, 1><<<grd, 256, 0, st_>>>(w, y, y2, ln, pin, nch, pstride(), 0, hexp, hstride, hoff);
+  }
+  // CGS2 of w against V_0..V_{nv-1}, normalised into dst (and dst2 if given).  Exports h_i (both passes summed) to
+  // hexp[b*hstride + i] and ||w''||^2 to hexp[b*hstride + nv].  No host synchronisation.
+  template <typename U>
+  void gs_cgs2(const U *V, size_t vs, size_t ln, int nv, U *w, U *dst, U *dst2, U *hexp, size_t hstride) {
+    U *P0 = gpart<U>(0), *P1 = gpart<U>(1), *P2 = gpart<U>(2);
+    const int nch = gs_chunks(ln);
+    if (nv <= kGsGroup) {
+      k_dots<U>(V, vs, ln, w, nv, P0, 0, nch);
+      k_update_dots<U>(V, vs, ln, w, nv, P0, nch, P1, hexp, hstride, 0);
+      k_update_norm<U>(V, vs, ln, w, nv, P1, nch, P2, 1, hexp, hstride, 1);
+    } else {
+      k_dots<U>(V, vs, ln, w, nv, P0, 0, nch);
+      k_update_norm<U>(V, vs, ln, w, nv, P0, nch, P2, 0, hexp, hstride, 0);
+      k_dots<U>(V, vs, ln, w, nv, P1, 0, nch);
+      k_update_norm<U>(V, vs, ln, w, nv, P1, nch, P2, 1, hexp, hstride, 1);
+    }
+    k_scale<U>(w, dst, dst2, ln, P2, nch, hexp, hstride, nv);
+  }
+  // outer (Krylov-Schur) orthonormalisation through the device kernels: one read-back of h and ||w||
+  void orthonormalise_dev(const T *V, int nv, T *w, T *dst, std::vector<cd> &h, std::vector<double> &nrm) {
+    const int hs = hstride();
+    gs_cgs2<T>(V, vstride, len, nv, w, dst, nullptr, hbuf_, (size_t)hs);
+    fetch_h((size_t)B * hs);
+    h.assign((size_t)B * nv, cd(0, 0));
+    nrm.assign(B, 0.0);
+    for (int b = 0; b < B; ++b) {
+      for (int i = 0; i < nv; ++i) h[(size_t)b * nv + i] = to_cd(hhost_[(size_t)b * hs + i]);
+      nrm[b] = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hs + nv]).real()));
+    }
+  }
+
+  template <typename U>
+  void apply_true_u(int mode, const U *x, const U *rhs, U *y) {
+    if constexpr (std::is_same<U, T>::value) {
+      apply_true(mode, x, rhs, y);
+    } else {
+      stats.stencil_applies++;
+      launch_stencil<P, PC>(lv[0], mode, x, rhs, y, lv[0].fields, cx_true_p_, cy_true_p_, sigma_p_);
+    }
+  }
+  // z = M^-1 v.  For the multigrid-precision path the input is expected in lv[0].b already (the kernels that produce
+  // Krylov vectors store them there as well) and the V-cycle result is copied into the Z slot.
+  template <typename U>
+  void precondition_u(const U *v, U *z, bool input_staged) {
+    if constexpr (std::is_same<U, T>::value) {
+      precondition(v, z);
+    } else {
+      if (!input_staged) CUDA_CHECK(cudaMemcpyAsync(lv[0].b, v, vsE * sizeof(P), cudaMemcpyDeviceToDevice, st_));
+      const int ncyc = std::max(1, opt_.mg_cycles);
+      if (graph_exec_) {
+        CUDA_CHECK(cudaGraphLaunch(graph_exec_, st_));
+        stats.launches += graph_nodes_;
+        stats.stencil_applies += graph_fine_applies_;
+      } else {
+        precondition_body(lv[0].b, nullptr, ncyc);
+        graph_result_ = ncyc == 1 ? lv[0].x : pre_b_;
+      }
+      CUDA_CHECK(cudaMemcpyAsync(z, graph_result_, vsE * sizeof(P), cudaMemcpyDeviceToDevice, st_));
+    }
+  }
+
+  // One FGMRES cycle from the unit-norm residual sitting in slot 0 of the basis.  tol[b] < 0: problem inactive.
+  // Returns the number of Arnoldi steps run; y (device, type U) holds the solution coefficients.
+  template <typename U>
+  int fgmres_cycle(const std::vector<double> &tol, std::vector<double> &res, std::vector<int> &jused, bool staged, int budget) {
+    U *Vu = reinterpret_cast<U *>(Vg_), *Zu = reinterpret_cast<U *>(Zg_), *Hu = reinterpret_cast<U *>(Hd_);
+    U *yu = reinterpret_cast<U *>(ydev_);
+    const int ld = restart + 4;
+    constexpr bool kStage = kMixed && std::is_same<U, P>::value;
+    CUDA_CHECK(cudaMemcpyAsync(tol_dev_, tol.data(), B * sizeof(double), cudaMemcpyHostToDevice, st_));
+    double tmin = 1.0;
+    for (int b = 0; b < B; ++b)
+      if (tol[b] >= 0) tmin = std::min(tmin, tol[b]);
+    const int cap = std::max(1, std::min(restart, budget));
+    int target = (int)std::ceil(std::log(std::max(tmin, 1e-300)) / std::log(std::min(0.9, std::max(1e-3, rho_))));
+    target = std::max(1, std::min(cap, target));
+    int j = 0;
+    res.assign(B, 0.0);
+    jused.assign(B, 0);
+    std::vector<double> hres(B);
+    std::vector<int> hju(B);
+    while (true) {
+      for (; j < target; ++j) {
+        U *vj = Vu + (size_t)j * vstride, *zj = Zu + (size_t)j * vstride, *w = Vu + (size_t)(j + 1) * vstride;
+        precondition_u<U>(vj, zj, kStage && (j > 0 || staged));
+        apply_true_u<U>(MODE_APPLY, zj, nullptr, w);
+        gs_cgs2<U>(Vu, vstride, len, j + 1, w, w, kStage ? reinterpret_cast<U *>(lv[0].b) : nullptr, Hu + (size_t)j * ld, (size_t)restart * ld);
+      }
+      fgmres_lsq_kernel<U><<<(B + 31) / 32, 32, 0, st_>>>(Hu, restart, ld, j, tol_dev_, lsq_work_, yu, restart, res_dev_, jused_dev_, B);
+      stats.launches++;
+      CUDA_CHECK(cudaMemcpyAsync(hres.data(), res_dev_, B * sizeof(double), cudaMemcpyDeviceToHost, st_));
+      CUDA_CHECK(cudaMemcpyAsync(hju.data(), jused_dev_, B * sizeof(int), cudaMemcpyDeviceToHost, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+      stats.host_syncs++;
+      bool all = true;
+      int need = 0;
+      for (int b = 0; b < B; ++b) {
+        if (tol[b] < 0) continue;
+        if (hres[b] > tol[b] && hju[b] == j) {  // not converged and no breakdown
+          all = false;
+          const double rate = std::min(0.95, std::max(1e-3, std::pow(std::max(hres[b], 1e-300), 1.0 / std::max(1, j))));
+          need = std::max(need, (int)std::ceil(std::log(tol[b] / hres[b]) / std::log(rate)));
+        }
+      }
+      if (all || j >= cap) break;
+      target = std::min(cap, j + std::max(1, std::min(need, 8)));
+    }
+    double rmax = 1e-3;
+    for (int b = 0; b < B; ++b) {
+      res[b] = hres[b];
+      jused[b] = hju[b];
+      if (tol[b] >= 0 && hju[b] > 0) rmax = std::max(rmax, std::pow(std::max(hres[b], 1e-300), 1.0 / hju[b]));
+    }
+    rho_ = std::min(0.9, rmax);
+    return j;
+  }
+
+  // xsol = (A - sigma)^-1 rhs for every problem not in `skip`, to the relative residuals tolv.  Returns the worst
+  // final relative residual; iters_out = Arnoldi steps run (all cycles).
+  double solve_op(const T *rhs, T *xsol, int &iters_out, const std::vector<char> *skip = nullptr, const std::vector<double> *tolv = nullptr) {
+    if (opt_.inner_mode == 0) return fgmres(rhs, xsol, iters_out, skip, tolv);
+    auto tol_of = [&](int b) { return tolv ? (*tolv)[b] : opt_.inner_tol; };
+    bool ir = kMixed && !tensor_ && opt_.inner_ir != 0;
+    std::vector<char> done(B, 0);
+    if (skip) done = *skip;
+    std::vector<unsigned char> hskip(B);
+    std::vector<double> resrel(B, 1.0), bn2(B, 0.0), n2(B, 0.0), tolc(B), cres;
+    std::vector<int> ju;
+    CUDA_CHECK(cudaMemsetAsync(xsol, 0, vstride * sizeof(T), st_));
+    const T *rcur = rhs;
+    const int nch = gs_chunks(len);
+    int total = 0, cyc = 0;
+    bool verified = true;
+    const dim3 egrd((unsigned)std::min<size_t>((len / 4 + 255) / 256 + 1, 2048), B);
+    while (true) {
+      // ||r||^2 of the current residual (partials; reduced inside ir_begin)
+      k_dots<T>(rcur, vstride, len, rcur, 1, gpart<T>(0), 0, nch);
+      if (cyc > 0) {  // decide on the true fp64 residual
+        sum_partials_kernel<T><<<(B + 63) / 64, 64, 0, st_>>>(gpart<T>(0), nch, pstride(), 0, n2_dev_, B);
+        stats.launches++;
+        CUDA_CHECK(cudaMemcpyAsync(n2.data(), n2_dev_, B * sizeof(double), cudaMemcpyDeviceToHost, st_));
+        if (cyc == 1) CUDA_CHECK(cudaMemcpyAsync(bn2.data(), bn2_dev_, B * sizeof(double), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        stats.host_syncs++;
+        bool all = true, stagnated = false;
+        for (int b = 0; b < B; ++b) {
+          if (done[b]) continue;
+          const double r = bn2[b] > 0 ? std::sqrt(n2[b] / bn2[b]) : 0.0;
+          if (ir && !(r < 0.5 * resrel[b])) stagnated = true;
+          resrel[b] = r;
+          if (r <= tol_of(b)) done[b] = 1; else all = false;
+        }
+        if (all || total >= opt_.gmres_maxit) break;
+        if (stagnated || cyc >= 8) ir = false;  // finish in fp64
+      }
+      for (int b = 0; b < B; ++b) {
+        hskip[b] = done[b] ? 1 : 0;
+        const double want = 0.5 * tol_of(b) / std::max(resrel[b], 1e-300);
+        tolc[b] = done[b] ? -1.0 : std::min(0.5, std::max(want, ir ? opt_.ir_floor : 0.0));
+      }
+      CUDA_CHECK(cudaMemcpyAsync(skip_dev_, hskip.data(), B, cudaMemcpyHostToDevice, st_));
+      stats.launches++;
+      double *n2cur = cyc == 0 ? bn2_dev_ : n2_dev_;  // ||r||^2 of this cycle (cycle 0: ||b||^2, kept for the relative residuals)
+      int steps;
+      if (ir) {
+        P *Vp = reinterpret_cast<P *>(Vg_);
+#define B200_IRB(E) ir_begin_kernel<T, P, E><<<egrd, 256, 0, st_>>>(rcur, Vp, lv[0].b, len, gpart<T>(0), nch, pstride(), 0, n2cur, skip_dev_)
+        if (vec_ok<P>(len)) B200_IRB(PackTraits<P>::EPV); else B200_IRB(1);
+#undef B200_IRB
+        steps = fgmres_cycle<P>(tolc, cres, ju, true, opt_.gmres_maxit - total);
+        int nvmax = 0;
+        for (int b = 0; b < B; ++b) nvmax = std::max(nvmax, ju[b]);
+        if (nvmax > 0) {
+          stats.launches++;
+          const P *Zp = reinterpret_cast<const P *>(Zg_), *yp = reinterpret_cast<const P *>(ydev_);
+          if (vec_ok<P>(len)) ir_update_kernel<T, P, PackTraits<P>::EPV><<<egrd, 256, 0, st_>>>(Zp, vstride, len, yp, restart, nvmax, n2cur, xsol);
+          else ir_update_kernel<T, P, 1><<<egrd, 256, 0, st_>>>(Zp, vstride, len, yp, restart, nvmax, n2cur, xsol);
+        }
+      } else {
+#define B200_IRB(E) ir_begin_kernel<T, T, E><<<egrd, 256, 0, st_>>>(rcur, Vg_, nullptr, len, gpart<T>(0), nch, pstride(), 0, n2cur, skip_dev_)
+        if (vec_ok<T>(len)) B200_IRB(PackTraits<T>::EPV); else B200_IRB(1);
+#undef B200_IRB
+        steps = fgmres_cycle<T>(tolc, cres, ju, false, opt_.gmres_maxit - total);
+        int nvmax = 0;
+        for (int b = 0; b < B; ++b) nvmax = std::max(nvmax, ju[b]);
+        if (nvmax > 0) {
+          stats.launches++;
+          if (vec_ok<T>(len)) ir_update_kernel<T, T, PackTraits<T>::EPV><<<egrd, 256, 0, st_>>>(Zg_, vstride, len, ydev_, restart, nvmax, n2cur, xsol);
+          else ir_update_kernel<T, T, 1><<<egrd, 256, 0, st_>>>(Zg_, vstride, len, ydev_, restart, nvmax, n2cur, xsol);
+        }
+      }
+      total += steps;
+      // estimates: res_cycle is relative to the residual the cycle started from
+      bool all_est = true, trust = true;
+      for (int b = 0; b < B; ++b) {
+        if (done[b]) continue;
+        const double est = cres[b] * resrel[b];
+        if (est > tol_of(b)) all_est = false;
+        if (ir && tolc[b] < opt_.ir_trust) trust = false;  // the fp32 estimate is good to ~1e-5 of the cycle's starting residual
+        cres[b] = est;
+      }
+      ++cyc;
+      if (all_est && trust) {  // fp64 cycles: the estimate is the true residual up to rounding; fp32: loose tolerances only
+        for (int b = 0; b < B; ++b)
+          if (!done[b]) resrel[b] = cres[b];
+        verified = false;
+        break;
+      }
+      if (total >= opt_.gmres_maxit && !ir) {
+        for (int b = 0; b < B; ++b)
+          if (!done[b]) resrel[b] = cres[b];
+        break;
+      }
+      apply_true(MODE_RESID, xsol, rhs, rhs_);
+      rcur = rhs_;
+    }
+    (void)verified;
+    iters_out = total;
+    stats.inner_iters += total;
+    stats.inner_cycles += cyc;
+    double worst = 0.0;
+    for (int b = 0; b < B; ++b)
+      if (!skip || !(*skip)[b]) worst = std::max(worst, resrel[b]);
+    return worst;
+  }
+
   // -- Krylov-Schur ---------------------------------------------------------------------------------
   struct EigResult {
     std::vector<cd> theta;      // [B][k] Ritz values of OP
@@ -932,10 +1245,11 @@ class BatchSolver {
       for (int j = nkeep; j < m; ++j) {
         T *vj = Vout_ + (size_t)j * vstride, *w = Vout_ + (size_t)(j + 1) * vstride;
         int its = 0;
-        double worst = fgmres(vj, w, its, &done, &tolv);
+        double worst = solve_op(vj, w, its, &done, &tolv);
         stats.op_applies++;
         if (!(worst <= 1e-3)) stats.inner_failures++;
-        orthonormalise(Vout_, j + 1, w, w, h, nrm);
+        if (opt_.inner_mode != 0 && j + 2 < kGsMaxCoef) orthonormalise_dev(Vout_, j + 1, w, w, h, nrm);
+        else orthonormalise(Vout_, j + 1, w, w, h, nrm);
         for (int b = 0; b < B; ++b) {
           if (done[b]) continue;
           for (int i = 0; i <= j; ++i) Bm[b](i, j) += h[(size_t)b * (j + 1) + i];
@@ -1219,7 +1533,7 @@ class BatchSolver {
         t.jz_e = jz_; t.jz_h = jz_ + (size_t)B * jz_len; t.jz_axis = p0.jz_axis; t.jz_len = jz_len;
         t.jac_a = p0.jac_a; t.jac_b = p0.jac_b;
         t.conj_flip = (!p0.eps_complex && p0.direction < 0) ? 1 : 0;
-        t.h_scale = 1.0 / eta0(); t.out = fields_out_;
+        t.h_scale = 1.0 / eta0(); t.out = fields_out_; t.single = single_out_ ? 1 : 0;
         dim3 blk(64, 4), grd((ny + 63) / 64, (nx + 3) / 4, B * k);
         tensor_epilogue_kernel<C><<<grd, blk, 0, st_>>>(t);
         CUDA_CHECK(cudaGetLastError());
@@ -1230,7 +1544,7 @@ class BatchSolver {
     a.nx = nx; a.ny = ny; a.num_modes = k; a.vec = Zg_; a.vstride = vstride;
     a.fields = lv[0].fields_true; a.field_bstride = lv[0].fbstride; a.cx = lv[0].cx_true; a.cy = lv[0].cy_true;
     a.ncomplex = ncomplex_; a.jz_e = jz_; a.jz_h = jz_ + (size_t)B * jz_len; a.jz_axis = p0.jz_axis; a.jz_len = jz_len;
-    a.direction = p0.direction; a.h_scale = 1.0 / eta0(); a.out = fields_out_;
+    a.direction = p0.direction; a.h_scale = 1.0 / eta0(); a.out = fields_out_; a.single = single_out_ ? 1 : 0;
     dim3 blk(64, 4), grd((ny + 63) / 64, (nx + 3) / 4, B * k);
     if (has_mu) epilogue_kernel<T, C, true><<<grd, blk, 0, st_>>>(a);
     else epilogue_kernel<T, C, false><<<grd, blk, 0, st_>>>(a);
@@ -1238,16 +1552,19 @@ class BatchSolver {
   }
   // device -> host copy of the packed fields (kept out of the compute-only timing window)
   void copy_fields_out(cplx *host_dst_per_problem[]) {
+    const size_t esz = single_out_ ? sizeof(cplxf) : sizeof(cplx);
     for (int b = 0; b < B; ++b)
       if (host_dst_per_problem[b])
-        CUDA_CHECK(cudaMemcpyAsync(host_dst_per_problem[b], fields_out_ + (size_t)b * 6 * N * k, 6 * N * k * sizeof(cplx),
-                                   cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaMemcpyAsync(host_dst_per_problem[b], reinterpret_cast<unsigned char *>(fields_out_) + (size_t)b * 6 * N * k * esz,
+                                   6 * N * k * esz, cudaMemcpyDefault, st_));  // destination may be host or device memory
     CUDA_CHECK(cudaStreamSynchronize(st_));
   }
 
   T *scratch_vec(int i) { return i == 0 ? xsol_ : rhs_; }
   T *basis0() { return Vout_; }
   T *gmres_z() { return Zg_; }
+  T *gmres_v() { return Vg_; }
+  T *hessenberg() { return Hd_; }
   T *ritz_ptr() { return ritz_; }
 
  private:
@@ -1339,6 +1656,14 @@ class BatchSolver {
   P *cV_ = nullptr, *cZ_ = nullptr, *cH_ = nullptr, *cH2_ = nullptr, *cy_ = nullptr, *cbeta_ = nullptr, *cone_ = nullptr;
   std::vector<T> hhost_;
   std::vector<cd> sig_host_;
+  // round-2 inner solver state
+  P *cx_true_p_ = nullptr, *cy_true_p_ = nullptr;  // reference-operator difference coefficients in the multigrid precision
+  T *Hd_ = nullptr, *ydev_ = nullptr, *gpart_ = nullptr;
+  cplx *lsq_work_ = nullptr;
+  double *tol_dev_ = nullptr, *res_dev_ = nullptr, *n2_dev_ = nullptr, *bn2_dev_ = nullptr;
+  int *jused_dev_ = nullptr;
+  unsigned char *skip_dev_ = nullptr;
+  double rho_ = 0.2;  // convergence factor per Arnoldi step seen in the last cycle (plans the next one)
 };
 
 }  // namespace b200ms

@@ -23,16 +23,23 @@ from . import _cabi
 _handles = {}
 _hlock = threading.Lock()
 
+# Tolerance presets.  "reference" (the default of the library) asks for what the reference asks ARPACK for
+# (tol = TOL_EIGS = fp_eps, solver.py:20, 745); "tight" is the setting the parity tests use to pin n_eff to 1e-8.
+TOLERANCES = {"reference": dict(eig_tol=1.1920928955078125e-07, inner_tol=1e-8), "tight": dict(eig_tol=1e-9, inner_tol=1e-10)}
 
-def get_handle(device: int = -1) -> _cabi.Handle:
+
+def get_handle(device: int = -1, tolerance: str = "reference") -> _cabi.Handle:
+    """One cached solver handle per (GPU, tolerance preset).  Calls on one handle are serialised by a per-handle lock
+    (ctypes releases the GIL during the solve and the C ABI forbids overlapping calls on a handle)."""
+    key = (device, tolerance)
     with _hlock:
-        if device not in _handles:
-            _handles[device] = _cabi.Handle(device)
-        return _handles[device]
+        if key not in _handles:
+            _handles[key] = _cabi.Handle(device, **TOLERANCES[tolerance])
+        return _handles[key]
 
 
-def _raise_for(rc: int, handle, where=""):
-    msg = handle.last_error()
+def _raise_for(rc: int, handle, where="", msg=None):
+    msg = handle.last_error() if msg is None else msg
     if rc == _cabi.ERR_SHAPE:
         raise ValueError("Mismatch between 'coords' and 'esp_cross' shapes.")  # solver.py:107
     if rc == _cabi.ERR_NO_MODES:
@@ -80,23 +87,32 @@ def _undo_split_curl(fields, split):
     split = np.asarray(split)
     outside = ~np.isclose(split, 0)
     scale = np.where(outside, split, 1.0)
-    fields[0] = fields[0] / scale[:, :, :, None, None] * outside[:, :, :, None, None]
+    fields[0] = (fields[0] / scale[:, :, :, None, None] * outside[:, :, :, None, None]).astype(fields.dtype)
     return fields
 
 
 def compute_modes_batch(
-    problems: Sequence[dict], device: int = -1, want_fields: bool = True, return_info: bool = False, handle=None
+    problems: Sequence[dict], device: int = -1, want_fields: bool = True, return_info: bool = False, handle=None,
+    fields_ptrs=None,
 ):
     """Solve many independent mode problems in one device call.
 
     Each problem is a dict with the keyword arguments of ``compute_modes`` (``eps_cross, coords, freq, mode_spec``
     and optionally ``symmetry, direction``).  Problems that share the same ``eps_cross`` object are packed once.
     Returns a list of ``(fields, n_complex, eps_spec)`` tuples (``fields`` is None when ``want_fields=False``),
-    plus a list of per-problem info dicts when ``return_info``.
+    plus a list of per-problem info dicts when ``return_info``.  ``fields_ptrs`` (list of raw addresses, host or device
+    memory) makes the library write each problem's fields there instead (``fields`` is then None): used to keep the
+    fields in HBM for the NCCL gather of ``tidy3d_b200.sharding`` / on-device post-processing.
     """
     packed, cache = [], {}
     for p in problems:
         split = p.get("split_curl_scaling")
+        target_override = None
+        if split is not None and getattr(p["mode_spec"], "target_neff", None) is None and not isinstance(p["eps_cross"], np.ndarray):
+            # solver.py:204-207: the default target comes from `eps_cross` as passed; for a list/tuple input that is the
+            # permittivity BEFORE the split-curl division (format_medium_data copies, solver.py:900)
+            ec = np.array([np.asarray(c) for c in p["eps_cross"]])
+            target_override = float(np.sqrt(np.max(np.abs(ec[np.abs(ec) < abs(PEC_VAL)]))))
         _check_unsupported(p["eps_cross"], p.get("mu_cross"), split)
         if split is not None and p.get("solver_basis_fields") is not None:
             raise RuntimeError("Split curl not yet implemented for relative mode solver.")  # solver.py:938
@@ -105,7 +121,7 @@ def compute_modes_batch(
         pk = _cabi.PackedProblem(
             eps_in, p["coords"], p["freq"], p["mode_spec"], p.get("symmetry", (0, 0)), p.get("direction", "+"),
             eps_packed=None if split is not None else cache.get(key), basis_fields=p.get("solver_basis_fields"),
-            mu_cross=p.get("mu_cross"),
+            mu_cross=p.get("mu_cross"), target_override=target_override,
         )  # fmt: skip
         if split is None:
             cache[key] = pk.eps
@@ -117,17 +133,17 @@ def compute_modes_batch(
                 pk.struct.coords_x, pk.struct.coords_y = prev.struct.coords_x, prev.struct.coords_y
         packed.append(pk)
     h = handle or get_handle(device)  # after input validation: argument errors do not need a GPU
-    rc, fields, ncs, results = h.solve_batch(packed, want_fields)
+    with h.lock:
+        rc, fields, ncs, results = h.solve_batch(packed, want_fields, fields_ptrs)
+        err = h.last_error() if rc != _cabi.OK else ""
     if rc != _cabi.OK:
         bad = [i for i in range(len(packed)) if results[i].status != _cabi.OK]
-        _raise_for(rc, h, f"(problems {bad[:8]})")
+        _raise_for(rc, h, f"(problems {bad[:8]})", err)
     out, infos = [], []
     for i, pk in enumerate(packed):
-        f = fields[i] if want_fields else None
+        f = fields[i] if fields is not None else None
         if f is not None and problems[i].get("split_curl_scaling") is not None:
             f = _undo_split_curl(f, problems[i]["split_curl_scaling"])
-        if f is not None and pk.struct.precision == 1:
-            f = f.astype(np.complex64)  # solver.py:265-267
         out.append((f, ncs[i], _cabi.SPEC_NAMES[results[i].eps_spec]))
         r = results[i]
         infos.append(
@@ -148,9 +164,12 @@ def compute_modes(
     symmetry=(0, 0),
     direction="+",
     solver_basis_fields=None,
+    handle=None,
 ) -> Tuple[np.ndarray, np.ndarray, str]:
-    """Drop-in for ``tidy3d.plugins.mode.solver.compute_modes`` (solver.py:941)."""
+    """Drop-in for ``tidy3d.plugins.mode.solver.compute_modes`` (solver.py:941).  ``handle`` (not in the reference
+    signature) selects a solver handle, e.g. ``get_handle(tolerance="tight")``."""
     return compute_modes_batch(
         [dict(eps_cross=eps_cross, coords=coords, freq=freq, mode_spec=mode_spec, symmetry=symmetry, direction=direction,
-              solver_basis_fields=solver_basis_fields, mu_cross=mu_cross, split_curl_scaling=split_curl_scaling)]
+              solver_basis_fields=solver_basis_fields, mu_cross=mu_cross, split_curl_scaling=split_curl_scaling)],
+        handle=handle,
     )[0]
