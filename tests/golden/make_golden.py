@@ -32,13 +32,26 @@ def run(name):
     kw = resolve_kwargs(wl, kw)
     ref = ref_shim.load()
     out = {}
+    single = getattr(wl.mode_spec, "precision", "double") == "single"
     for tag, tol in (("ref", None), ("tight", 1e-12)):
+        if single and tag == "tight":
+            # a single-precision ARPACK run cannot reach 1e-12: the "tight" companion of a single case is the reference
+            # in DOUBLE precision at TOL_EIGS = 1e-12 (what the single result approximates)
+            wl.mode_spec.precision = "double"
         old = ref.TOL_EIGS
         if tol is not None:
             ref.TOL_EIGS = tol
         t0 = time.time()
         try:
             fields, n_complex, spec = ref_shim.compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, **kw)
+        except Exception as e:  # noqa: BLE001  (scipy ArpackNoConvergence on the pathological rand10 input at 1e-12)
+            if tag != "tight":
+                raise
+            print(name, "tight run failed:", type(e).__name__, "-> n_tight := n_ref", flush=True)
+            out["tight_failed"] = True
+            out["n_tight"], out["sig_tight"], out["sec_tight"] = out["n_ref"], out["sig_ref"], 0.0
+            ref.TOL_EIGS = old
+            continue
         finally:
             ref.TOL_EIGS = old
         out[f"n_{tag}"] = n_complex
@@ -47,6 +60,8 @@ def run(name):
         out["spec"] = spec
         if store and tag == "tight":
             out["fields_tight"] = fields
+        if store and single and tag == "ref":
+            out["fields_ref"] = fields  # complex64, the reference's own single-precision fields
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, out["spec"], out["n_ref"], "max|n_ref-n_tight|=%.2e" % np.abs(out["n_ref"] - out["n_tight"]).max(),
           "%.1fs/%.1fs" % (out["sec_ref"], out["sec_tight"]), flush=True)  # fmt: skip

@@ -16,10 +16,34 @@
 
 using namespace b200ms;
 
+// grow-only device buffer
+struct DevBuf {
+  unsigned char *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CUDA_CHECK(cudaMalloc(&p, n));
+    cap = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
 struct b200ms_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t io_stream = nullptr;  // uploads of raw media / downloads of fields
   Arena arena;
+  DevBuf raw[2];      // raw eps/mu of a window of problems (+ bend factors), double-buffered
+  DevBuf out[2];      // packed fields of a window, double-buffered
+  DevBuf scan;        // reduction scratch + per-medium results of prepare_window
+  DevBuf refs;        // MediumRef array of the batch being built
   b200ms_options opt;
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -72,6 +96,7 @@ extern "C" int b200ms_create(int device, b200ms_handle **out) {
   h->device = device;
   b200ms_default_options(&h->opt);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
     delete h;
     return B200MS_ERR_CUDA;
@@ -84,6 +109,13 @@ extern "C" int b200ms_destroy(b200ms_handle *h) {
   if (!h) return B200MS_OK;
   cudaSetDevice(h->device);
   h->arena.release();
+  for (int q = 0; q < 2; ++q) {
+    h->raw[q].release();
+    h->out[q].release();
+  }
+  h->scan.release();
+  h->refs.release();
+  if (h->io_stream) cudaStreamDestroy(h->io_stream);
   if (h->flush_buf) cudaFree(h->flush_buf);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -130,36 +162,149 @@ struct GroupKey {
 };
 struct MediumKey {
   const double *eps, *mu, *cx, *cy;
-  int nx, ny, k, p0, p1, s0, s1, bend_axis, dir;
-  double bend_radius, target, theta, phi;
+  int nx, ny, p0, p1, bend_axis;
+  double bend_radius, theta, phi;
   bool operator==(const MediumKey &o) const {
     auto same = [](double a, double b) { return (std::isnan(a) && std::isnan(b)) || a == b; };
-    return eps == o.eps && mu == o.mu && cx == o.cx && cy == o.cy && nx == o.nx && ny == o.ny && k == o.k && p0 == o.p0 && p1 == o.p1 &&
-           s0 == o.s0 && s1 == o.s1 && bend_axis == o.bend_axis && dir == o.dir && same(bend_radius, o.bend_radius) &&
-           same(target, o.target) && theta == o.theta && phi == o.phi;
+    return eps == o.eps && mu == o.mu && cx == o.cx && cy == o.cy && nx == o.nx && ny == o.ny && p0 == o.p0 && p1 == o.p1 &&
+           bend_axis == o.bend_axis && same(bend_radius, o.bend_radius) && theta == o.theta && phi == o.phi;
   }
 };
 // kind: 0 real, 1 complex vectors + real fields, 2 all complex
 int kind_of(const ProblemSetup &s) { return !s.is_complex ? 0 : (s.coef_complex ? 2 : 1); }
 
+inline size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
+
+// A window of consecutive problems whose raw media are resident on the device: set-up stages A-C of host_setup.hpp with
+// the per-cell work (reductions) done by medium_scan_kernel.
+struct Window {
+  int i0 = 0, i1 = 0;
+  std::vector<ProblemSetup> setups;  // one per problem of the window
+  std::vector<MediumRef> refs;       // one per problem (device pointers into the raw buffer)
+  std::vector<int> slot;             // medium slot of each problem (problems sharing eps/mu/geometry share a slot)
+  size_t h2d_bytes = 0;
+};
+
+void prepare_window(b200ms_handle *h, const b200ms_problem *prob, int i0, int i1, DevBuf &raw, cudaStream_t st, Window &W) {
+  const int n = i1 - i0;
+  W.i0 = i0;
+  W.i1 = i1;
+  W.setups.assign(n, ProblemSetup());
+  W.refs.assign(n, MediumRef());
+  W.slot.assign(n, -1);
+  W.h2d_bytes = 0;
+  std::vector<std::pair<MediumKey, int>> seen;  // key -> first problem with that medium
+  std::vector<size_t> off_eps(n, 0), off_mu(n, 0), off_d(n, 0);
+  size_t total = 0;
+  for (int q = 0; q < n; ++q) {
+    const b200ms_problem &p = prob[i0 + q];
+    ProblemSetup &s = W.setups[q];
+    setup_geometry(p, s);
+    if (s.status != B200MS_OK) continue;
+    MediumKey mk{p.eps, p.mu, p.coords_x, p.coords_y, p.nx, p.ny, p.num_pml[0], p.num_pml[1], p.bend_axis, p.bend_radius, p.angle_theta, p.angle_phi};
+    auto it = std::find_if(seen.begin(), seen.end(), [&](const std::pair<MediumKey, int> &e) { return e.first == mk; });
+    if (it != seen.end()) {
+      W.slot[q] = W.slot[it->second];
+      continue;
+    }
+    W.slot[q] = (int)seen.size();
+    seen.push_back({mk, q});
+    const size_t N = (size_t)p.nx * p.ny;
+    off_eps[q] = total;
+    total += align256(9 * N * sizeof(cplx));
+    if (p.mu) {
+      off_mu[q] = total;
+      total += align256(9 * N * sizeof(cplx));
+    }
+    if (s.jz_axis >= 0) {
+      off_d[q] = total;
+      total += align256(2 * s.jz_e.size() * sizeof(double));
+    }
+  }
+  const int nslot = (int)seen.size();
+  raw.reserve(std::max<size_t>(total, 256));
+  // scan scratch: [kScanBlocks][kScanSlots] partials, then nslot result rows
+  h->scan.reserve(align256((size_t)kScanBlocks * kScanSlots * sizeof(double)) + align256((size_t)std::max(nslot, 1) * kScanSlots * sizeof(double)) +
+                  4096);
+  double *d_partial = reinterpret_cast<double *>(h->scan.p);
+  double *d_res = reinterpret_cast<double *>(h->scan.p + align256((size_t)kScanBlocks * kScanSlots * sizeof(double)));
+  std::vector<MediumRef> slot_ref(nslot);
+  for (auto &e : seen) {
+    const int q = e.second;
+    const b200ms_problem &p = prob[i0 + q];
+    const ProblemSetup &s = W.setups[q];
+    const size_t N = (size_t)p.nx * p.ny;
+    MediumRef r;
+    r.eps = reinterpret_cast<const cplx *>(raw.p + off_eps[q]);
+    CUDA_CHECK(cudaMemcpyAsync(raw.p + off_eps[q], p.eps, 9 * N * sizeof(cplx), cudaMemcpyDefault, st));
+    W.h2d_bytes += 9 * N * sizeof(cplx);
+    r.mu = nullptr;
+    if (p.mu) {
+      r.mu = reinterpret_cast<const cplx *>(raw.p + off_mu[q]);
+      CUDA_CHECK(cudaMemcpyAsync(raw.p + off_mu[q], p.mu, 9 * N * sizeof(cplx), cudaMemcpyDefault, st));
+      W.h2d_bytes += 9 * N * sizeof(cplx);
+    }
+    const double *d_de = nullptr, *d_dh = nullptr;
+    if (s.jz_axis >= 0) {
+      const size_t nn = s.jz_e.size();
+      double *dd = reinterpret_cast<double *>(raw.p + off_d[q]);
+      CUDA_CHECK(cudaMemcpyAsync(dd, s.jz_e.data(), nn * sizeof(double), cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(dd + nn, s.jz_h.data(), nn * sizeof(double), cudaMemcpyHostToDevice, st));
+      d_de = dd;
+      d_dh = dd + nn;
+    }
+    r.p = medium_params(s, p, d_de, d_dh);
+    const int nb = (int)std::min<size_t>(kScanBlocks, (N + 255) / 256);
+    medium_scan_kernel<<<nb, 256, 0, st>>>(r.eps, r.mu, r.p, d_partial);
+    medium_scan_final_kernel<<<1, 32, 0, st>>>(d_partial, nb, d_res + (size_t)W.slot[q] * kScanSlots);
+    slot_ref[W.slot[q]] = r;
+  }
+  std::vector<MediumScan> scans(std::max(nslot, 1));
+  if (nslot > 0) CUDA_CHECK(cudaMemcpyAsync(scans.data(), d_res, (size_t)nslot * kScanSlots * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(cudaGetLastError());
+  for (int q = 0; q < n; ++q) {
+    if (W.setups[q].status != B200MS_OK) continue;
+    W.refs[q] = slot_ref[W.slot[q]];
+    W.setups[q].medium = W.slot[q];
+    finish_setup(prob[i0 + q], W.setups[q], scans[W.slot[q]]);
+  }
+}
+
+// device array of MediumRef for a batch (fB entries)
+const MediumRef *upload_refs(b200ms_handle *h, const std::vector<MediumRef> &refs, cudaStream_t st) {
+  h->refs.reserve(align256(refs.size() * sizeof(MediumRef)) + 4096);
+  MediumRef *d = reinterpret_cast<MediumRef *>(h->refs.p);
+  CUDA_CHECK(cudaMemcpyAsync(d, refs.data(), refs.size() * sizeof(MediumRef), cudaMemcpyHostToDevice, st));
+  return d;
+}
+
+struct FieldCopy {  // one pending delivery of packed fields: device region -> caller memory (host or device)
+  void *dst;
+  const void *src;
+  size_t bytes;
+};
+
 template <typename T, typename C, typename P, typename PC>
-void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vector<ProblemSetup> &setups,
-                 const b200ms_problem *prob, b200ms_result *res) {
+void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W, const b200ms_problem *prob, b200ms_result *res,
+                 unsigned char *out_region, std::vector<FieldCopy> &copies) {
+  // ids index into the window (global problem index = W.i0 + id)
   const int B = (int)ids.size();
   std::vector<const ProblemSetup *> ps(B);
+  std::vector<MediumRef> refs(B);
   bool share = true;
   for (int b = 0; b < B; ++b) {
-    ps[b] = &setups[ids[b]];
-    const b200ms_problem &p = prob[ids[b]], &p0 = prob[ids[0]];
-    if (p.eps != p0.eps || p.mu != p0.mu || p.coords_x != p0.coords_x || p.coords_y != p0.coords_y ||
-        !((std::isnan(p.bend_radius) && std::isnan(p0.bend_radius)) || p.bend_radius == p0.bend_radius) ||
-        p.bend_axis != p0.bend_axis)
-      share = false;
+    ps[b] = &W.setups[ids[b]];
+    refs[b] = W.refs[ids[b]];
+    if (W.slot[ids[b]] != W.slot[ids[0]]) share = false;
   }
+  if (share) refs.resize(1);
   BatchSolver<T, C, P, PC> S(h->arena, h->stream, h->opt);
   auto wall0 = std::chrono::steady_clock::now();
-  S.single_out_ = prob[ids[0]].precision == 1;
-  S.build(ps, share);
+  S.single_out_ = prob[W.i0 + ids[0]].precision == 1;
+  const MediumRef *d_refs = upload_refs(h, refs, h->stream);
+  S.build(ps, share, d_refs);
+  S.set_output(reinterpret_cast<cplx *>(out_region));
   h->stats.setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));  // inputs are resident in HBM from here on
   const bool real_arith = std::is_same<T, double>::value;
@@ -169,7 +314,7 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
   std::vector<cd> rel_vals;
   if (relative) {
     std::vector<const cd *> basis(B);
-    for (int b = 0; b < B; ++b) basis[b] = reinterpret_cast<const cd *>(prob[ids[b]].basis_e);
+    for (int b = 0; b < B; ++b) basis[b] = reinterpret_cast<const cd *>(prob[W.i0 + ids[b]].basis_e);
     rel_vals = S.solve_relative(basis);
     eig.nconv.assign(B, k);
     eig.resid.assign(B, 0.0);
@@ -205,17 +350,13 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
       lam[(size_t)b * k + q] = ll[o[q]];
     }
   }
-  std::vector<cplx *> dst(B);
   bool want_fields = false;
-  for (int b = 0; b < B; ++b) {
-    dst[b] = reinterpret_cast<cplx *>(res[ids[b]].fields);
-    if (dst[b]) want_fields = true;
-  }
-  S.epilogue(nsorted, perm, ps, dst.data(), want_fields);
+  for (int b = 0; b < B; ++b)
+    if (res[W.i0 + ids[b]].fields) want_fields = true;
+  S.epilogue(nsorted, perm, ps, nullptr, want_fields);
   // true residuals on the sorted Ritz vectors (they sit in the FGMRES Z scratch after the permutation)
   std::vector<double> maxres(B, 0.0);
   {
-    // reuse eigen_residuals on the permuted vectors: copy them back into the Ritz slots
     CUDA_CHECK(cudaMemcpyAsync(S.ritz_ptr(), S.gmres_z(), (size_t)k * S.vstride * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     for (int q = 0; q < k; ++q) {
       std::vector<cd> lq(B);
@@ -228,9 +369,10 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
   CUDA_CHECK(cudaEventSynchronize(h->ev1));
   float ms = 0.f;
   CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  auto dl0 = std::chrono::steady_clock::now();
-  if (want_fields) S.copy_fields_out(dst.data());
-  h->stats.download_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dl0).count();
+  const size_t per = S.output_bytes_per_problem();
+  if (want_fields)
+    for (int b = 0; b < B; ++b)
+      if (res[W.i0 + ids[b]].fields) copies.push_back({res[W.i0 + ids[b]].fields, out_region + (size_t)b * per, per});
   h->stats.device_ms += ms;
   h->stats.launches += S.stats.launches;
   h->stats.inner_iters += (long long)S.stats.inner_iters * B;
@@ -239,7 +381,7 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
   h->stats.device_batches += 1;
   const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   for (int b = 0; b < B; ++b) {
-    b200ms_result &r = res[ids[b]];
+    b200ms_result &r = res[W.i0 + ids[b]];
     for (int q = 0; q < k; ++q) {
       cd n = nsorted[(size_t)b * k + q] * ps[b]->knorm;  // solver.py:262-263
       r.n_complex[2 * q] = n.real();
@@ -260,18 +402,42 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const std::vecto
     // screened for garbage (O(1)) here.
     r.status = (relative || (eig.nconv[b] == k && eig.ok && maxres[b] < 1e-1 && S.stats.inner_failures == 0)) ? B200MS_OK : B200MS_ERR_NOCONV;
     if (h->opt.verbose)
-      fprintf(stderr, "[b200ms] prob %d: conv %d/%d restarts %d op %d inner %d stencil %ld res %.2e ms %.1f\n", ids[b],
-              eig.nconv[b], k, S.stats.restarts, S.stats.op_applies, S.stats.inner_iters, S.stats.stencil_applies,
-              maxres[b], ms);
+      fprintf(stderr, "[b200ms] prob %d: conv %d/%d restarts %d op %d inner %d cycles %d syncs %ld stencil %ld res %.2e ms %.1f\n", W.i0 + ids[b],
+              eig.nconv[b], k, S.stats.restarts, S.stats.op_applies, S.stats.inner_iters, S.stats.inner_cycles, S.stats.host_syncs,
+              S.stats.stencil_applies, maxres[b], ms);
   }
 }
 
+// device memory one problem of a batch needs in the solver arena (Krylov bases dominate)
 size_t bytes_per_problem(const ProblemSetup &s, const b200ms_options &opt) {
-  const size_t len = (size_t)2 * s.nx * s.ny;
+  const size_t N = (size_t)s.nx * s.ny;
+  const size_t len = (s.tensorial ? 4 : 2) * N;
   const size_t sv = s.is_complex ? 16 : 8;
   const int m = opt.ncv > 0 ? opt.ncv : std::max(2 * s.num_modes + 1, 20);
-  size_t vecs = (m + 1) + (2 * opt.gmres_restart + 1) + 2 + s.num_modes + 6 /* level work x 4/3 */ + 3;
-  return vecs * len * sv + (size_t)6 * s.nx * s.ny * s.num_modes * 16 + (size_t)8 * s.nx * s.ny * 16;
+  size_t vecs = (m + 1) + (2 * opt.gmres_restart + 1) + 4 + s.num_modes;
+  size_t bytes = vecs * len * sv;
+  bytes += (size_t)7 * 2 * N * sv * 4 / 3;            // multigrid level work vectors (x, b, r, tmp, dinv + coarse levels)
+  bytes += (size_t)(s.has_mu ? 6 : 3) * N * 16 * 2;   // coefficient fields in both precisions
+  if (s.tensorial) bytes += (size_t)18 * N * 16 + (size_t)6 * 2 * N * sv;  // derived tensor fields + preconditioner scratch
+  return bytes;
+}
+
+template <typename... A>
+void dispatch_group(int kind, bool f32, A &&...a) {
+  switch (kind) {
+    case 0:
+      if (f32) solve_group<double, double, float, float>(std::forward<A>(a)...);
+      else solve_group<double, double, double, double>(std::forward<A>(a)...);
+      break;
+    case 1:
+      if (f32) solve_group<cplx, double, cplxf, float>(std::forward<A>(a)...);
+      else solve_group<cplx, double, cplx, double>(std::forward<A>(a)...);
+      break;
+    default:
+      if (f32) solve_group<cplx, cplx, cplxf, cplxf>(std::forward<A>(a)...);
+      else solve_group<cplx, cplx, cplx, cplx>(std::forward<A>(a)...);
+      break;
+  }
 }
 
 }  // namespace
@@ -285,75 +451,74 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
   const auto call0 = std::chrono::steady_clock::now();
   int first_err = B200MS_OK;
   try {
-    const auto su0 = std::chrono::steady_clock::now();
-    std::vector<ProblemSetup> setups(nprob);
-    std::map<GroupKey, std::vector<int>> groups;
-    std::vector<std::pair<MediumKey, int>> seen;
-    for (int i = 0; i < nprob; ++i) {
-      res[i].status = B200MS_OK;
-      res[i].converged = 0;
-      if (!res[i].n_complex) {
-        res[i].status = B200MS_ERR_ARG;
-      } else {
-        // a sweep over one cross-section sets the medium up once (pointer equality == identical content)
-        MediumKey mk{prob[i].eps, prob[i].mu, prob[i].coords_x, prob[i].coords_y, prob[i].nx, prob[i].ny, prob[i].num_modes,
-                     prob[i].num_pml[0], prob[i].num_pml[1], prob[i].symmetry[0], prob[i].symmetry[1], prob[i].bend_axis,
-                     prob[i].direction, prob[i].bend_radius, prob[i].target_neff, prob[i].angle_theta, prob[i].angle_phi};
-        auto it = std::find_if(seen.begin(), seen.end(), [&](const std::pair<MediumKey, int> &e) { return e.first == mk; });
-        if (it != seen.end() && setups[it->second].status == B200MS_OK) {
-          setup_problem_like(prob[i], setups[it->second], setups[i]);
-        } else {
-          setup_problem(prob[i], setups[i]);
-          seen.push_back({mk, i});
-        }
-        res[i].status = setups[i].status;
-        res[i].eps_spec = setups[i].eps_spec;
-        res[i].is_complex = setups[i].is_complex;
-      }
-      if (res[i].status != B200MS_OK) {
-        if (first_err == B200MS_OK) {
-          first_err = res[i].status;
-          h->err = setups[i].error;
-        }
-        continue;
-      }
-      const ProblemSetup &s = setups[i];
-      GroupKey key{s.nx, s.ny, s.num_modes, kind_of(s), s.has_mu ? 1 : 0, prob[i].symmetry[0], prob[i].symmetry[1],
-                   s.jz_axis, s.direction, s.relative ? 1 : 0, s.tensorial ? (s.eps_complex ? 2 : 1) : 0, prob[i].precision == 1 ? 1 : 0,
-                   prob[i].angle_theta, prob[i].angle_phi};
-      groups[key].push_back(i);
-    }
-    h->stats.setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - su0).count();
+    // windows of consecutive problems: a window's raw media are uploaded and scanned together, then its problems are
+    // grouped by (shape, arithmetic kind, ...) and solved in device batches
+    const int wsize = std::max(1, h->opt.max_batch);
     size_t free_b = 0, total_b = 0;
-    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    free_b += h->arena.cap;
-    for (auto &kv : groups) {
-      const std::vector<int> &all = kv.second;
-      const size_t per = bytes_per_problem(setups[all[0]], h->opt);
-      int bmax = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, h->opt.max_batch), (size_t)(0.6 * free_b) / per));
-      for (size_t s0 = 0; s0 < all.size(); s0 += bmax) {
-        std::vector<int> ids(all.begin() + s0, all.begin() + std::min(all.size(), s0 + bmax));
-        const bool f32 = h->opt.mg_precision == 1;
-        switch (kv.first.kind) {
-          case 0:
-            if (f32) solve_group<double, double, float, float>(h, ids, setups, prob, res);
-            else solve_group<double, double, double, double>(h, ids, setups, prob, res);
-            break;
-          case 1:
-            if (f32) solve_group<cplx, double, cplxf, float>(h, ids, setups, prob, res);
-            else solve_group<cplx, double, cplx, double>(h, ids, setups, prob, res);
-            break;
-          default:
-            if (f32) solve_group<cplx, cplx, cplxf, cplxf>(h, ids, setups, prob, res);
-            else solve_group<cplx, cplx, cplx, cplx>(h, ids, setups, prob, res);
-            break;
-        }
-        for (int id : ids)
-          if (res[id].status != B200MS_OK && first_err == B200MS_OK) {
-            first_err = res[id].status;
-            h->err = "eigen-iteration did not converge";
-          }
+    for (int i0 = 0, wi = 0; i0 < nprob; i0 += wsize, ++wi) {
+      const int i1 = std::min(nprob, i0 + wsize);
+      for (int i = i0; i < i1; ++i) {
+        res[i].status = res[i].n_complex ? B200MS_OK : B200MS_ERR_ARG;
+        res[i].converged = 0;
       }
+      Window W;
+      const auto su0 = std::chrono::steady_clock::now();
+      prepare_window(h, prob, i0, i1, h->raw[wi & 1], h->stream, W);
+      h->stats.setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - su0).count();
+      std::map<GroupKey, std::vector<int>> groups;
+      size_t out_bytes = 0;
+      for (int q = 0; q < i1 - i0; ++q) {
+        const int i = i0 + q;
+        const ProblemSetup &s = W.setups[q];
+        if (res[i].status == B200MS_OK) res[i].status = s.status;
+        res[i].eps_spec = s.eps_spec;
+        res[i].is_complex = s.is_complex;
+        if (res[i].status != B200MS_OK) {
+          if (first_err == B200MS_OK) {
+            first_err = res[i].status;
+            h->err = s.error.empty() ? "bad result buffers" : s.error;
+          }
+          continue;
+        }
+        GroupKey key{s.nx, s.ny, s.num_modes, kind_of(s), s.has_mu ? 1 : 0, prob[i].symmetry[0], prob[i].symmetry[1],
+                     s.jz_axis, s.direction, s.relative ? 1 : 0, s.tensorial ? (s.eps_complex ? 2 : 1) : 0, prob[i].precision == 1 ? 1 : 0,
+                     prob[i].angle_theta, prob[i].angle_phi};
+        groups[key].push_back(q);
+        if (res[i].fields) out_bytes += align256((size_t)6 * s.nx * s.ny * s.num_modes * (prob[i].precision == 1 ? 8 : 16));
+      }
+      DevBuf &ob = h->out[wi & 1];
+      ob.reserve(std::max<size_t>(out_bytes + 4096, 4096));
+      CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+      free_b += h->arena.cap;
+      std::vector<FieldCopy> copies;
+      size_t cursor = 0;
+      for (auto &kv : groups) {
+        const std::vector<int> &all = kv.second;
+        const size_t per = bytes_per_problem(W.setups[all[0]], h->opt);
+        int bmax = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, h->opt.max_batch), (size_t)(0.8 * free_b) / per));
+        for (size_t s0 = 0; s0 < all.size(); s0 += bmax) {
+          std::vector<int> ids(all.begin() + s0, all.begin() + std::min(all.size(), s0 + bmax));
+          const ProblemSetup &sg = W.setups[ids[0]];
+          const size_t pb = (size_t)6 * sg.nx * sg.ny * sg.num_modes * (prob[i0 + ids[0]].precision == 1 ? 8 : 16);
+          unsigned char *region = ob.p + cursor;
+          if (cursor + pb * ids.size() > ob.cap) throw std::runtime_error("output buffer accounting error");
+          dispatch_group(kv.first.kind, h->opt.mg_precision == 1, h, ids, W, prob, res, region, copies);
+          bool any_fields = false;
+          for (int id : ids) {
+            if (res[i0 + id].fields) any_fields = true;
+            if (res[i0 + id].status != B200MS_OK && first_err == B200MS_OK) {
+              first_err = res[i0 + id].status;
+              h->err = "eigen-iteration did not converge";
+            }
+          }
+          if (any_fields) cursor += align256(pb * ids.size());
+        }
+      }
+      // deliver the fields of this window (destination may be host or device memory)
+      const auto dl0 = std::chrono::steady_clock::now();
+      for (const FieldCopy &c : copies) CUDA_CHECK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDefault, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      h->stats.download_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dl0).count();
     }
   } catch (const std::exception &e) {
     h->err = e.what();
@@ -367,11 +532,12 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
 // mode 0: the fp64 operator apply of the Krylov iteration (true PML);  mode 1: the production smoother sweep
 // (stored-diagonal Jacobi in the multigrid precision, fp32 by default)
 template <typename T, typename C, typename P, typename PC>
-static void bench_group(b200ms_handle *h, const ProblemSetup &s, int nbatch, int mode, int nrep, int flush_l2,
+static void bench_group(b200ms_handle *h, const Window &W, int nbatch, int mode, int nrep, int flush_l2,
                         const double *x, double *y, double *ms_out, double *bytes_out) {
-  std::vector<const ProblemSetup *> ps(nbatch, &s);
+  std::vector<const ProblemSetup *> ps(nbatch, &W.setups[0]);
+  std::vector<MediumRef> refs(nbatch, W.refs[0]);
   BatchSolver<T, C, P, PC> S(h->arena, h->stream, h->opt);
-  S.build(ps, false);
+  S.build(ps, false, upload_refs(h, refs, h->stream));
   const size_t len = S.len;
   std::vector<T> hx(len);
   std::vector<P> hp(len);
@@ -461,8 +627,9 @@ extern "C" int b200ms_bench_stencil(b200ms_handle *h, const b200ms_problem *prob
   if (!h || !prob || nbatch < 1 || nrep < 1) return B200MS_ERR_ARG;
   if (cudaSetDevice(h->device) != cudaSuccess) return B200MS_ERR_CUDA;
   try {
-    ProblemSetup s;
-    setup_problem(*prob, s);
+    Window W;
+    prepare_window(h, prob, 0, 1, h->raw[0], h->stream, W);
+    const ProblemSetup &s = W.setups[0];
     if (s.status != B200MS_OK) {
       h->err = s.error;
       return s.status;
@@ -470,16 +637,16 @@ extern "C" int b200ms_bench_stencil(b200ms_handle *h, const b200ms_problem *prob
     const bool f32 = h->opt.mg_precision == 1;
     switch (kind_of(s)) {
       case 0:
-        if (f32) bench_group<double, double, float, float>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
-        else bench_group<double, double, double, double>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        if (f32) bench_group<double, double, float, float>(h, W, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        else bench_group<double, double, double, double>(h, W, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
         break;
       case 1:
-        if (f32) bench_group<cplx, double, cplxf, float>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
-        else bench_group<cplx, double, cplx, double>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        if (f32) bench_group<cplx, double, cplxf, float>(h, W, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        else bench_group<cplx, double, cplx, double>(h, W, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
         break;
       default:
-        if (f32) bench_group<cplx, cplx, cplxf, cplxf>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
-        else bench_group<cplx, cplx, cplx, cplx>(h, s, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        if (f32) bench_group<cplx, cplx, cplxf, cplxf>(h, W, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
+        else bench_group<cplx, cplx, cplx, cplx>(h, W, nbatch, mode, nrep, flush_l2, x, y, ms_per_launch, bytes_per_apply);
         break;
     }
   } catch (const std::exception &e) {
@@ -569,11 +736,12 @@ extern "C" int b200ms_debug_hierarchy(const b200ms_problem *prob, const b200ms_o
 // ---- device debug hooks -------------------------------------------------------------------------------
 namespace {
 template <typename T, typename C, typename P, typename PC>
-int debug_run(b200ms_handle *h, const ProblemSetup &s, int what, int level, int mode, const double *in0, const double *in1,
+int debug_run(b200ms_handle *h, const Window &W, int what, int level, int mode, const double *in0, const double *in1,
               double *out, int *iters, double *relres) {
-  std::vector<const ProblemSetup *> ps(1, &s);
+  std::vector<const ProblemSetup *> ps(1, &W.setups[0]);
+  std::vector<MediumRef> refs(1, W.refs[0]);
   BatchSolver<T, C, P, PC> S(h->arena, h->stream, h->opt);
-  S.build(ps, false);
+  S.build(ps, false, upload_refs(h, refs, h->stream));
   if (what == 0 && (level > 0 || mode == 3)) {  // multigrid operator of level `level` in preconditioner precision
     if (level < 0 || level >= (int)S.lv.size()) return B200MS_ERR_ARG;
     const size_t n2 = 2 * S.lv[level].N;
@@ -634,8 +802,9 @@ int debug_dispatch(b200ms_handle *h, const b200ms_problem *prob, int what, int l
   if (!h || !prob || !in0 || !out) return B200MS_ERR_ARG;
   if (cudaSetDevice(h->device) != cudaSuccess) return B200MS_ERR_CUDA;
   try {
-    ProblemSetup s;
-    setup_problem(*prob, s);
+    Window W;
+    prepare_window(h, prob, 0, 1, h->raw[0], h->stream, W);
+    const ProblemSetup &s = W.setups[0];
     if (s.status != B200MS_OK) {
       h->err = s.error;
       return s.status;
@@ -643,14 +812,14 @@ int debug_dispatch(b200ms_handle *h, const b200ms_problem *prob, int what, int l
     const bool f32 = h->opt.mg_precision == 1;
     switch (kind_of(s)) {
       case 0:
-        return f32 ? debug_run<double, double, float, float>(h, s, what, level, mode, in0, in1, out, iters, relres)
-                   : debug_run<double, double, double, double>(h, s, what, level, mode, in0, in1, out, iters, relres);
+        return f32 ? debug_run<double, double, float, float>(h, W, what, level, mode, in0, in1, out, iters, relres)
+                   : debug_run<double, double, double, double>(h, W, what, level, mode, in0, in1, out, iters, relres);
       case 1:
-        return f32 ? debug_run<cplx, double, cplxf, float>(h, s, what, level, mode, in0, in1, out, iters, relres)
-                   : debug_run<cplx, double, cplx, double>(h, s, what, level, mode, in0, in1, out, iters, relres);
+        return f32 ? debug_run<cplx, double, cplxf, float>(h, W, what, level, mode, in0, in1, out, iters, relres)
+                   : debug_run<cplx, double, cplx, double>(h, W, what, level, mode, in0, in1, out, iters, relres);
       default:
-        return f32 ? debug_run<cplx, cplx, cplxf, cplxf>(h, s, what, level, mode, in0, in1, out, iters, relres)
-                   : debug_run<cplx, cplx, cplx, cplx>(h, s, what, level, mode, in0, in1, out, iters, relres);
+        return f32 ? debug_run<cplx, cplx, cplxf, cplxf>(h, W, what, level, mode, in0, in1, out, iters, relres)
+                   : debug_run<cplx, cplx, cplx, cplx>(h, W, what, level, mode, in0, in1, out, iters, relres);
     }
   } catch (const std::exception &e) {
     h->err = e.what();

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/b200ms.h"
+#include "medium.cuh"
 
 namespace b200ms {
 
@@ -72,6 +73,8 @@ struct ProblemSetup {
   std::vector<double> jz_e, jz_h;  // bend back-transform E_z *= jz_e[ix or iy], H_z *= jz_h (solver.py:254-259)
   int jz_axis = -1;          // axis along which jz varies (-1: none)
   double max_k2 = 0;         // max over cells of Re(eps) - target^2 (positive => indefinite region)
+  bool has_pec = false;      // some diagonal eps entry is PEC-valued (solver.py:327-333)
+  int medium = -1;           // slot of the raw eps/mu on the device (product path)
 };
 
 inline cd s_value(double dl, double step, double omega, cd avg_speed) {
@@ -97,50 +100,6 @@ inline void sfactors(double omega, const std::vector<double> &dlf, const std::ve
     else if (i > n - npml)
       sb[i] = s_value(dlb[n - 1], double(i - (n - npml)) / npml, omega, sp_max);
   }
-}
-
-// eps' = J eps J^T / det J and mu' = J J^T / det J (mu = identity) at one cell, for J = [[1,0,a],[0,1,b],[0,0,d]]
-// (angled transform followed by the bend, solver.py:142-172; d differs between E and H sites for a bend)
-inline void transformed_tensors(const cd *eps, const cd *mu, size_t n, size_t c, double a, double b, double d_e, double d_h, cd e[9],
-                                cd m[9]) {
-  cd raw[9];
-  for (int k = 0; k < 9; ++k) raw[k] = eps[(size_t)k * n + c];
-  const double Je[3][3] = {{1, 0, a}, {0, 1, b}, {0, 0, d_e}}, Jh[3][3] = {{1, 0, a}, {0, 1, b}, {0, 0, d_h}};
-  cd tmp[9];
-  for (int i = 0; i < 3; ++i)
-    for (int p2 = 0; p2 < 3; ++p2) {
-      cd acc = 0.0;
-      for (int j = 0; j < 3; ++j) acc += Je[i][j] * raw[3 * j + p2];
-      tmp[3 * i + p2] = acc;
-    }
-  for (int i = 0; i < 3; ++i)
-    for (int p2 = 0; p2 < 3; ++p2) {
-      cd acc = 0.0;
-      for (int j = 0; j < 3; ++j) acc += tmp[3 * i + j] * Je[p2][j];
-      e[3 * i + p2] = acc / d_e;
-    }
-  if (!mu) {
-    for (int i = 0; i < 3; ++i)
-      for (int p2 = 0; p2 < 3; ++p2) {
-        double acc = 0.0;
-        for (int j = 0; j < 3; ++j) acc += Jh[i][j] * Jh[p2][j];
-        m[3 * i + p2] = acc / d_h;
-      }
-    return;
-  }
-  for (int k = 0; k < 9; ++k) raw[k] = mu[(size_t)k * n + c];
-  for (int i = 0; i < 3; ++i)
-    for (int p2 = 0; p2 < 3; ++p2) {
-      cd acc = 0.0;
-      for (int j = 0; j < 3; ++j) acc += Jh[i][j] * raw[3 * j + p2];
-      tmp[3 * i + p2] = acc;
-    }
-  for (int i = 0; i < 3; ++i)
-    for (int p2 = 0; p2 < 3; ++p2) {
-      cd acc = 0.0;
-      for (int j = 0; j < 3; ++j) acc += tmp[3 * i + j] * Jh[p2][j];
-      m[3 * i + p2] = acc / d_h;
-    }
 }
 
 // Frequency-dependent part of the set-up: PML stretch and the k0-scaled lengths of both axes.  Needs s.k0,
@@ -183,16 +142,20 @@ inline bool setup_axes(const b200ms_problem &p, ProblemSetup &s) {
   return der_complex;
 }
 
-// Same cross-section as `ref` (same eps / coords / bend / PML / symmetry), different frequency: share the medium.
-inline void setup_problem_like(const b200ms_problem &p, const ProblemSetup &ref, ProblemSetup &s) {
-  s = ref;
-  s.k0 = 2.0 * M_PI * p.freq / kC0;
-  const bool der_complex = setup_axes(p, s);
-  s.relative = p.basis_e != nullptr;
-  s.is_complex = s.coef_complex || der_complex || s.tensorial || s.relative;
+struct MediumScan {
+  double v[kScanSlots];
+};
+
+inline MediumParams medium_params(const ProblemSetup &s, const b200ms_problem &p, const double *de, const double *dh) {
+  MediumParams m;
+  m.nx = s.nx; m.ny = s.ny; m.npml_x = p.num_pml[0]; m.npml_y = p.num_pml[1];
+  m.a = s.jac_a; m.b = s.jac_b; m.norm_axis = s.jz_axis; m.de = de; m.dh = dh;
+  return m;
 }
 
-inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
+// Stage A of the set-up: everything that does not touch the per-cell medium (solver.py:86-92, 142-162, 187-190;
+// transforms.py:14-111): shapes, k0, k-vector norm, coordinates, grid steps, Jacobian factors.
+inline void setup_geometry(const b200ms_problem &p, ProblemSetup &s) {
   const int nx = p.nx, ny = p.ny;
   s.nx = nx;
   s.ny = ny;
@@ -203,62 +166,32 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
     s.error = "bad problem description";
     return;
   }
-  const size_t n = (size_t)nx * ny;
-  const cd *eps = reinterpret_cast<const cd *>(p.eps);
-  const cd *mu_in = reinterpret_cast<const cd *>(p.mu);
-  if (mu_in) s.has_mu = true;
-  const double omega = 2.0 * M_PI * p.freq;
-  s.k0 = omega / kC0;
+  if (p.mu) s.has_mu = true;
+  s.k0 = 2.0 * M_PI * p.freq / kC0;
   const bool bend = !std::isnan(p.bend_radius);
   const bool angled = std::abs(p.angle_theta) > 0.0;
-
-  // k-vector transformation, solver.py:160-162
-  {
+  {  // k-vector transformation, solver.py:160-162
     double c = std::cos(p.angle_theta), sn = std::sin(p.angle_theta);
     double kxy = c * c, kz = c * sn;
     double a = kxy * std::sin(p.angle_phi), b = kxy * std::cos(p.angle_phi);
     s.knorm = std::sqrt(a * a + b * b + kz * kz);
   }
-  // target, solver.py:204-217
-  if (std::isnan(p.target_neff)) {
-    double mx = 0.0;
-    for (size_t i = 0; i < 9 * n; ++i) {
-      double a = std::abs(eps[i]);
-      if (a < std::abs(kPecVal) && a > mx) mx = a;
-    }
-    s.target = std::sqrt(mx);
-  } else {
-    s.target = p.target_neff;
-  }
-  s.target_raw = s.target;
-  s.target /= s.knorm;
-  const double shift = 10 * kFpEps;
-  if (std::abs(shift) > std::abs(s.target * shift))
-    s.target += shift;
-  else
-    s.target *= 1 + shift;
-  s.sigma = cd(-(s.target * s.target), 0.0);
-
   // coordinates and Jacobian (transforms.py:14-71); only dwdz != 1 for a bend
   std::vector<double> coords[2] = {std::vector<double>(p.coords_x, p.coords_x + nx + 1),
                                    std::vector<double>(p.coords_y, p.coords_y + ny + 1)};
-  std::vector<double> de, dh;  // dwdz at E / H sites along the normal axis
-  int norm_axis = -1;
   if (bend) {
-    norm_axis = (p.bend_axis == 1) ? 0 : 1;
+    const int norm_axis = (p.bend_axis == 1) ? 0 : 1;
     std::vector<double> &c = coords[norm_axis];
     const int nn = (int)c.size() - 1;
     const double off = p.bend_radius - c[nn / 2];
     for (double &v : c) v += off;
-    de.resize(nn);
-    dh.resize(nn);
+    s.jz_e.resize(nn);
+    s.jz_h.resize(nn);
     for (int i = 0; i < nn; ++i) {
-      de[i] = p.bend_radius / c[i];
-      dh[i] = 2.0 * p.bend_radius / (c[i] + c[i + 1]);
+      s.jz_e[i] = p.bend_radius / c[i];
+      s.jz_h[i] = 2.0 * p.bend_radius / (c[i] + c[i + 1]);
     }
     s.jz_axis = norm_axis;
-    s.jz_e = de;
-    s.jz_h = dh;
     s.has_mu = true;
   }
   if (angled) {
@@ -267,112 +200,55 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
     s.jac_b = -std::tan(p.angle_theta) * std::sin(p.angle_phi);
     s.has_mu = true;
   }
-
-  // eps' = J eps J^T / det J with J = diag(1,1,d) (solver.py:165-172); mu' likewise from identity
-  for (int k = 0; k < 6; ++k) s.fp[k] = std::make_shared<std::vector<cd>>(n, cd(1, 0));
-  std::vector<cd> *F[6];
-  for (int k = 0; k < 6; ++k) F[k] = s.fp[k].get();
-  double off_max = 0.0, im2 = 0.0, all2 = 0.0;
-  for (int ix = 0; ix < nx; ++ix)
-    for (int iy = 0; iy < ny; ++iy) {
-      const size_t c = (size_t)ix * ny + iy;
-      double d_e = 1.0, d_h = 1.0;
-      if (bend) {
-        int t = norm_axis == 0 ? ix : iy;
-        d_e = de[t];
-        d_h = dh[t];
-      }
-      cd e[9], m[9];
-      transformed_tensors(eps, mu_in, n, c, s.jac_a, s.jac_b, d_e, d_h, e, m);
-      (*F[0])[c] = e[0];
-      (*F[1])[c] = e[4];
-      (*F[2])[c] = e[8];
-      (*F[3])[c] = m[0];
-      (*F[4])[c] = m[4];
-      (*F[5])[c] = m[8];
-    }
-
   // grid steps, solver.py:187-190
-  std::vector<double> (&dlf)[2] = s.dlf, (&dlb)[2] = s.dlb;
   for (int a = 0; a < 2; ++a) {
     const int nn = a == 0 ? nx : ny;
-    dlf[a].resize(nn);
-    dlb[a].resize(nn);
-    for (int i = 0; i < nn; ++i) dlf[a][i] = coords[a][i + 1] - coords[a][i];
-    dlb[a][0] = dlf[a][0];
-    for (int i = 1; i < nn; ++i) dlb[a][i] = 0.5 * (dlf[a][i - 1] + dlf[a][i]);
+    s.dlf[a].resize(nn);
+    s.dlb[a].resize(nn);
+    for (int i = 0; i < nn; ++i) s.dlf[a][i] = coords[a][i + 1] - coords[a][i];
+    s.dlb[a][0] = s.dlf[a][0];
+    for (int i = 1; i < nn; ++i) s.dlb[a][i] = 0.5 * (s.dlf[a][i - 1] + s.dlf[a][i]);
+    s.ax[a].pos = coords[a];
   }
-  // average relative speed in the four PML strips (derivatives.py:129-155), BEFORE the PEC model
-  cd (&speed)[4] = s.speed;
-  {
+  s.relative = p.basis_e != nullptr;
+}
+
+// Stage C: everything that follows from the reductions over the medium (solver.py:204-217 target; derivatives.py:129-155
+// PML strip speeds; solver.py:336-339 tensorial test; :389-411 complex test).
+inline void finish_setup(const b200ms_problem &p, ProblemSetup &s, const MediumScan &sc) {
+  if (s.status != B200MS_OK) return;
+  const int nx = s.nx, ny = s.ny;
+  if (std::isnan(p.target_neff)) s.target = std::sqrt(sc.v[SC_MAX_ABS_EPS]);
+  else s.target = p.target_neff;
+  s.target_raw = s.target;
+  s.target /= s.knorm;
+  const double shift = 10 * kFpEps;
+  if (std::abs(shift) > std::abs(s.target * shift)) s.target += shift;
+  else s.target *= 1 + shift;
+  s.sigma = cd(-(s.target * s.target), 0.0);
+  {  // average relative speed in the four PML strips: [:npml], [N-npml+1:] (derivatives.py:147-150)
     const int npx = p.num_pml[0], npy = p.num_pml[1];
-    cd esum[4] = {0, 0, 0, 0}, msum[4] = {0, 0, 0, 0};
-    size_t cnt[4] = {0, 0, 0, 0};
-    for (int ix = 0; ix < nx; ++ix)
-      for (int iy = 0; iy < ny; ++iy) {
-        const size_t c = (size_t)ix * ny + iy;
-        bool in[4] = {ix < npx, ix >= nx - npx + 1, iy < npy, iy >= ny - npy + 1};
-        cd es = (*F[0])[c] + (*F[1])[c] + (*F[2])[c], ms = (*F[3])[c] + (*F[4])[c] + (*F[5])[c];
-        for (int r = 0; r < 4; ++r)
-          if (in[r]) {
-            esum[r] += es;
-            msum[r] += ms;
-            cnt[r] += 3;
-          }
-      }
+    auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    const double cells[4] = {(double)clampi(npx, 0, nx) * ny, (double)clampi(npx - 1, 0, nx) * ny, (double)clampi(npy, 0, ny) * nx,
+                             (double)clampi(npy - 1, 0, ny) * nx};
     for (int r = 0; r < 4; ++r) {
-      cd ea = cnt[r] ? esum[r] / double(cnt[r]) : cd(1, 0);
-      cd ma = cnt[r] ? msum[r] / double(cnt[r]) : cd(1, 0);
-      speed[r] = 1.0 / std::sqrt(ea * ma);
+      const double cnt = 3.0 * cells[r];
+      cd ea = cnt > 0 ? cd(sc.v[SC_ESUM + 2 * r], sc.v[SC_ESUM + 2 * r + 1]) / cnt : cd(1, 0);
+      cd ma = cnt > 0 ? cd(sc.v[SC_MSUM + 2 * r], sc.v[SC_MSUM + 2 * r + 1]) / cnt : cd(1, 0);
+      s.speed[r] = 1.0 / std::sqrt(ea * ma);
     }
   }
-  for (int a = 0; a < 2; ++a) s.ax[a].pos = coords[a];
-  bool der_complex = setup_axes(p, s);
-  // PEC -> high-conductivity model (solver.py:327-333), tensorial test (solver.py:336-339),
-  // complex test on the full tensors (solver.py:355, 399-401)
-  const cd pec_model(1.0, std::abs(kPecVal));
-  auto is_pec = [](cd v) { return v.real() < 0.9 * kPecVal || (v.real() == 0.9 * kPecVal && v.imag() <= 0); };
-  double mu_i2 = 0, mu_a2 = 0;
-  for (int ix = 0; ix < nx; ++ix)
-    for (int iy = 0; iy < ny; ++iy) {
-      const size_t c = (size_t)ix * ny + iy;
-      double d_e = bend ? de[norm_axis == 0 ? ix : iy] : 1.0;
-      for (int k = 0; k < 3; ++k) {
-        if (is_pec((*F[k])[c])) (*F[k])[c] = pec_model;
-        im2 += (*F[k])[c].imag() * (*F[k])[c].imag();
-        all2 += std::norm((*F[k])[c]);
-      }
-      const double d_h2 = bend ? dh[norm_axis == 0 ? ix : iy] : 1.0;
-      cd et[9], mt[9];
-      transformed_tensors(eps, mu_in, n, c, s.jac_a, s.jac_b, d_e, d_h2, et, mt);
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) {
-          if (a == b) continue;
-          cd v = et[3 * a + b];
-          if (is_pec(v)) v = pec_model;
-          double av = std::max(std::abs(v), std::abs(mt[3 * a + b]));
-          if (av > off_max) off_max = av;
-          im2 += v.imag() * v.imag();
-          all2 += std::norm(v);
-          mu_i2 += mt[3 * a + b].imag() * mt[3 * a + b].imag();
-          mu_a2 += std::norm(mt[3 * a + b]);
-        }
-      for (int k = 3; k < 6; ++k) {
-        mu_i2 += (*F[k])[c].imag() * (*F[k])[c].imag();
-        mu_a2 += std::norm((*F[k])[c]);
-      }
-      if (std::abs((*F[0])[c]) < 1e7 && std::abs((*F[1])[c]) < 1e7)
-        s.max_k2 = std::max(s.max_k2, std::max((*F[0])[c].real(), (*F[1])[c].real()) - s.target * s.target);
-    }
-  if (off_max > kTolTensorial) s.tensorial = true;
-  const bool eps_complex = std::sqrt(im2) / (std::sqrt(all2) + kFpEps) > kFpEps;
-  const bool mu_complex = std::sqrt(mu_i2) / (std::sqrt(mu_a2) + kFpEps) > kFpEps;
+  const bool der_complex = setup_axes(p, s);
+  if (sc.v[SC_OFF_MAX] > kTolTensorial) s.tensorial = true;
+  const bool eps_complex = std::sqrt(sc.v[SC_IM2]) / (std::sqrt(sc.v[SC_ALL2]) + kFpEps) > kFpEps;
+  const bool mu_complex = std::sqrt(sc.v[SC_MU_IM2]) / (std::sqrt(sc.v[SC_MU_ALL2]) + kFpEps) > kFpEps;
   s.coef_complex = eps_complex || mu_complex;
   s.is_complex = s.coef_complex || der_complex;
-  s.relative = p.basis_e != nullptr;
   if (s.relative) s.is_complex = true;  // the supplied basis is complex (solver.py:771-775)
   s.eps_complex = eps_complex;
   s.mu_complex = mu_complex;
+  s.has_pec = sc.v[SC_HAS_PEC] > 0.5;
+  s.max_k2 = std::max(0.0, sc.v[SC_MAX_RE] - s.target * s.target);
   s.sigma_t = cd(s.target, 0.0);
   if (s.tensorial) {
     s.has_mu = true;      // the tensorial kernels always carry the six diagonal-part fields
@@ -382,38 +258,60 @@ inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
       s.status = B200MS_ERR_UNSUPPORTED;  // solver.py:357-361
       s.error = "Tensorial eps not yet supported in relative mode solver (with basis fields provided).";
     }
-    // derived coefficient fields of the 4N first-order operator (solver.py:604-653), PEC model applied entry-wise
-    for (int k = 0; k < 18; ++k) s.ft[k] = std::make_shared<std::vector<cd>>(n);
-    for (int ix = 0; ix < nx; ++ix)
-      for (int iy = 0; iy < ny; ++iy) {
-        const size_t c = (size_t)ix * ny + iy;
-        const double d_e = bend ? de[norm_axis == 0 ? ix : iy] : 1.0, d_h2 = bend ? dh[norm_axis == 0 ? ix : iy] : 1.0;
-        cd et[9], mt[9];
-        transformed_tensors(eps, mu_in, n, c, s.jac_a, s.jac_b, d_e, d_h2, et, mt);
-        for (int q = 0; q < 9; ++q)
-          if (is_pec(et[q])) et[q] = pec_model;
-        const cd *tt[2] = {et, mt};
-        for (int w = 0; w < 2; ++w) {
-          const cd *t = tt[w];
-          const cd izz = 1.0 / t[8];
-          cd *dst[9];
-          for (int q = 0; q < 9; ++q) dst[q] = &(*s.ft[9 * w + q])[c];
-          *dst[0] = t[6] * izz;                    // t_zx / t_zz
-          *dst[1] = t[7] * izz;                    // t_zy / t_zz
-          *dst[2] = izz;                           // 1 / t_zz
-          *dst[3] = t[5] * izz;                    // t_yz / t_zz
-          *dst[4] = t[2] * izz;                    // t_xz / t_zz
-          *dst[5] = t[0] - t[2] * t[6] * izz;      // S_xx = t_xx - t_xz t_zx / t_zz
-          *dst[6] = t[1] - t[2] * t[7] * izz;      // S_xy
-          *dst[7] = t[3] - t[5] * t[6] * izz;      // S_yx
-          *dst[8] = t[4] - t[5] * t[7] * izz;      // S_yy
-        }
-      }
   }
   if (s.relative && p.num_modes > 20) {
     s.status = B200MS_ERR_UNSUPPORTED;
     s.error = "relative mode solver: at most 20 basis modes";
   }
+}
+
+// Same medium as `ref` (same eps / coords / bend / PML / symmetry), different frequency: only the axes change.
+inline void setup_problem_like(const b200ms_problem &p, const ProblemSetup &ref, ProblemSetup &s) {
+  s = ref;
+  s.k0 = 2.0 * M_PI * p.freq / kC0;
+  const bool der_complex = setup_axes(p, s);
+  s.relative = p.basis_e != nullptr;
+  s.is_complex = s.coef_complex || der_complex || s.tensorial || s.relative;
+}
+
+// ---- host mirror of the device medium kernels (debug hook b200ms_debug_setup and the CPU tests) ------------------
+inline void scan_medium_host(const b200ms_problem &p, const ProblemSetup &s, MediumScan &sc) {
+  const MediumParams mp = medium_params(s, p, s.jz_e.data(), s.jz_h.data());
+  scan_init(sc.v);
+  const cplx *eps = reinterpret_cast<const cplx *>(p.eps), *mu = reinterpret_cast<const cplx *>(p.mu);
+  for (int ix = 0; ix < s.nx; ++ix)
+    for (int iy = 0; iy < s.ny; ++iy) scan_cell(eps, mu, mp, ix, iy, sc.v);
+}
+inline void fill_fields_host(const b200ms_problem &p, ProblemSetup &s) {
+  const MediumParams mp = medium_params(s, p, s.jz_e.data(), s.jz_h.data());
+  const size_t n = (size_t)s.nx * s.ny;
+  const cplx *eps = reinterpret_cast<const cplx *>(p.eps), *mu = reinterpret_cast<const cplx *>(p.mu);
+  for (int k = 0; k < 6; ++k) s.fp[k] = std::make_shared<std::vector<cd>>(n);
+  if (s.tensorial)
+    for (int k = 0; k < 18; ++k) s.ft[k] = std::make_shared<std::vector<cd>>(n);
+  for (int ix = 0; ix < s.nx; ++ix)
+    for (int iy = 0; iy < s.ny; ++iy) {
+      const size_t c = (size_t)ix * s.ny + iy;
+      cplx f[18];
+      cell_fields(eps, mu, mp, ix, iy, f);
+      for (int k = 0; k < 6; ++k) {
+        const cplx v = (k == 2 || k == 5) ? recip(f[k]) : f[k];  // the host mirror stores ezz / mzz themselves
+        (*s.fp[k])[c] = cd(v.re, v.im);
+      }
+      if (s.tensorial) {
+        cell_tensor_fields(eps, mu, mp, ix, iy, f);
+        for (int k = 0; k < 18; ++k) (*s.ft[k])[c] = cd(f[k].re, f[k].im);
+      }
+    }
+}
+
+inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
+  setup_geometry(p, s);
+  if (s.status != B200MS_OK) return;
+  MediumScan sc;
+  scan_medium_host(p, s, sc);
+  finish_setup(p, s, sc);
+  fill_fields_host(p, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -115,7 +115,9 @@ class BatchSolver {
   std::vector<int> level_shapes;
 
   // -- build ---------------------------------------------------------------------------------------
-  void build(const std::vector<const ProblemSetup *> &ps, bool share_fields) {
+  // d_refs: device array of the raw media of the problems (B entries, or one when share_fields): the coefficient fields
+  // are generated on the device from the raw eps/mu uploaded by the caller (csrc/medium.cuh)
+  void build(const std::vector<const ProblemSetup *> &ps, bool share_fields, const MediumRef *d_refs) {
     B = (int)ps.size();
     const ProblemSetup &p0 = *ps[0];
     nx = p0.nx;
@@ -192,7 +194,6 @@ class BatchSolver {
     sz.add<int>((size_t)B + 64);
     sz.add<unsigned char>((size_t)B + 64);
     sz.add<cplx>((size_t)B * k);
-    sz.add<cplx>((size_t)B * 6 * N * k);
     sz.add<double>((size_t)B * 2 * std::max(nx, ny) + 64);
     if (tensor_) {
       sz.add<C>(fB * 18 * N);
@@ -287,24 +288,12 @@ class BatchSolver {
       }
       CUDA_CHECK(cudaStreamSynchronize(st_));
     }
-    // fine-level coefficient fields: exx, eyy, 1/ezz, (mxx, myy, 1/mzz)
+    // fine-level coefficient fields: exx, eyy, 1/ezz, (mxx, myy, 1/mzz) from the raw media, in both precisions at once
     {
-      std::vector<C> hf(fB * nf * N);
-      for (size_t b = 0; b < fB; ++b) {
-        const ProblemSetup &p = *ps[b];
-        for (int q = 0; q < nf; ++q) {
-          const bool inv = (q == 2 || q == 5);
-          C *dst = hf.data() + (b * nf + q) * N;
-          const std::vector<cd> &src = p.f(q);
-          for (size_t i = 0; i < N; ++i) dst[i] = from_cd<C>(inv ? 1.0 / src[i] : src[i]);
-        }
-      }
-      CUDA_CHECK(cudaMemcpyAsync(lv[0].fields_true, hf.data(), hf.size() * sizeof(C), cudaMemcpyHostToDevice, st_));
-      if constexpr (kMixed) {
-        const size_t tot = hf.size();
-        convert_kernel<C, PC><<<(unsigned)std::min<size_t>((tot + 255) / 256, 4096), 256, 0, st_>>>(tot, lv[0].fields_true, lv[0].fields);
-      }
-      CUDA_CHECK(cudaStreamSynchronize(st_));
+      dim3 grd((unsigned)std::min<size_t>((N + 255) / 256, 2048), (unsigned)fB);
+      fields_kernel<C, PC><<<grd, 256, 0, st_>>>(d_refs, nf, lv[0].fields_true, lv[0].fields, (size_t)nf * N);
+      stats.launches++;
+      CUDA_CHECK(cudaGetLastError());
     }
     // transfer lists + coarse fields
     for (int l = 0; l + 1 < L; ++l) {
@@ -364,20 +353,17 @@ class BatchSolver {
     jused_dev_ = arena_.get<int>((size_t)B + 64);
     skip_dev_ = arena_.get<unsigned char>((size_t)B + 64);
     ncomplex_ = arena_.get<cplx>((size_t)B * k);
-    fields_out_ = arena_.get<cplx>((size_t)B * 6 * N * k);
     jz_ = arena_.get<double>((size_t)B * 2 * std::max(nx, ny) + 64);
     if (tensor_) {
       ft_ = arena_.get<C>(fB * 18 * N);
       for (int q = 0; q < 6; ++q) tb_[q] = arena_.get<T>(vsE);
       tcoef_ = arena_.get<cplx>((size_t)B * 8);
-      std::vector<C> hft(fB * 18 * N);
-      for (size_t b = 0; b < fB; ++b)
-        for (int q = 0; q < 18; ++q) {
-          const std::vector<cd> &src = *ps[b]->ft[q];
-          C *dst = hft.data() + (b * 18 + q) * N;
-          for (size_t i = 0; i < N; ++i) dst[i] = from_cd<C>(src[i]);
-        }
-      CUDA_CHECK(cudaMemcpyAsync(ft_, hft.data(), hft.size() * sizeof(C), cudaMemcpyHostToDevice, st_));
+      {
+        dim3 grd((unsigned)std::min<size_t>((N + 255) / 256, 2048), (unsigned)fB);
+        tensor_fields_kernel<C><<<grd, 256, 0, st_>>>(d_refs, ft_, (size_t)18 * N);
+        stats.launches++;
+        CUDA_CHECK(cudaGetLastError());
+      }
       // per-problem scalars of the preconditioner: [0] -sigma_t, [1] i*msign, [2] 1/s, [3] -1/s, [4] 1  (s = -sigma_t^2)
       std::vector<cplx> hc((size_t)B * 8);
       for (int b = 0; b < B; ++b) {
@@ -1550,20 +1536,12 @@ class BatchSolver {
     else epilogue_kernel<T, C, false><<<grd, blk, 0, st_>>>(a);
     CUDA_CHECK(cudaGetLastError());
   }
-  // device -> host copy of the packed fields (kept out of the compute-only timing window)
-  void copy_fields_out(cplx *host_dst_per_problem[]) {
-    const size_t esz = single_out_ ? sizeof(cplxf) : sizeof(cplx);
-    for (int b = 0; b < B; ++b)
-      if (host_dst_per_problem[b])
-        CUDA_CHECK(cudaMemcpyAsync(host_dst_per_problem[b], reinterpret_cast<unsigned char *>(fields_out_) + (size_t)b * 6 * N * k * esz,
-                                   6 * N * k * esz, cudaMemcpyDefault, st_));  // destination may be host or device memory
-    CUDA_CHECK(cudaStreamSynchronize(st_));
-  }
-
   T *scratch_vec(int i) { return i == 0 ? xsol_ : rhs_; }
   T *basis0() { return Vout_; }
   T *gmres_z() { return Zg_; }
   T *gmres_v() { return Vg_; }
+  void set_output(cplx *buf) { fields_out_ = buf; }  // device buffer for the packed fields (owned by the caller)
+  size_t output_bytes_per_problem() const { return (size_t)6 * N * k * (single_out_ ? sizeof(cplxf) : sizeof(cplx)); }
   T *hessenberg() { return Hd_; }
   T *ritz_ptr() { return ritz_; }
 

@@ -1,0 +1,45 @@
+"""DEV TOOL (round 2): parameter sweeps on the headline problem (run under gpurun)."""
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, "/root/repo")
+from tidy3d_b200 import _cabi, compute_modes_batch  # noqa: E402
+from tidy3d_b200 import workloads as W  # noqa: E402
+
+REF = dict(eig_tol=1.1920928955078125e-07, inner_tol=1e-8)
+g = np.load("/root/repo/tests/golden/headline_512_f0.npz")
+
+
+def run(nb, label, n=512, **opts):
+    wl = W.headline(nf=256, n=n)
+    h = _cabi.Handle(**{**REF, "max_batch": 64, **opts})
+    fr = wl.freqs[:nb]
+    probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=f, mode_spec=wl.mode_spec) for f in fr]
+    try:
+        t0 = time.time()
+        out, info = compute_modes_batch(probs, return_info=True, handle=h)
+        dt = time.time() - t0
+        st = h.last_stats()
+        dn = np.abs(out[0][1] - g["n_tight"]).max() if n == 512 else float("nan")
+        print(f"## B={nb} {label} {opts}: |dn| {dn:.1e} op {info[0]['op_applies']} inner {info[0]['inner_iters']} rst {info[0]['restarts']} "
+              f"dev_ms {st['device_ms']:.0f} ({st['device_ms'] / max(1, info[0]['inner_iters']):.2f}/it) wall {dt:.2f} syncs {st['host_syncs']} launches {st['launches']}", flush=True)
+    except Exception as e:  # noqa: BLE001
+        print(f"## B={nb} {label} {opts}: FAILED {e}", flush=True)
+    h.close()
+
+
+which = sys.argv[1:] or ["a"]
+if "a" in which:
+    for nb in (16, 64):
+        run(nb, "legacy", inner_mode=0)
+        run(nb, "new-ir", inner_mode=1)
+        run(nb, "new-ir floor1e-4", inner_mode=1, ir_floor=1e-4)
+        run(nb, "new-ir floor1e-3", inner_mode=1, ir_floor=1e-3)
+        run(nb, "new-fp64", inner_mode=1, inner_ir=0)
+    for ncv in (24, 28, 32, 40):
+        run(16, "legacy ncv", inner_mode=0, ncv=ncv)
+    for kw in (dict(mg_nu=1), dict(mg_nu=3), dict(mg_nu_growth=1), dict(mg_omega=0.7), dict(mg_cycles=2), dict(inner_relax=3.0), dict(inner_relax=10.0),
+               dict(inner_relax_cap=1e-3), dict(gmres_cgs2=0), dict(gmres_cgs2=1), dict(use_graph=0)):
+        run(16, "legacy", inner_mode=0, **kw)
