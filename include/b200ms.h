@@ -36,7 +36,8 @@ enum {
   B200MS_OK = 0,
   B200MS_ERR_SHAPE = 1,       /* ValueError: "Mismatch between 'coords' and 'esp_cross' shapes." (solver.py:107) */
   B200MS_ERR_NO_MODES = 2,    /* RuntimeError: "Could not find any eigenmodes for this waveguide." (solver.py:876) */
-  B200MS_ERR_UNSUPPORTED = 3, /* option outside the built scope (tensorial eps / mu_cross / split-curl / basis fields) */
+  B200MS_ERR_UNSUPPORTED = 3, /* combination the reference itself rejects (tensorial eps + basis fields, solver.py:357-361) or that is
+                                 outside the built scope (basis fields together with removed PEC unknowns) */
   B200MS_ERR_CUDA = 4,        /* CUDA runtime failure or no device -- never falls back to the CPU */
   B200MS_ERR_NOCONV = 5,      /* eigen-iteration did not converge (scipy ArpackNoConvergence analogue) */
   B200MS_ERR_ARG = 6          /* bad argument (null pointer, num_modes < 1, ...) */
@@ -57,6 +58,12 @@ typedef struct {
   int direction;         /* +1 "+", -1 "-" */
   int precision;         /* mode_spec.precision: 0 double, 1 single.  single: result.fields is a complex64 buffer (solver.py:265-267);
                             the eigenproblem itself is always solved to the handle's tolerances */
+  int incidence;         /* 1 when the caller passed mu_cross or split_curl_scaling (solver.py:93 enable_incidence_matrices): Ex/Ey
+                            unknowns on PEC-valued cells are removed and 1/eps_zz is zeroed there (solver.py:441-449, 474-477,
+                            506-508, 568-569); no effect without PEC-valued cells */
+  int post;              /* on-device post-processing of the fields before delivery (ModeSolver.data_raw steps, solver-plane
+                            coordinates): bit 0 = gauge (largest in-plane E entry real positive, mode_solver.py:802-810), bit 1 =
+                            flux normalisation (fields / sqrt|flux|, mode_solver.py:517-521 with monitor_data.py:582-618) */
   double freq;           /* Hz */
   double target_neff;    /* NaN == None */
   double bend_radius;    /* NaN == None */
@@ -77,6 +84,12 @@ typedef struct {
                             layout [E/H][comp][ix][iy][0][mode]; HOST or DEVICE memory (unified addressing; a device buffer
                             keeps the fields in HBM for an NCCL gather or on-device post-processing); NULL skips the fields */
   double *n_complex;     /* caller-allocated num_modes complex128 (re,im): n_eff + i k_eff */
+  double *flux;          /* NULL, or caller-allocated num_modes doubles: flux of every mode BEFORE normalisation (colocated
+                            tangential fields, trapezoid weights; monitor_data.py:523-539, 425-467, 582-618) */
+  double *overlap_prev;  /* NULL, or caller-allocated num_modes^2 complex128 (re,im), row-major [m_prev][m]: modal overlap
+                            dot(mode m_prev of the PREVIOUS problem of this call, mode m of this one) (monitor_data.py:640-697,
+                            after gauge/normalisation), the input of overlap_sort (monitor_data.py:1295-1375).  Zeros when
+                            there is no previous problem or its shape / num_modes / precision differ */
   int eps_spec;          /* out: B200MS_SPEC_* */
   int status;            /* out: per-problem B200MS_* code */
   int converged;         /* out: number of converged modes */
@@ -112,7 +125,8 @@ typedef struct {
   double inner_relax_cap; /* loosest inner tolerance allowed (default 1e-4) */
   int gmres_cgs2;        /* inner FGMRES Gram-Schmidt: 1 always two passes (CGS2); 0 one pass (+ a second on cancellation; measured 3x more
                             iterations at tol 1e-10); 2 (default) one pass while all residuals are > 3e-6, CGS2 below */
-  int stencil_variant;   /* 0: marching kernel (default), 1: shared-memory tiled kernel (reference implementation) */
+  int stencil_variant;   /* 0: marching kernel, rows per CTA chosen by level size (default); 1: shared-memory tiled kernel (reference
+                            implementation); 2: marching kernel with 32 rows per CTA on every level (round-1 behaviour) */
   int mg_nu_growth;      /* extra Jacobi sweeps per coarser level (variable V-cycle), default 0 */
   int use_graph;         /* 1 (default): replay the multigrid V-cycle as one CUDA graph (fp32 multigrid only) */
   int mg_cycles;         /* V-cycles per preconditioner application (default 1) */
@@ -121,8 +135,10 @@ typedef struct {
                             two host read-backs per cycle); 0: the round-1 host-driven FGMRES */
   int inner_ir;          /* 1 (default): run the FGMRES cycles in the multigrid precision (fp32) inside an fp64 iterative
                             refinement (needs mg_precision == 1; diagonal path); 0: fp64 cycles */
-  double ir_floor;       /* smallest residual reduction asked of one fp32 cycle (default 2e-5) */
+  double ir_floor;       /* smallest residual reduction asked of one fp32 cycle (default 1e-4) */
   double ir_trust;       /* solves whose tolerance is >= this accept the fp32 residual estimate without an fp64 check (3e-5) */
+  int outer_dgks;        /* 1 (default): Krylov-Schur orthogonalisation reorthogonalises only when ARPACK's DGKS test asks for it;
+                            0: always two Gram-Schmidt passes */
 } b200ms_options;
 
 /* Counters of the most recent b200ms_solve_batch call on a handle (all its device batches together). */

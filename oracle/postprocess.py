@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the post-processing ``ModeSolver.data_raw`` applies to the output of
+``compute_modes``, in solver-plane coordinates (propagation along z; the rotation to the simulation's
+axes, mode_solver.py:788-792, is a relabelling of arrays and is not restated).
+
+PARITY UNPINNED for this file as a whole: ``ModeSolverData`` needs xarray / shapely / the full tidy3d package, which this
+image lacks, so no fixture could be generated from the unmodified reference.  Each function cites the
+reference lines it follows; the pieces that have an available third-party ground truth are pinned in
+tests/test_postprocess_cpu.py: the colocation against ``scipy.interpolate.interp1d`` (what ``xarray.DataArray.interp``
+calls for 1-D linear interpolation) and the integration weights against ``numpy.trapz``.
+
+Yee sites of the six components in the solver plane (tidy3d/components/grid/grid.py ``Grid.yee``; c = cell centre,
+b = lower cell boundary):  Ex (c,b)  Ey (b,c)  Ez (b,b)  Hx (b,c)  Hy (c,b)  Hz (c,c).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SITES = {"Ex": ("c", "b"), "Ey": ("b", "c"), "Ez": ("b", "b"), "Hx": ("b", "c"), "Hy": ("c", "b"), "Hz": ("c", "c")}
+COMP = {"Ex": (0, 0), "Ey": (0, 1), "Ez": (0, 2), "Hx": (1, 0), "Hy": (1, 1), "Hz": (1, 2)}
+
+
+def gauge(fields):
+    """mode_solver.py:802-810: per mode, rotate the phase so that the largest-|.| in-plane E entry is real positive.
+    ``fields`` (2,3,Nx,Ny,1,M) -> (gauged copy, phi[M]).  ``np.argmax`` takes the FIRST maximum in C order of E[:2]."""
+    out = np.array(fields, dtype=complex, copy=True)
+    phis = np.zeros(out.shape[-1])
+    for m in range(out.shape[-1]):
+        e = out[0, :2, ..., m]
+        ind = np.argmax(np.abs(e))
+        phi = np.angle(e.ravel()[ind])
+        out[..., m] *= np.exp(-1j * phi)
+        phis[m] = phi
+    return out, phis
+
+
+def colocation_points(coords, symmetry=(0, 0)):
+    """mode_solver.py:494-502: interior cell boundaries; with a symmetry plane at the min side the first boundary is kept."""
+    pts = []
+    for c, s in zip(coords, symmetry):
+        c = np.asarray(c, float)
+        if c.size > 2:
+            pts.append(c[1:-1] if s == 0 else c[:-1])
+        else:
+            pts.append(None)  # a one-cell axis is not interpolated
+    return pts
+
+
+def _site_coords(coords, kind):
+    c = np.asarray(coords, float)
+    return 0.5 * (c[:-1] + c[1:]) if kind == "c" else c[:-1]
+
+
+def interp_weights(src, dst):
+    """Linear interpolation src -> dst as (i0, w0, i1, w1) per destination point; points outside [src[0], src[-1]] get
+    zero weights (xarray/scipy return NaN there and the reference's ``.sum`` skips NaN, monitor_data.py:532-539, 611)."""
+    src, dst = np.asarray(src, float), np.asarray(dst, float)
+    i1 = np.searchsorted(src, dst, side="left")
+    i0 = np.clip(i1 - 1, 0, src.size - 1)
+    i1 = np.clip(i1, 0, src.size - 1)
+    w1 = np.where(src[i1] > src[i0], (dst - src[i0]) / np.where(src[i1] > src[i0], src[i1] - src[i0], 1.0), 0.0)
+    exact = dst == src[i1]
+    w0 = np.where(exact, 0.0, 1.0 - w1)
+    w1 = np.where(exact, 1.0, w1)
+    outside = (dst < src[0]) | (dst > src[-1])
+    return i0, np.where(outside, 0.0, w0), i1, np.where(outside, 0.0, w1)
+
+
+def colocate(fields, coords, symmetry=(0, 0)):
+    """mode_solver.py:504-507 / monitor_data.py:523-539: every component linearly interpolated from its Yee sites to the
+    colocation points.  Returns dict name -> (Px, Py, M) arrays."""
+    pts = colocation_points(coords, symmetry)
+    out = {}
+    for name, (kx, ky) in SITES.items():
+        f = np.asarray(fields)[COMP[name][0], COMP[name][1], :, :, 0, :]
+        for ax, (kind, p) in enumerate(zip((kx, ky), pts)):
+            if p is None:
+                continue
+            i0, w0, i1, w1 = interp_weights(_site_coords(coords[ax], kind), p)
+            shape = [1, 1, 1]
+            shape[ax] = -1
+            f = np.take(f, i0, axis=ax) * w0.reshape(shape) + np.take(f, i1, axis=ax) * w1.reshape(shape)
+        out[name] = f
+    return out
+
+
+def diff_area(coords, symmetry=(0, 0)):
+    """monitor_data.py:425-467 for data colocated at the points of ``colocation_points``: cell sizes from the mid-points
+    between neighbouring points, closed with the first and last point (trapezoid weights); a one-cell axis has size 1."""
+    sizes = []
+    for p in colocation_points(coords, symmetry):
+        if p is None or p.size == 1:
+            sizes.append(np.array([1.0]))
+            continue
+        ctr = 0.5 * (p[1:] + p[:-1])
+        ext = np.concatenate(([p[0]], ctr, [p[-1]]))
+        sizes.append(ext[1:] - ext[:-1])
+    return np.outer(sizes[0], sizes[1])
+
+
+def flux(fields, coords, symmetry=(0, 0)):
+    """monitor_data.py:582-618: 0.5 Re(E1 H2* - E2 H1*) of the colocated tangential fields integrated with ``diff_area``;
+    a symmetry plane doubles the integral (symmetry_expanded mirrors the half domain)."""
+    c = colocate(fields, coords, symmetry)
+    s = 0.5 * np.real(c["Ex"] * np.conj(c["Hy"]) - c["Ey"] * np.conj(c["Hx"]))
+    mult = 2 ** sum(1 for q in symmetry if q != 0)
+    return mult * np.einsum("xym,xy->m", s, diff_area(coords, symmetry))
+
+
+def normalize(fields, coords, symmetry=(0, 0)):
+    """mode_solver.py:517-521: all six components divided by sqrt(|flux|)."""
+    fl = flux(fields, coords, symmetry)
+    return np.asarray(fields) / np.sqrt(np.abs(fl)), fl
+
+
+def dot(fields_a, fields_b, coords, symmetry=(0, 0), conjugate=True):
+    """monitor_data.py:640-697: M_a x M_b matrix  1/4 sum (E_a* x H_b + H_a* ... ) dS  of the colocated tangential fields
+    (``outer_dot`` for all pairs)."""
+    a, b = colocate(fields_a, coords, symmetry), colocate(fields_b, coords, symmetry)
+    if conjugate:
+        a = {k: np.conj(v) for k, v in a.items()}
+    da = diff_area(coords, symmetry)
+    mult = 2 ** sum(1 for q in symmetry if q != 0)
+
+    def integ(x, y):
+        return np.einsum("xym,xyn,xy->mn", x, y, da)
+
+    e_x_h = integ(a["Ex"], b["Hy"]) - integ(a["Ey"], b["Hx"])
+    h_x_e = integ(a["Hx"], b["Ey"]) - integ(a["Hy"], b["Ex"])
+    return 0.25 * mult * (e_x_h - h_x_e)
+
+
+def find_closest_pairs(arr):
+    """monitor_data.py:1421-1440 (``_find_closest_pairs``): greedy pairing by largest |overlap|."""
+    arr = np.asarray(arr)
+    n = arr.shape[0]
+    arr_abs = np.abs(arr).astype(float)
+    pairs = -np.ones(n, dtype=int)
+    values = np.zeros(n, dtype=complex)
+    for _ in range(n):
+        imax, jmax = np.unravel_index(np.argmax(arr_abs, axis=None), arr_abs.shape)
+        pairs[imax] = jmax
+        values[imax] = arr[imax, jmax]
+        arr_abs[imax, :] = -1
+        arr_abs[:, jmax] = -1
+    return pairs, values
+
+
+def find_ordering_one_freq(amps_matrix, overlap_thresh=0.9, direction="+"):
+    """monitor_data.py:1378-1419 given the full M x M overlap matrix template -> to_sort: modes whose diagonal overlap is
+    already above the threshold stay, the rest are re-paired."""
+    amps_matrix = np.array(amps_matrix, dtype=complex)
+    if direction == "-":
+        amps_matrix = -amps_matrix
+    m = amps_matrix.shape[0]
+    pairs = np.arange(m)
+    complex_amps = np.diag(amps_matrix).copy()
+    to_sort = np.where(np.abs(complex_amps) < overlap_thresh)[0]
+    if len(to_sort) <= 1:
+        return pairs, complex_amps
+    pr, vals = find_closest_pairs(amps_matrix[np.ix_(to_sort, to_sort)])
+    complex_amps[to_sort] = vals
+    pairs[to_sort] = to_sort[pr]
+    return pairs, complex_amps
+
+
+def overlap_sort(overlaps_next, num_freqs, num_modes, track_freq="central", overlap_thresh=0.9, direction="+"):
+    """monitor_data.py:1295-1375.  ``overlaps_next[i]`` = dot(modes at f_i, modes at f_{i+1}) (M x M, already normalised
+    fields), i < num_freqs - 1.  Returns (sorting[F,M], phase[F,M], overlap[F,M])."""
+    f0 = {"lowest": 0, "highest": num_freqs - 1, "central": num_freqs // 2}[track_freq]
+    sorting = -np.ones((num_freqs, num_modes), dtype=int)
+    overlap = np.zeros((num_freqs, num_modes))
+    phase = np.zeros((num_freqs, num_modes))
+    sorting[f0] = np.arange(num_modes)
+    overlap[f0] = 1.0
+    for step, last in ((-1, -1), (1, num_freqs)):
+        for fi in range(f0 + step, last, step):
+            # template = previous frequency (fi - step), to_sort = fi;  dot(template, to_sort)
+            if step == 1:
+                mat = overlaps_next[fi - 1]
+            else:  # dot(f_{i+1}, f_i) = conj(dot(f_i, f_{i+1}))^T term by term (monitor_data.py:680-697)
+                mat = np.conj(overlaps_next[fi]).T
+            one, amps = find_ordering_one_freq(mat, overlap_thresh, direction)
+            sorting[fi] = one[sorting[fi - step]]
+            overlap[fi] = np.abs(amps[sorting[fi - step]])
+            phase[fi] = phase[fi - step] + np.angle(amps[sorting[fi - step]])
+    return sorting, phase, overlap

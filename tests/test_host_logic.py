@@ -145,9 +145,3 @@ def test_input_validation(built_lib):
         built_lib.PackedProblem(wl.eps_cross[:8], wl.coords, wl.freqs[0], wl.mode_spec)
     with pytest.raises(ValueError, match="Wrong input to mode solver"):
         built_lib.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, mu_cross=wl.eps_cross[:5])
-    from tidy3d_b200.solver import compute_modes
-
-    pec = [e.copy() for e in wl.eps_cross]
-    pec[0][3:6, 3:6] = -1e8
-    with pytest.raises(NotImplementedError, match="incidence"):  # PEC cells + mu_cross: solver.py:441-449 not built
-        compute_modes(pec, wl.coords, wl.freqs[0], wl.mode_spec, mu_cross=wl.eps_cross)

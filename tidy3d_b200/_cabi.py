@@ -27,7 +27,7 @@ _ip = C.POINTER(C.c_int)
 class Problem(C.Structure):
     _fields_ = [
         ("nx", C.c_int), ("ny", C.c_int), ("num_modes", C.c_int), ("num_pml", C.c_int * 2),
-        ("symmetry", C.c_int * 2), ("bend_axis", C.c_int), ("direction", C.c_int), ("precision", C.c_int),
+        ("symmetry", C.c_int * 2), ("bend_axis", C.c_int), ("direction", C.c_int), ("precision", C.c_int), ("incidence", C.c_int), ("post", C.c_int),
         ("freq", C.c_double), ("target_neff", C.c_double), ("bend_radius", C.c_double),
         ("angle_theta", C.c_double), ("angle_phi", C.c_double),
         ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp), ("mu", _dp), ("basis_e", _dp),
@@ -36,7 +36,7 @@ class Problem(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [
-        ("fields", _dp), ("n_complex", _dp), ("eps_spec", C.c_int), ("status", C.c_int), ("converged", C.c_int),
+        ("fields", _dp), ("n_complex", _dp), ("flux", _dp), ("overlap_prev", _dp), ("eps_spec", C.c_int), ("status", C.c_int), ("converged", C.c_int),
         ("outer_iters", C.c_int), ("op_applies", C.c_int), ("inner_iters", C.c_int), ("stencil_applies", C.c_int),
         ("is_complex", C.c_int), ("solve_ms", C.c_double), ("total_ms", C.c_double), ("max_residual", C.c_double),
     ]  # fmt: skip
@@ -48,7 +48,7 @@ class Options(C.Structure):
         ("gmres_restart", C.c_int), ("gmres_maxit", C.c_int), ("mg_nu", C.c_int), ("mg_min_size", C.c_int),
         ("mg_coarse_iters", C.c_int), ("max_batch", C.c_int), ("mg_omega", C.c_double), ("mg_ppw", C.c_double),
         ("verbose", C.c_int), ("mg_pml_phase", C.c_double), ("inner_relax", C.c_double), ("inner_relax_cap", C.c_double), ("gmres_cgs2", C.c_int), ("stencil_variant", C.c_int), ("mg_nu_growth", C.c_int), ("use_graph", C.c_int), ("mg_cycles", C.c_int), ("mg_precision", C.c_int),
-        ("inner_mode", C.c_int), ("inner_ir", C.c_int), ("ir_floor", C.c_double), ("ir_trust", C.c_double),
+        ("inner_mode", C.c_int), ("inner_ir", C.c_int), ("ir_floor", C.c_double), ("ir_trust", C.c_double), ("outer_dgks", C.c_int),
     ]  # fmt: skip
 
 
@@ -114,7 +114,7 @@ class PackedProblem:
     """Owns the contiguous arrays a ``Problem`` struct points to."""
 
     def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None, basis_fields=None,
-                 mu_cross=None, target_override=None):
+                 mu_cross=None, target_override=None, incidence=False, post=0):
         if eps_packed is not None:
             eps = eps_packed
         elif isinstance(eps_cross, np.ndarray) and eps_cross.dtype == np.complex128 and eps_cross.flags.c_contiguous and eps_cross.ndim == 3:
@@ -152,6 +152,8 @@ class PackedProblem:
         p.bend_axis = -1 if ba is None else int(ba)
         p.direction = -1 if direction == "-" else 1
         p.precision = 1 if getattr(mode_spec, "precision", "single") == "single" else 0
+        p.incidence = 1 if incidence else 0
+        p.post = int(post)
         p.freq = float(freq)
         tn = getattr(mode_spec, "target_neff", None) if target_override is None else target_override
         p.target_neff = math.nan if tn is None else float(tn)
@@ -191,7 +193,7 @@ class PinnedPool:
     faults).  A buffer returns to the pool when the numpy array built on it (and every view of it) is garbage
     collected; at most ``max_cached`` bytes are kept, the rest is freed."""
 
-    def __init__(self, max_cached=8 << 30):
+    def __init__(self, max_cached=int(os.environ.get("B200MS_PINNED_CACHE_GB", "48")) << 30):
         self.free = {}
         self.cached = 0
         self.max_cached = max_cached
@@ -272,7 +274,7 @@ class Handle:
         except Exception:
             pass
 
-    def solve_batch(self, packed, want_fields=True, fields_ptrs=None):
+    def solve_batch(self, packed, want_fields=True, fields_ptrs=None, want_flux=False, want_overlaps=False):
         """packed: list of PackedProblem.  Returns (rc, fields list | None, n_complex list, Result structs).
 
         ``fields_ptrs``: optional list of raw addresses (host or DEVICE memory, e.g. ``tensor.data_ptr()``) the library
@@ -282,10 +284,19 @@ class Handle:
         probs = (Problem * n)(*[p.struct for p in packed])
         results = (Result * n)()
         fields, ncs = [], []
+        self.last_flux, self.last_overlaps = [], []
         for i, p in enumerate(packed):
             nc = np.zeros(p.num_modes, dtype=np.complex128)
             ncs.append(nc)
             results[i].n_complex = _ptr(nc.view(np.float64))
+            if want_flux:
+                fl = np.zeros(p.num_modes)
+                self.last_flux.append(fl)
+                results[i].flux = _ptr(fl)
+            if want_overlaps:
+                ov = np.zeros((p.num_modes, p.num_modes), dtype=np.complex128)
+                self.last_overlaps.append(ov)
+                results[i].overlap_prev = _ptr(ov.view(np.float64))
             if fields_ptrs is not None:
                 results[i].fields = C.cast(C.c_void_p(int(fields_ptrs[i])), _dp)
             elif want_fields:

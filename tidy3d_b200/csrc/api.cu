@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <future>
 #include <map>
 #include <memory>
 #include <string>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "../../include/b200ms.h"
+#include "post.cuh"
 #include "solver.cuh"
 
 using namespace b200ms;
@@ -38,12 +40,14 @@ struct DevBuf {
 struct b200ms_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t io_stream = nullptr;  // uploads of raw media / downloads of fields
+  cudaStream_t io_stream = nullptr;  // uploads of raw media (+ scan kernels)
+  cudaStream_t dl_stream = nullptr;  // delivery of packed fields
   Arena arena;
   DevBuf raw[2];      // raw eps/mu of a window of problems (+ bend factors), double-buffered
   DevBuf out[2];      // packed fields of a window, double-buffered
   DevBuf scan;        // reduction scratch + per-medium results of prepare_window
   DevBuf refs;        // MediumRef array of the batch being built
+  DevBuf post;        // interpolation tables / partials / results of the on-device post-processing
   b200ms_options opt;
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -79,8 +83,9 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->inner_relax_cap = 1e-4;
   o->inner_mode = 1;
   o->inner_ir = 1;
-  o->ir_floor = 2e-5;
+  o->ir_floor = 1e-4;
   o->ir_trust = 3e-5;
+  o->outer_dgks = 1;
 }
 
 extern "C" int b200ms_create(int device, b200ms_handle **out) {
@@ -97,6 +102,7 @@ extern "C" int b200ms_create(int device, b200ms_handle **out) {
   b200ms_default_options(&h->opt);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->dl_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
     delete h;
     return B200MS_ERR_CUDA;
@@ -115,7 +121,9 @@ extern "C" int b200ms_destroy(b200ms_handle *h) {
   }
   h->scan.release();
   h->refs.release();
+  h->post.release();
   if (h->io_stream) cudaStreamDestroy(h->io_stream);
+  if (h->dl_stream) cudaStreamDestroy(h->dl_stream);
   if (h->flush_buf) cudaFree(h->flush_buf);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -153,21 +161,21 @@ extern "C" int b200ms_get_stats(b200ms_handle *h, b200ms_stats *out) {
 namespace {
 
 struct GroupKey {
-  int nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens, prec;
+  int nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens, prec, masked;
   double theta, phi;
   bool operator<(const GroupKey &o) const {
-    return std::tie(nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens, prec, theta, phi) <
-           std::tie(o.nx, o.ny, o.k, o.kind, o.has_mu, o.sx, o.sy, o.jz_axis, o.dir, o.rel, o.tens, o.prec, o.theta, o.phi);
+    return std::tie(nx, ny, k, kind, has_mu, sx, sy, jz_axis, dir, rel, tens, prec, masked, theta, phi) <
+           std::tie(o.nx, o.ny, o.k, o.kind, o.has_mu, o.sx, o.sy, o.jz_axis, o.dir, o.rel, o.tens, o.prec, o.masked, o.theta, o.phi);
   }
 };
 struct MediumKey {
   const double *eps, *mu, *cx, *cy;
-  int nx, ny, p0, p1, bend_axis;
+  int nx, ny, p0, p1, bend_axis, incidence;
   double bend_radius, theta, phi;
   bool operator==(const MediumKey &o) const {
     auto same = [](double a, double b) { return (std::isnan(a) && std::isnan(b)) || a == b; };
     return eps == o.eps && mu == o.mu && cx == o.cx && cy == o.cy && nx == o.nx && ny == o.ny && p0 == o.p0 && p1 == o.p1 &&
-           bend_axis == o.bend_axis && same(bend_radius, o.bend_radius) && theta == o.theta && phi == o.phi;
+           bend_axis == o.bend_axis && incidence == o.incidence && same(bend_radius, o.bend_radius) && theta == o.theta && phi == o.phi;
   }
 };
 // kind: 0 real, 1 complex vectors + real fields, 2 all complex
@@ -201,7 +209,8 @@ void prepare_window(b200ms_handle *h, const b200ms_problem *prob, int i0, int i1
     ProblemSetup &s = W.setups[q];
     setup_geometry(p, s);
     if (s.status != B200MS_OK) continue;
-    MediumKey mk{p.eps, p.mu, p.coords_x, p.coords_y, p.nx, p.ny, p.num_pml[0], p.num_pml[1], p.bend_axis, p.bend_radius, p.angle_theta, p.angle_phi};
+    MediumKey mk{p.eps, p.mu, p.coords_x, p.coords_y, p.nx, p.ny, p.num_pml[0], p.num_pml[1], p.bend_axis, p.incidence ? 1 : 0,
+                 p.bend_radius, p.angle_theta, p.angle_phi};
     auto it = std::find_if(seen.begin(), seen.end(), [&](const std::pair<MediumKey, int> &e) { return e.first == mk; });
     if (it != seen.end()) {
       W.slot[q] = W.slot[it->second];
@@ -279,6 +288,222 @@ const MediumRef *upload_refs(b200ms_handle *h, const std::vector<MediumRef> &ref
   return d;
 }
 
+
+// ---- on-device post-processing (csrc/post.cuh) ----------------------------------------------------------------------
+// 1-D tables of one axis: colocation points = interior cell boundaries (mode_solver.py:494-502), linear interpolation from
+// the centre / boundary Yee sites (monitor_data.py:523-539), trapezoid weights (monitor_data.py:425-467).
+struct HostAxisTables {
+  std::vector<int> ci0, ci1, bi0, bi1;
+  std::vector<double> cw0, cw1, bw0, bw1, area;
+  int P = 0;
+};
+void interp_row(const std::vector<double> &src, double d, int &i0, double &w0, int &i1, double &w1) {
+  const int n = (int)src.size();
+  int hi = (int)(std::lower_bound(src.begin(), src.end(), d) - src.begin());
+  i0 = std::min(std::max(hi - 1, 0), n - 1);
+  i1 = std::min(std::max(hi, 0), n - 1);
+  w1 = src[i1] > src[i0] ? (d - src[i0]) / (src[i1] - src[i0]) : 0.0;
+  if (d == src[i1]) {
+    w0 = 0.0;
+    w1 = 1.0;
+  } else {
+    w0 = 1.0 - w1;
+  }
+  if (d < src.front() || d > src.back()) w0 = w1 = 0.0;  // NaN in the reference, skipped by its sums
+}
+void axis_tables(const double *coords, int n, int sym, HostAxisTables &t) {
+  std::vector<double> pts;
+  if (n + 1 > 2) {
+    for (int i = (sym == 0 ? 1 : 0); i < n; ++i) pts.push_back(coords[i]);
+  }
+  t.P = pts.empty() ? 1 : (int)pts.size();
+  t.ci0.assign(t.P, 0); t.ci1.assign(t.P, 0); t.bi0.assign(t.P, 0); t.bi1.assign(t.P, 0);
+  t.cw0.assign(t.P, 1.0); t.cw1.assign(t.P, 0.0); t.bw0.assign(t.P, 1.0); t.bw1.assign(t.P, 0.0); t.area.assign(t.P, 1.0);
+  if (pts.empty()) return;  // a one-cell axis is not interpolated and has unit size
+  std::vector<double> cen(n), bnd(n);
+  for (int i = 0; i < n; ++i) {
+    cen[i] = 0.5 * (coords[i] + coords[i + 1]);
+    bnd[i] = coords[i];
+  }
+  for (int p = 0; p < t.P; ++p) {
+    interp_row(cen, pts[p], t.ci0[p], t.cw0[p], t.ci1[p], t.cw1[p]);
+    interp_row(bnd, pts[p], t.bi0[p], t.bw0[p], t.bi1[p], t.bw1[p]);
+  }
+  if (t.P == 1) return;
+  for (int p = 0; p < t.P; ++p) {
+    const double lo = p == 0 ? pts[0] : 0.5 * (pts[p - 1] + pts[p]);
+    const double hi = p == t.P - 1 ? pts[t.P - 1] : 0.5 * (pts[p] + pts[p + 1]);
+    t.area[p] = hi - lo;
+  }
+}
+
+struct PostBatch {  // device-side description of the problems of one device batch (kept until the window's overlaps are done)
+  std::vector<PostProblem> pp;
+};
+
+// Gauge / flux / normalisation of the B problems whose packed fields start at `region` (stride `per` bytes).
+void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, const b200ms_problem *prob, b200ms_result *res,
+                unsigned char *region, size_t per) {
+  const int B = (int)ids.size();
+  const b200ms_problem &p0 = prob[W.i0 + ids[0]];
+  const int nx = p0.nx, ny = p0.ny, M = p0.num_modes;
+  bool any = false;
+  for (int b = 0; b < B; ++b)
+    if (prob[W.i0 + ids[b]].post || res[W.i0 + ids[b]].flux) any = true;
+  if (!any) return;
+  if (M > kPostMaxModes) throw std::runtime_error("post-processing supports at most 64 modes");
+  // pack the tables of all problems into one upload
+  std::vector<HostAxisTables> tx(B), ty(B);
+  size_t ints = 0, dbls = 0;
+  for (int b = 0; b < B; ++b) {
+    const b200ms_problem &p = prob[W.i0 + ids[b]];
+    axis_tables(p.coords_x, nx, p.symmetry[0], tx[b]);
+    axis_tables(p.coords_y, ny, p.symmetry[1], ty[b]);
+    ints += 4 * (size_t)(tx[b].P + ty[b].P);
+    dbls += 5 * (size_t)(tx[b].P + ty[b].P);
+  }
+  const size_t off_d = align256(ints * sizeof(int)), off_pp = off_d + align256(dbls * sizeof(double));
+  const size_t off_part = off_pp + align256((size_t)B * sizeof(PostProblem));
+  const size_t off_flux = off_part + align256((size_t)B * kPostChunks * M * 5 * sizeof(double));
+  const size_t off_scal = off_flux + align256((size_t)B * M * sizeof(double));
+  const size_t total = off_scal + align256((size_t)B * M * sizeof(cplx));
+  h->post.reserve(total + 4096);
+  std::vector<int> hi(ints);
+  std::vector<double> hd(dbls);
+  std::vector<PostProblem> pp(B);
+  size_t ci = 0, cd = 0;
+  int *di = reinterpret_cast<int *>(h->post.p);
+  double *dd = reinterpret_cast<double *>(h->post.p + off_d);
+  auto put = [&](const HostAxisTables &t, PostAxis &a) {
+    a.P = t.P;
+    auto pi = [&](const std::vector<int> &v) { const int *r = di + ci; std::copy(v.begin(), v.end(), hi.begin() + ci); ci += v.size(); return r; };
+    auto pd = [&](const std::vector<double> &v) { const double *r = dd + cd; std::copy(v.begin(), v.end(), hd.begin() + cd); cd += v.size(); return r; };
+    a.c_i0 = pi(t.ci0); a.c_i1 = pi(t.ci1); a.b_i0 = pi(t.bi0); a.b_i1 = pi(t.bi1);
+    a.c_w0 = pd(t.cw0); a.c_w1 = pd(t.cw1); a.b_w0 = pd(t.bw0); a.b_w1 = pd(t.bw1); a.area = pd(t.area);
+  };
+  int do_gauge = 0, do_norm = 0;
+  for (int b = 0; b < B; ++b) {
+    const b200ms_problem &p = prob[W.i0 + ids[b]];
+    put(tx[b], pp[b].ax);
+    put(ty[b], pp[b].ay);
+    pp[b].fields = region + (size_t)b * per;
+    pp[b].mult = (p.symmetry[0] != 0 ? 2.0 : 1.0) * (p.symmetry[1] != 0 ? 2.0 : 1.0);
+    pp[b].flags = p.post;
+    do_gauge |= p.post & 1;
+    do_norm |= p.post & 2;
+  }
+  cudaStream_t st = h->stream;
+  CUDA_CHECK(cudaMemcpyAsync(di, hi.data(), ints * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dd, hd.data(), dbls * sizeof(double), cudaMemcpyHostToDevice, st));
+  PostProblem *dpp = reinterpret_cast<PostProblem *>(h->post.p + off_pp);
+  CUDA_CHECK(cudaMemcpyAsync(dpp, pp.data(), (size_t)B * sizeof(PostProblem), cudaMemcpyHostToDevice, st));
+  double *dpart = reinterpret_cast<double *>(h->post.p + off_part), *dflux = reinterpret_cast<double *>(h->post.p + off_flux);
+  cplx *dscal = reinterpret_cast<cplx *>(h->post.p + off_scal);
+  const bool single = p0.precision == 1;
+  const int nch = (int)std::min<size_t>(kPostChunks, ((size_t)2 * nx * ny + 255) / 256);
+  dim3 g1(nch, B);
+  if (single) post_scan_kernel<cplxf><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
+  else post_scan_kernel<cplx><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
+  post_final_kernel<<<B, std::max(32, ((M + 31) / 32) * 32), 0, st>>>(dpp, dpart, nch, M, dflux, dscal);
+  if (do_gauge || do_norm) {
+    dim3 g2((unsigned)std::min<size_t>(((size_t)6 * nx * ny * M + 255) / 256, 2048), B);
+    if (single) post_apply_kernel<cplxf><<<g2, 256, 0, st>>>(dpp, (size_t)6 * nx * ny, M, dscal);
+    else post_apply_kernel<cplx><<<g2, 256, 0, st>>>(dpp, (size_t)6 * nx * ny, M, dscal);
+  }
+  std::vector<double> hflux((size_t)B * M);
+  CUDA_CHECK(cudaMemcpyAsync(hflux.data(), dflux, hflux.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.launches += 3;
+  for (int b = 0; b < B; ++b)
+    if (res[W.i0 + ids[b]].flux) std::copy(hflux.begin() + (size_t)b * M, hflux.begin() + (size_t)(b + 1) * M, res[W.i0 + ids[b]].flux);
+}
+
+// Modal overlaps between consecutive problems of the call (result.overlap_prev) for the problems [i0, i1); dev_fields[i] is
+// the device address of the packed fields of problem i (null if not produced).
+void post_overlaps(b200ms_handle *h, const b200ms_problem *prob, b200ms_result *res, int i0, int i1, const std::vector<const void *> &dev_fields) {
+  struct Job { int i; };
+  std::vector<int> todo;
+  for (int i = i0; i < i1; ++i) {
+    if (!res[i].overlap_prev || res[i].status != B200MS_OK) continue;
+    const int M = prob[i].num_modes;
+    std::fill(res[i].overlap_prev, res[i].overlap_prev + (size_t)2 * M * M, 0.0);
+    if (i == 0 || !dev_fields[i] || !dev_fields[i - 1]) continue;
+    const b200ms_problem &a = prob[i - 1], &b = prob[i];
+    if (a.nx != b.nx || a.ny != b.ny || a.num_modes != b.num_modes || (a.precision == 1) != (b.precision == 1) || M > 32) continue;
+    todo.push_back(i);
+  }
+  // one launch per (shape, precision) run of jobs; jobs are few and small, so they are simply processed one shape at a time
+  size_t k = 0;
+  while (k < todo.size()) {
+    const b200ms_problem &p0 = prob[todo[k]];
+    size_t e = k;
+    while (e < todo.size() && prob[todo[e]].nx == p0.nx && prob[todo[e]].ny == p0.ny && prob[todo[e]].num_modes == p0.num_modes &&
+           (prob[todo[e]].precision == 1) == (p0.precision == 1))
+      ++e;
+    const int np = (int)(e - k), nx = p0.nx, ny = p0.ny, M = p0.num_modes;
+    std::vector<HostAxisTables> tx(np), ty(np);
+    size_t ints = 0, dbls = 0;
+    for (int q = 0; q < np; ++q) {
+      const b200ms_problem &p = prob[todo[k + q]];
+      axis_tables(p.coords_x, nx, p.symmetry[0], tx[q]);
+      axis_tables(p.coords_y, ny, p.symmetry[1], ty[q]);
+      ints += 4 * (size_t)(tx[q].P + ty[q].P);
+      dbls += 5 * (size_t)(tx[q].P + ty[q].P);
+    }
+    const size_t off_d = align256(ints * sizeof(int)), off_pp = off_d + align256(dbls * sizeof(double));
+    const size_t off_pairs = off_pp + align256((size_t)np * sizeof(PostProblem));
+    const size_t off_part = off_pairs + align256((size_t)np * sizeof(PostPair));
+    const size_t off_out = off_part + align256((size_t)np * kPostChunks * M * M * sizeof(cplx));
+    h->post.reserve(off_out + align256((size_t)np * M * M * sizeof(cplx)) + 4096);
+    std::vector<int> hi(ints);
+    std::vector<double> hd(dbls);
+    std::vector<PostProblem> pp(np);
+    std::vector<PostPair> pairs(np);
+    size_t ci = 0, cd = 0;
+    int *di = reinterpret_cast<int *>(h->post.p);
+    double *dd = reinterpret_cast<double *>(h->post.p + off_d);
+    auto put = [&](const HostAxisTables &t, PostAxis &a) {
+      a.P = t.P;
+      auto pi = [&](const std::vector<int> &v) { const int *r = di + ci; std::copy(v.begin(), v.end(), hi.begin() + ci); ci += v.size(); return r; };
+      auto pd = [&](const std::vector<double> &v) { const double *r = dd + cd; std::copy(v.begin(), v.end(), hd.begin() + cd); cd += v.size(); return r; };
+      a.c_i0 = pi(t.ci0); a.c_i1 = pi(t.ci1); a.b_i0 = pi(t.bi0); a.b_i1 = pi(t.bi1);
+      a.c_w0 = pd(t.cw0); a.c_w1 = pd(t.cw1); a.b_w0 = pd(t.bw0); a.b_w1 = pd(t.bw1); a.area = pd(t.area);
+    };
+    for (int q = 0; q < np; ++q) {
+      const int i = todo[k + q];
+      put(tx[q], pp[q].ax);
+      put(ty[q], pp[q].ay);
+      pp[q].fields = const_cast<void *>(dev_fields[i]);
+      pp[q].mult = (prob[i].symmetry[0] != 0 ? 2.0 : 1.0) * (prob[i].symmetry[1] != 0 ? 2.0 : 1.0);
+      pp[q].flags = 0;
+      pairs[q].a = dev_fields[i - 1];
+      pairs[q].b = dev_fields[i];
+      pairs[q].prob = q;
+    }
+    cudaStream_t st = h->stream;
+    CUDA_CHECK(cudaMemcpyAsync(di, hi.data(), ints * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dd, hd.data(), dbls * sizeof(double), cudaMemcpyHostToDevice, st));
+    PostProblem *dpp = reinterpret_cast<PostProblem *>(h->post.p + off_pp);
+    PostPair *dpairs = reinterpret_cast<PostPair *>(h->post.p + off_pairs);
+    CUDA_CHECK(cudaMemcpyAsync(dpp, pp.data(), (size_t)np * sizeof(PostProblem), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dpairs, pairs.data(), (size_t)np * sizeof(PostPair), cudaMemcpyHostToDevice, st));
+    cplx *dpart = reinterpret_cast<cplx *>(h->post.p + off_part), *dout = reinterpret_cast<cplx *>(h->post.p + off_out);
+    const int nch = (int)std::min<size_t>(kPostChunks, ((size_t)nx * ny + 255) / 256);
+    dim3 g(nch, np, M * M);
+    if (p0.precision == 1) post_dot_kernel<cplxf><<<g, 256, 0, st>>>(dpp, dpairs, nx, ny, M, dpart);
+    else post_dot_kernel<cplx><<<g, 256, 0, st>>>(dpp, dpairs, nx, ny, M, dpart);
+    post_dot_final_kernel<<<np, std::max(32, ((M * M + 31) / 32) * 32), 0, st>>>(dpart, nch, M, dout);
+    std::vector<cplx> hout((size_t)np * M * M);
+    CUDA_CHECK(cudaMemcpyAsync(hout.data(), dout, hout.size() * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(cudaGetLastError());
+    h->stats.launches += 2;
+    for (int q = 0; q < np; ++q) std::memcpy(res[todo[k + q]].overlap_prev, hout.data() + (size_t)q * M * M, (size_t)M * M * sizeof(cplx));
+    k = e;
+  }
+}
+
 struct FieldCopy {  // one pending delivery of packed fields: device region -> caller memory (host or device)
   void *dst;
   const void *src;
@@ -296,6 +521,7 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W,
   for (int b = 0; b < B; ++b) {
     ps[b] = &W.setups[ids[b]];
     refs[b] = W.refs[ids[b]];
+    refs[b].p.incidence = ps[b]->masked ? 1 : 0;  // zero-markers only where the diagonal path really removes unknowns
     if (W.slot[ids[b]] != W.slot[ids[0]]) share = false;
   }
   if (share) refs.resize(1);
@@ -351,8 +577,10 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W,
     }
   }
   bool want_fields = false;
-  for (int b = 0; b < B; ++b)
-    if (res[W.i0 + ids[b]].fields) want_fields = true;
+  for (int b = 0; b < B; ++b) {
+    const b200ms_result &rb = res[W.i0 + ids[b]];
+    if (rb.fields || rb.flux || rb.overlap_prev || prob[W.i0 + ids[b]].post) want_fields = true;  // post-processing needs them in HBM
+  }
   S.epilogue(nsorted, perm, ps, nullptr, want_fields);
   // true residuals on the sorted Ritz vectors (they sit in the FGMRES Z scratch after the permutation)
   std::vector<double> maxres(B, 0.0);
@@ -400,11 +628,13 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W,
     // converged == Ritz residuals of OP below eig_tol (ARPACK's criterion).  The residual with respect to A itself is
     // reported for information: it is amplified by ||A - sigma|| ~ 1/(k0 dl)^2 (and by 1e8 next to PEC cells) and only
     // screened for garbage (O(1)) here.
-    r.status = (relative || (eig.nconv[b] == k && eig.ok && maxres[b] < 1e-1 && S.stats.inner_failures == 0)) ? B200MS_OK : B200MS_ERR_NOCONV;
+    // With PEC-valued cells (|eps| = 1e8) that amplification makes the figure meaningless at the reference's tolerance
+    // (measured 0.25 on pec_block_40 with |dn| < 1e-8), so the screen is skipped there.
+    r.status = (relative || (eig.nconv[b] == k && eig.ok && (maxres[b] < 1e-1 || ps[b]->has_pec) && S.stats.inner_failures == 0)) ? B200MS_OK : B200MS_ERR_NOCONV;
     if (h->opt.verbose)
-      fprintf(stderr, "[b200ms] prob %d: conv %d/%d restarts %d op %d inner %d cycles %d syncs %ld stencil %ld res %.2e ms %.1f\n", W.i0 + ids[b],
-              eig.nconv[b], k, S.stats.restarts, S.stats.op_applies, S.stats.inner_iters, S.stats.inner_cycles, S.stats.host_syncs,
-              S.stats.stencil_applies, maxres[b], ms);
+      fprintf(stderr, "[b200ms] prob %d: conv %d/%d ok %d restarts %d op %d inner %d cycles %d syncs %ld reorth %d innerfail %d res %.2e ms %.1f\n", W.i0 + ids[b],
+              eig.nconv[b], k, (int)eig.ok, S.stats.restarts, S.stats.op_applies, S.stats.inner_iters, S.stats.inner_cycles, S.stats.host_syncs,
+              S.stats.outer_second_pass, S.stats.inner_failures, maxres[b], ms);
   }
 }
 
@@ -451,75 +681,103 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
   const auto call0 = std::chrono::steady_clock::now();
   int first_err = B200MS_OK;
   try {
-    // windows of consecutive problems: a window's raw media are uploaded and scanned together, then its problems are
-    // grouped by (shape, arithmetic kind, ...) and solved in device batches
+    // Windows of consecutive problems: a window's raw media are uploaded and scanned together, then its problems are
+    // grouped by (shape, arithmetic kind, ...) and solved in device batches.  Three things run concurrently: the solve of
+    // window w (this thread, h->stream), the upload + scan of window w+1 and the delivery of the fields of window w-1
+    // (helper threads, h->io_stream); raw media and packed fields are double-buffered.
     const int wsize = std::max(1, h->opt.max_batch);
+    const int nwin = (nprob + wsize - 1) / wsize;
+    const int dev = h->device;
+    Window Wn[2];
+    auto upload = [h, prob, nprob, wsize, dev](int wi, Window *W) {
+      if (cudaSetDevice(dev) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed in the upload thread");
+      const auto t0 = std::chrono::steady_clock::now();
+      prepare_window(h, prob, wi * wsize, std::min(nprob, (wi + 1) * wsize), h->raw[wi & 1], h->io_stream, *W);
+      return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    auto download = [h, dev](std::vector<FieldCopy> copies) {
+      if (cudaSetDevice(dev) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed in the download thread");
+      const auto t0 = std::chrono::steady_clock::now();
+      for (const FieldCopy &c : copies) CUDA_CHECK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDefault, h->dl_stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->dl_stream));
+      return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    std::future<double> up_f, dl_f;
+    std::vector<const void *> dev_fields(nprob, nullptr);  // device address of each problem's packed fields (this + previous window)
+    if (nwin > 0) h->stats.setup_ms += upload(0, &Wn[0]);
     size_t free_b = 0, total_b = 0;
-    for (int i0 = 0, wi = 0; i0 < nprob; i0 += wsize, ++wi) {
-      const int i1 = std::min(nprob, i0 + wsize);
-      for (int i = i0; i < i1; ++i) {
-        res[i].status = res[i].n_complex ? B200MS_OK : B200MS_ERR_ARG;
-        res[i].converged = 0;
-      }
-      Window W;
-      const auto su0 = std::chrono::steady_clock::now();
-      prepare_window(h, prob, i0, i1, h->raw[wi & 1], h->stream, W);
-      h->stats.setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - su0).count();
-      std::map<GroupKey, std::vector<int>> groups;
-      size_t out_bytes = 0;
-      for (int q = 0; q < i1 - i0; ++q) {
-        const int i = i0 + q;
-        const ProblemSetup &s = W.setups[q];
-        if (res[i].status == B200MS_OK) res[i].status = s.status;
-        res[i].eps_spec = s.eps_spec;
-        res[i].is_complex = s.is_complex;
-        if (res[i].status != B200MS_OK) {
-          if (first_err == B200MS_OK) {
-            first_err = res[i].status;
-            h->err = s.error.empty() ? "bad result buffers" : s.error;
-          }
-          continue;
+    for (int wi = 0; wi < nwin; ++wi) {
+      const int i0 = wi * wsize, i1 = std::min(nprob, i0 + wsize);
+      Window &W = Wn[wi & 1];
+      if (wi + 1 < nwin) up_f = std::async(std::launch::async, upload, wi + 1, &Wn[(wi + 1) & 1]);
+      try {
+        for (int i = i0; i < i1; ++i) {
+          res[i].status = res[i].n_complex ? B200MS_OK : B200MS_ERR_ARG;
+          res[i].converged = 0;
         }
-        GroupKey key{s.nx, s.ny, s.num_modes, kind_of(s), s.has_mu ? 1 : 0, prob[i].symmetry[0], prob[i].symmetry[1],
-                     s.jz_axis, s.direction, s.relative ? 1 : 0, s.tensorial ? (s.eps_complex ? 2 : 1) : 0, prob[i].precision == 1 ? 1 : 0,
-                     prob[i].angle_theta, prob[i].angle_phi};
-        groups[key].push_back(q);
-        if (res[i].fields) out_bytes += align256((size_t)6 * s.nx * s.ny * s.num_modes * (prob[i].precision == 1 ? 8 : 16));
-      }
-      DevBuf &ob = h->out[wi & 1];
-      ob.reserve(std::max<size_t>(out_bytes + 4096, 4096));
-      CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-      free_b += h->arena.cap;
-      std::vector<FieldCopy> copies;
-      size_t cursor = 0;
-      for (auto &kv : groups) {
-        const std::vector<int> &all = kv.second;
-        const size_t per = bytes_per_problem(W.setups[all[0]], h->opt);
-        int bmax = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, h->opt.max_batch), (size_t)(0.8 * free_b) / per));
-        for (size_t s0 = 0; s0 < all.size(); s0 += bmax) {
-          std::vector<int> ids(all.begin() + s0, all.begin() + std::min(all.size(), s0 + bmax));
-          const ProblemSetup &sg = W.setups[ids[0]];
-          const size_t pb = (size_t)6 * sg.nx * sg.ny * sg.num_modes * (prob[i0 + ids[0]].precision == 1 ? 8 : 16);
-          unsigned char *region = ob.p + cursor;
-          if (cursor + pb * ids.size() > ob.cap) throw std::runtime_error("output buffer accounting error");
-          dispatch_group(kv.first.kind, h->opt.mg_precision == 1, h, ids, W, prob, res, region, copies);
-          bool any_fields = false;
-          for (int id : ids) {
-            if (res[i0 + id].fields) any_fields = true;
-            if (res[i0 + id].status != B200MS_OK && first_err == B200MS_OK) {
-              first_err = res[i0 + id].status;
-              h->err = "eigen-iteration did not converge";
+        std::map<GroupKey, std::vector<int>> groups;
+        size_t out_bytes = 0;
+        for (int q = 0; q < i1 - i0; ++q) {
+          const int i = i0 + q;
+          const ProblemSetup &s = W.setups[q];
+          if (res[i].status == B200MS_OK) res[i].status = s.status;
+          res[i].eps_spec = s.eps_spec;
+          res[i].is_complex = s.is_complex;
+          if (res[i].status != B200MS_OK) {
+            if (first_err == B200MS_OK) {
+              first_err = res[i].status;
+              h->err = s.error.empty() ? "bad result buffers" : s.error;
             }
+            continue;
           }
-          if (any_fields) cursor += align256(pb * ids.size());
+          GroupKey key{s.nx, s.ny, s.num_modes, kind_of(s), s.has_mu ? 1 : 0, prob[i].symmetry[0], prob[i].symmetry[1],
+                       s.jz_axis, s.direction, s.relative ? 1 : 0, s.tensorial ? (s.eps_complex ? 2 : 1) : 0, prob[i].precision == 1 ? 1 : 0,
+                       s.masked ? 1 : 0, prob[i].angle_theta, prob[i].angle_phi};
+          groups[key].push_back(q);
+          out_bytes += align256((size_t)6 * s.nx * s.ny * s.num_modes * (prob[i].precision == 1 ? 8 : 16));
         }
+        DevBuf &ob = h->out[wi & 1];  // last read by the delivery of window wi-2, which has completed (see below)
+        ob.reserve(std::max<size_t>(out_bytes + 4096, 4096));
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        free_b += h->arena.cap;
+        std::vector<FieldCopy> copies;
+        size_t cursor = 0;
+        for (auto &kv : groups) {
+          const std::vector<int> &all = kv.second;
+          const size_t per = bytes_per_problem(W.setups[all[0]], h->opt);
+          int bmax = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, h->opt.max_batch), (size_t)(0.8 * free_b) / per));
+          for (size_t s0 = 0; s0 < all.size(); s0 += bmax) {
+            std::vector<int> ids(all.begin() + s0, all.begin() + std::min(all.size(), s0 + bmax));
+            const ProblemSetup &sg = W.setups[ids[0]];
+            const size_t pb = (size_t)6 * sg.nx * sg.ny * sg.num_modes * (prob[i0 + ids[0]].precision == 1 ? 8 : 16);
+            unsigned char *region = ob.p + cursor;
+            if (cursor + pb * ids.size() > ob.cap) throw std::runtime_error("output buffer accounting error");
+            dispatch_group(kv.first.kind, h->opt.mg_precision == 1, h, ids, W, prob, res, region, copies);
+            post_batch(h, ids, W, prob, res, region, pb);  // gauge / flux / normalisation in HBM, before delivery
+            for (size_t b = 0; b < ids.size(); ++b) {
+              const int id = ids[b];
+              dev_fields[i0 + id] = region + b * pb;
+              if (res[i0 + id].status != B200MS_OK && first_err == B200MS_OK) {
+                first_err = res[i0 + id].status;
+                h->err = "eigen-iteration did not converge";
+              }
+            }
+            cursor += align256(pb * ids.size());
+          }
+        }
+        post_overlaps(h, prob, res, i0, i1, dev_fields);  // modal overlaps between consecutive problems (fields still in HBM)
+        // deliver the fields of this window (destination may be host or device memory) while the next window is solved;
+        // at most one delivery is in flight, so out[wi & 1] is free again by the time window wi + 2 writes it
+        if (dl_f.valid()) h->stats.download_ms += dl_f.get();
+        if (!copies.empty()) dl_f = std::async(std::launch::async, download, std::move(copies));
+      } catch (...) {
+        if (up_f.valid()) try { up_f.get(); } catch (...) {}
+        if (dl_f.valid()) try { dl_f.get(); } catch (...) {}
+        throw;
       }
-      // deliver the fields of this window (destination may be host or device memory)
-      const auto dl0 = std::chrono::steady_clock::now();
-      for (const FieldCopy &c : copies) CUDA_CHECK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDefault, h->stream));
-      CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      h->stats.download_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dl0).count();
+      if (up_f.valid()) h->stats.setup_ms += up_f.get();
     }
+    if (dl_f.valid()) h->stats.download_ms += dl_f.get();
   } catch (const std::exception &e) {
     h->err = e.what();
     return B200MS_ERR_CUDA;

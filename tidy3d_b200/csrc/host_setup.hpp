@@ -74,6 +74,7 @@ struct ProblemSetup {
   int jz_axis = -1;          // axis along which jz varies (-1: none)
   double max_k2 = 0;         // max over cells of Re(eps) - target^2 (positive => indefinite region)
   bool has_pec = false;      // some diagonal eps entry is PEC-valued (solver.py:327-333)
+  bool masked = false;       // incidence-matrix formulation with PEC cells present: PEC unknowns are removed (solver.py:441-449)
   int medium = -1;           // slot of the raw eps/mu on the device (product path)
 };
 
@@ -150,6 +151,7 @@ inline MediumParams medium_params(const ProblemSetup &s, const b200ms_problem &p
   MediumParams m;
   m.nx = s.nx; m.ny = s.ny; m.npml_x = p.num_pml[0]; m.npml_y = p.num_pml[1];
   m.a = s.jac_a; m.b = s.jac_b; m.norm_axis = s.jz_axis; m.de = de; m.dh = dh;
+  m.incidence = p.incidence ? 1 : 0;
   return m;
 }
 
@@ -248,6 +250,7 @@ inline void finish_setup(const b200ms_problem &p, ProblemSetup &s, const MediumS
   s.eps_complex = eps_complex;
   s.mu_complex = mu_complex;
   s.has_pec = sc.v[SC_HAS_PEC] > 0.5;
+  s.masked = s.has_pec && p.incidence != 0;
   s.max_k2 = std::max(0.0, sc.v[SC_MAX_RE] - s.target * s.target);
   s.sigma_t = cd(s.target, 0.0);
   if (s.tensorial) {
@@ -258,6 +261,11 @@ inline void finish_setup(const b200ms_problem &p, ProblemSetup &s, const MediumS
       s.status = B200MS_ERR_UNSUPPORTED;  // solver.py:357-361
       s.error = "Tensorial eps not yet supported in relative mode solver (with basis fields provided).";
     }
+  }
+  if (s.masked && s.tensorial) s.masked = false;  // solver_tensorial has no incidence matrices (solver.py:594-721)
+  if (s.masked && s.relative) {
+    s.status = B200MS_ERR_UNSUPPORTED;  // the reference leaves the basis un-reduced there (solver.py:520-528): shape error
+    s.error = "basis fields together with mu_cross / split_curl_scaling and PEC-valued cells";
   }
   if (s.relative && p.num_modes > 20) {
     s.status = B200MS_ERR_UNSUPPORTED;
@@ -293,7 +301,7 @@ inline void fill_fields_host(const b200ms_problem &p, ProblemSetup &s) {
     for (int iy = 0; iy < s.ny; ++iy) {
       const size_t c = (size_t)ix * s.ny + iy;
       cplx f[18];
-      cell_fields(eps, mu, mp, ix, iy, f);
+      cell_fields(eps, mu, mp, ix, iy, f, false);
       for (int k = 0; k < 6; ++k) {
         const cplx v = (k == 2 || k == 5) ? recip(f[k]) : f[k];  // the host mirror stores ezz / mzz themselves
         (*s.fp[k])[c] = cd(v.re, v.im);

@@ -554,6 +554,10 @@ struct TransferArgs {
 };
 
 // coarse[b][comp] = R fine[b][comp]   (Ex: x edge / y node, Ey: x node / y edge)
+// Each thread produces one coarse value from an (up to) 4 x 4 patch of fine values.  The two 1-D lists of the thread
+// (<= 4 entries each for the aggregations plan_hierarchy produces: aggregates of <= 3 cells, linear interpolation) are read
+// into registers first and the 16 fine loads are issued together (predicated), instead of a doubly nested loop whose every
+// term waits on an index load and then on a data load; longer lists fall back to the loop.
 template <typename T>
 __global__ void __launch_bounds__(256) restrict_kernel(TransferArgs a, const T *fine, T *coarse) {
   const int J = blockIdx.x * 64 + threadIdx.x, I = blockIdx.y * 4 + threadIdx.y;
@@ -564,19 +568,45 @@ __global__ void __launch_bounds__(256) restrict_kernel(TransferArgs a, const T *
   const size_t Nf = (size_t)a.nxf * a.nyf, Nc = (size_t)a.nxc * a.nyc;
   const T *f = fine + ((size_t)b * 2 + comp) * Nf;
   T acc = zero_of<T>();
-  const int kx0 = tx.r_ptr[I], kx1 = tx.r_ptr[I + 1], ky0 = ty.r_ptr[J], ky1 = ty.r_ptr[J + 1];
-  for (int kx = kx0; kx < kx1; ++kx) {
-    const double wx = tx.r_w[kx];
-    const T *row = f + (size_t)tx.r_idx[kx] * a.nyf;
-    T racc = zero_of<T>();
-    for (int ky = ky0; ky < ky1; ++ky) racc += ty.r_w[ky] * ldg(row + ty.r_idx[ky]);
-    acc += wx * racc;
+  const int kx0 = __ldg(tx.r_ptr + I), kx1 = __ldg(tx.r_ptr + I + 1), ky0 = __ldg(ty.r_ptr + J), ky1 = __ldg(ty.r_ptr + J + 1);
+  if (kx1 - kx0 <= 4 && ky1 - ky0 <= 4) {
+    int ix[4], iy[4];
+    double wx[4], wy[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool vx = kx0 + q < kx1, vy = ky0 + q < ky1;
+      ix[q] = vx ? __ldg(tx.r_idx + kx0 + q) : 0;
+      wx[q] = vx ? __ldg(tx.r_w + kx0 + q) : 0.0;
+      iy[q] = vy ? __ldg(ty.r_idx + ky0 + q) : 0;
+      wy[q] = vy ? __ldg(ty.r_w + ky0 + q) : 0.0;
+    }
+    T v[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[p][q] = (kx0 + p < kx1 && ky0 + q < ky1) ? ldg(f + (size_t)ix[p] * a.nyf + iy[q]) : zero_of<T>();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      T racc = zero_of<T>();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) racc += wy[q] * v[p][q];
+      acc += wx[p] * racc;
+    }
+  } else {
+    for (int kx = kx0; kx < kx1; ++kx) {
+      const double wxk = tx.r_w[kx];
+      const T *row = f + (size_t)tx.r_idx[kx] * a.nyf;
+      T racc = zero_of<T>();
+      for (int ky = ky0; ky < ky1; ++ky) racc += ty.r_w[ky] * ldg(row + ty.r_idx[ky]);
+      acc += wxk * racc;
+    }
   }
   if ((comp == 0 && a.mask_y && J == 0 && a.nyc > 1) || (comp == 1 && a.mask_x && I == 0 && a.nxc > 1)) acc = zero_of<T>();
   coarse[((size_t)b * 2 + comp) * Nc + (size_t)I * a.nyc + J] = acc;
 }
 
-// fine[b][comp] += P coarse[b][comp]
+// fine[b][comp] += P coarse[b][comp].  All index / weight loads and the four coarse loads are independent and issued
+// before the read-modify-write of the fine value.
 template <typename T>
 __global__ void __launch_bounds__(256) prolong_add_kernel(TransferArgs a, const T *coarse, T *fine) {
   const int j = blockIdx.x * 64 + threadIdx.x, i = blockIdx.y * 4 + threadIdx.y;
@@ -587,12 +617,13 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(TransferArgs a, const 
   const Transfer1DDev &ty = comp == 0 ? a.yn : a.ye;
   const size_t Nf = (size_t)a.nxf * a.nyf, Nc = (size_t)a.nxc * a.nyc;
   const T *c = coarse + ((size_t)b * 2 + comp) * Nc;
-  const int I0 = tx.p_i0[i], I1 = tx.p_i1[i], J0 = ty.p_i0[j], J1 = ty.p_i1[j];
-  const double wx0 = tx.p_w0[i], wx1 = tx.p_w1[i], wy0 = ty.p_w0[j], wy1 = ty.p_w1[j];
-  T v = wx0 * (wy0 * ldg(c + (size_t)I0 * a.nyc + J0) + wy1 * ldg(c + (size_t)I0 * a.nyc + J1)) +
-        wx1 * (wy0 * ldg(c + (size_t)I1 * a.nyc + J0) + wy1 * ldg(c + (size_t)I1 * a.nyc + J1));
   T *f = fine + ((size_t)b * 2 + comp) * Nf + (size_t)i * a.nyf + j;
-  *f = *f + v;
+  const int I0 = __ldg(tx.p_i0 + i), I1 = __ldg(tx.p_i1 + i), J0 = __ldg(ty.p_i0 + j), J1 = __ldg(ty.p_i1 + j);
+  const double wx0 = __ldg(tx.p_w0 + i), wx1 = __ldg(tx.p_w1 + i), wy0 = __ldg(ty.p_w0 + j), wy1 = __ldg(ty.p_w1 + j);
+  const T fv = *f;
+  const T c00 = ldg(c + (size_t)I0 * a.nyc + J0), c01 = ldg(c + (size_t)I0 * a.nyc + J1);
+  const T c10 = ldg(c + (size_t)I1 * a.nyc + J0), c11 = ldg(c + (size_t)I1 * a.nyc + J1);
+  *f = fv + (wx0 * (wy0 * c00 + wy1 * c01) + wx1 * (wy0 * c10 + wy1 * c11));
 }
 
 // coefficient field restriction: out = R in (optionally on reciprocals: out = 1 / R (1 / in))

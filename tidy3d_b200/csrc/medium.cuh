@@ -74,6 +74,7 @@ struct MediumParams {
   int nx, ny, npml_x, npml_y;
   double a, b;        // angled transform J[0][2], J[1][2]
   int norm_axis;      // bend: axis along which d varies (0: x index, 1: y index), -1: no bend
+  int incidence;      // solver.py:93 enable_incidence_matrices: PEC-valued unknowns are removed instead of modelled
   const double *de, *dh;  // dwdz at E / H sites along norm_axis (device or host pointers matching the caller), may be null
 };
 
@@ -167,7 +168,9 @@ __global__ void medium_scan_final_kernel(const double *partial, int nblocks, dou
 
 // ---- coefficient fields ----------------------------------------------------------------------------------------
 // exx, eyy, 1/ezz, (mxx, myy, 1/mzz) of the diagonal-path operator after Jacobian + PEC model, per cell.
-HD void cell_fields(const cplx *eps, const cplx *mu, const MediumParams &p, int ix, int iy, cplx out[6]) {
+// `marked` (incidence-matrix formulation, solver.py:441-449, 474-477): a PEC-valued exx / eyy is stored as 0 -- the marker the
+// operator uses to drop that unknown -- and 1/ezz is zeroed on PEC-valued ezz.
+HD void cell_fields(const cplx *eps, const cplx *mu, const MediumParams &p, int ix, int iy, cplx out[6], bool marked = false) {
   const size_t n = (size_t)p.nx * p.ny, c = (size_t)ix * p.ny + iy;
   double d_e = 1.0, d_h = 1.0;
   if (p.norm_axis >= 0) {
@@ -178,10 +181,11 @@ HD void cell_fields(const cplx *eps, const cplx *mu, const MediumParams &p, int 
   cplx e[9], m[9];
   cell_tensors(eps, mu, n, c, p.a, p.b, d_e, d_h, e, m);
   cplx ex = e[0], ey = e[4], ez = e[8];
-  if (is_pec_val(ex)) ex = pec_model();
-  if (is_pec_val(ey)) ey = pec_model();
-  if (is_pec_val(ez)) ez = pec_model();
-  out[0] = ex; out[1] = ey; out[2] = recip(ez);
+  const bool px = is_pec_val(ex), py = is_pec_val(ey), pz = is_pec_val(ez);
+  if (px) ex = marked ? mk(0.0, 0.0) : pec_model();
+  if (py) ey = marked ? mk(0.0, 0.0) : pec_model();
+  if (pz) ez = pec_model();
+  out[0] = ex; out[1] = ey; out[2] = (pz && marked) ? mk(0.0, 0.0) : recip(ez);
   out[3] = m[0]; out[4] = m[4]; out[5] = recip(m[8]);
 }
 
@@ -226,14 +230,17 @@ __global__ void __launch_bounds__(256) fields_kernel(const MediumRef *med, int n
   const MediumRef r = med[blockIdx.y];
   const size_t n = (size_t)r.p.nx * r.p.ny;
   for (size_t c = (size_t)blockIdx.x * 256 + threadIdx.x; c < n; c += (size_t)gridDim.x * 256) {
-    cplx f[6];
-    cell_fields(r.eps, r.mu, r.p, (int)(c / r.p.ny), (int)(c % r.p.ny), f);
+    cplx f[6], fm[6];
+    const bool marked = r.p.incidence != 0;
+    cell_fields(r.eps, r.mu, r.p, (int)(c / r.p.ny), (int)(c % r.p.ny), f, marked);
+    // the multigrid twin keeps the PEC model (a preconditioner for the full space; its output is masked afterwards)
+    if (marked) cell_fields(r.eps, r.mu, r.p, (int)(c / r.p.ny), (int)(c % r.p.ny), fm, false);
     for (int q = 0; q < nf; ++q) {
       const C v = cast_to<C>(f[q]);
       fields[bstride * blockIdx.y + (size_t)q * n + c] = v;
       if ((const void *)fields_p != (const void *)fields) {
         PC w;
-        convert(v, w);
+        convert(marked ? cast_to<C>(fm[q]) : v, w);
         fields_p[bstride * blockIdx.y + (size_t)q * n + c] = w;
       }
     }
@@ -247,6 +254,18 @@ __global__ void __launch_bounds__(256) tensor_fields_kernel(const MediumRef *med
     cplx f[18];
     cell_tensor_fields(r.eps, r.mu, r.p, (int)(c / r.p.ny), (int)(c % r.p.ny), f);
     for (int q = 0; q < 18; ++q) ft[bstride * blockIdx.y + (size_t)q * n + c] = cast_to<C>(f[q]);
+  }
+}
+
+// y1 = 0 where exx == 0, y2 = 0 where eyy == 0 (the markers of removed PEC unknowns); strided two-component fields
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) mask_kernel(T *y, size_t y_bstride, const C *fields, size_t f_bstride, size_t n) {
+  const int b = blockIdx.y;
+  const C *fb = fields + f_bstride * b;
+  T *yb = y + y_bstride * b;
+  for (size_t c = (size_t)blockIdx.x * 256 + threadIdx.x; c < n; c += (size_t)gridDim.x * 256) {
+    if (abs2(fb[c]) == 0.0) yb[c] = zero_of<T>();
+    if (abs2(fb[n + c]) == 0.0) yb[n + c] = zero_of<T>();
   }
 }
 

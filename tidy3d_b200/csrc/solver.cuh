@@ -69,6 +69,7 @@ struct SolveStats {
   int inner_failures = 0;  // shift-invert solves that stopped above 1e4 x inner_tol
   long host_syncs = 0;     // stream synchronisations inside the inner solves
   int inner_cycles = 0;    // FGMRES cycles (iterative-refinement steps)
+  int outer_second_pass = 0;  // Krylov-Schur orthogonalisations that needed the second Gram-Schmidt pass (DGKS test)
 };
 
 template <typename T> inline cd to_cd(T v);
@@ -107,6 +108,7 @@ class BatchSolver {
   int B = 0, nx = 0, ny = 0, k = 0, m = 0, restart = 0, nf = 3;
   size_t N = 0, len = 0, vstride = 0, lenE = 0, vsE = 0;
   bool tensor_ = false;
+  bool masked_ = false;      // incidence-matrix formulation: unknowns marked by exx == 0 / eyy == 0 are held at zero
   bool single_out_ = false;  // fields are delivered as complex64 (mode_spec.precision == "single")
   double msign_ = 1.0;
   bool has_mu = false, shared_fields = false;
@@ -131,6 +133,7 @@ class BatchSolver {
     msign_ = (tensor_ && p0.eps_complex && p0.direction < 0) ? -1.0 : 1.0;  // solver.py:669-670
     k = p0.num_modes;
     has_mu = p0.has_mu;
+    masked_ = p0.masked;
     nf = has_mu ? 6 : 3;
     shared_fields = share_fields;
     const int ncv = opt_.ncv > 0 ? opt_.ncv : std::max(2 * k + 1, 20);
@@ -440,22 +443,11 @@ class BatchSolver {
     a.dinv = dinv;
     stats.launches++;
     if (opt_.stencil_variant != 1 && v.nx >= 32 && v.ny >= 2) {
-      constexpr int TXR = 32;
-      dim3 blk(kMarchCols), grd((v.ny + kMarchOut - 1) / kMarchOut, (v.nx + TXR - 1) / TXR, B);
-      if (mode == MODE_JACOBI && dinv) {  // stored-diagonal sweep: fewer registers and instructions than recomputing it
-        if (has_mu) stencil_march_kernel<TT, CC, MODE_JACOBI_D, true, TXR><<<grd, blk, 0, st_>>>(a);
-        else stencil_march_kernel<TT, CC, MODE_JACOBI_D, false, TXR><<<grd, blk, 0, st_>>>(a);
-        return;
-      }
-      if (has_mu) {
-        if (mode == MODE_APPLY) stencil_march_kernel<TT, CC, MODE_APPLY, true, TXR><<<grd, blk, 0, st_>>>(a);
-        else if (mode == MODE_RESID) stencil_march_kernel<TT, CC, MODE_RESID, true, TXR><<<grd, blk, 0, st_>>>(a);
-        else stencil_march_kernel<TT, CC, MODE_JACOBI, true, TXR><<<grd, blk, 0, st_>>>(a);
-      } else {
-        if (mode == MODE_APPLY) stencil_march_kernel<TT, CC, MODE_APPLY, false, TXR><<<grd, blk, 0, st_>>>(a);
-        else if (mode == MODE_RESID) stencil_march_kernel<TT, CC, MODE_RESID, false, TXR><<<grd, blk, 0, st_>>>(a);
-        else stencil_march_kernel<TT, CC, MODE_JACOBI, false, TXR><<<grd, blk, 0, st_>>>(a);
-      }
+      // rows marched per CTA: the march is a serial chain of (TXR + 3) row steps, each waiting on one global-load
+      // round trip, so small levels (few CTAs per SM, nothing to hide that latency behind) get short chains
+      if (v.nx >= 384 || opt_.stencil_variant == 2) launch_march<TT, CC, 32>(v, mode, a, dinv != nullptr);
+      else if (v.nx >= 192) launch_march<TT, CC, 16>(v, mode, a, dinv != nullptr);
+      else launch_march<TT, CC, 8>(v, mode, a, dinv != nullptr);
       return;
     }
     constexpr int TX = Tile<TT>::TX, TY = Tile<TT>::TY;
@@ -470,8 +462,37 @@ class BatchSolver {
       else stencil_kernel<TT, CC, MODE_JACOBI, false><<<grd, blk, 0, st_>>>(a);
     }
   }
+  template <typename TT, typename CC, int TXR>
+  void launch_march(const Level &v, int mode, const StencilArgs<TT, CC> &a, bool have_dinv) {
+    dim3 blk(kMarchCols), grd((v.ny + kMarchOut - 1) / kMarchOut, (v.nx + TXR - 1) / TXR, B);
+    if (mode == MODE_JACOBI && have_dinv) {  // stored-diagonal sweep: fewer registers and instructions than recomputing it
+      if (has_mu) stencil_march_kernel<TT, CC, MODE_JACOBI_D, true, TXR><<<grd, blk, 0, st_>>>(a);
+      else stencil_march_kernel<TT, CC, MODE_JACOBI_D, false, TXR><<<grd, blk, 0, st_>>>(a);
+      return;
+    }
+    if (has_mu) {
+      if (mode == MODE_APPLY) stencil_march_kernel<TT, CC, MODE_APPLY, true, TXR><<<grd, blk, 0, st_>>>(a);
+      else if (mode == MODE_RESID) stencil_march_kernel<TT, CC, MODE_RESID, true, TXR><<<grd, blk, 0, st_>>>(a);
+      else stencil_march_kernel<TT, CC, MODE_JACOBI, true, TXR><<<grd, blk, 0, st_>>>(a);
+    } else {
+      if (mode == MODE_APPLY) stencil_march_kernel<TT, CC, MODE_APPLY, false, TXR><<<grd, blk, 0, st_>>>(a);
+      else if (mode == MODE_RESID) stencil_march_kernel<TT, CC, MODE_RESID, false, TXR><<<grd, blk, 0, st_>>>(a);
+      else stencil_march_kernel<TT, CC, MODE_JACOBI, false, TXR><<<grd, blk, 0, st_>>>(a);
+    }
+  }
+  // incidence-matrix formulation (solver.py:441-449, 506-508): zero the components of removed (PEC) unknowns
+  void mask_E(T *y, size_t y_bs) {
+    if (!masked_) return;
+    dim3 grd((unsigned)std::min<size_t>((N + 255) / 256, 1024), B);
+    mask_kernel<T, C><<<grd, 256, 0, st_>>>(y, y_bs, lv[0].fields_true, lv[0].fbstride, N);
+    stats.launches++;
+  }
   // the reference operator (fp64, true PML) on the fine level
   void apply_true(int mode, const T *x, const T *rhs, T *y) {
+    apply_true_raw(mode, x, rhs, y);
+    if (!tensor_) mask_E(y, len);
+  }
+  void apply_true_raw(int mode, const T *x, const T *rhs, T *y) {
     stats.stencil_applies++;
     if constexpr (std::is_same<T, cplx>::value) {
       if (tensor_) {  // y = (mat - sigma) x  or  rhs - (mat - sigma) x,  mat = msign (-i) M  (solver.py:655-670)
@@ -548,8 +569,12 @@ class BatchSolver {
   // residual), converting on the way in and out when the multigrid runs in fp32.  Two cycles per application roughly
   // halve the FGMRES iteration count, which pays because the Gram-Schmidt cost grows quadratically with it.
   void precondition(const T *v, T *z) {
-    if (tensor_) precondition_tensor(v, z);
-    else precondition_E(v, len, z, len);
+    if (tensor_) {
+      precondition_tensor(v, z);
+    } else {
+      precondition_E(v, len, z, len);
+      mask_E(z, len);
+    }
   }
   // z = B_E v on two-component fields with batch strides v_bs / z_bs (== lenE for plain batched vectors)
   void precondition_E(const T *v, size_t v_bs, T *z, size_t z_bs) {
@@ -975,16 +1000,45 @@ class BatchSolver {
     }
     k_scale<U>(w, dst, dst2, ln, P2, nch, hexp, hstride, nv);
   }
-  // outer (Krylov-Schur) orthonormalisation through the device kernels: one read-back of h and ||w||
-  void orthonormalise_dev(const T *V, int nv, T *w, T *dst, std::vector<cd> &h, std::vector<double> &nrm) {
+  // outer (Krylov-Schur) orthonormalisation through the device kernels.  Classical Gram-Schmidt with the DGKS test
+  // ARPACK uses (dgetv0/dnaitr: reorthogonalise when ||w'|| < 0.717 ||w||): the second pass -- two more reads of the
+  // whole fp64 basis -- runs only when some active problem needs it.
+  void orthonormalise_dev(const T *V, int nv, T *w, T *dst, std::vector<cd> &h, std::vector<double> &nrm, const std::vector<char> *skip = nullptr) {
     const int hs = hstride();
-    gs_cgs2<T>(V, vstride, len, nv, w, dst, nullptr, hbuf_, (size_t)hs);
+    T *P0 = gpart<T>(0), *P1 = gpart<T>(1), *P2 = gpart<T>(2);
+    const int nch = gs_chunks(len);
+    k_dots<T>(V, vstride, len, w, nv, P0, 0, nch);
+    k_update_norm<T>(V, vstride, len, w, nv, P0, nch, P2, 1, hbuf_, (size_t)hs, 0);
+    sum_partials_kernel<T><<<(B + 63) / 64, 64, 0, st_>>>(P2, nch, pstride(), 0, n2_dev_, B);
+    stats.launches++;
+    std::vector<double> n2(B);
+    CUDA_CHECK(cudaMemcpyAsync(n2.data(), n2_dev_, B * sizeof(double), cudaMemcpyDeviceToHost, st_));
     fetch_h((size_t)B * hs);
     h.assign((size_t)B * nv, cd(0, 0));
     nrm.assign(B, 0.0);
+    bool second = false;
     for (int b = 0; b < B; ++b) {
-      for (int i = 0; i < nv; ++i) h[(size_t)b * nv + i] = to_cd(hhost_[(size_t)b * hs + i]);
-      nrm[b] = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hs + nv]).real()));
+      double before = n2[b];
+      for (int i = 0; i < nv; ++i) {
+        h[(size_t)b * nv + i] = to_cd(hhost_[(size_t)b * hs + i]);
+        before += std::norm(h[(size_t)b * nv + i]);
+      }
+      if (skip && (*skip)[b]) continue;
+      if (!(n2[b] >= 0.5 * before)) second = true;  // ||w'|| < 0.707 ||w||
+    }
+    if (second || opt_.outer_dgks == 0) {
+      k_dots<T>(V, vstride, len, w, nv, P1, 0, nch);
+      k_update_norm<T>(V, vstride, len, w, nv, P1, nch, P2, 1, hbuf_, (size_t)hs, 1);
+      stats.outer_second_pass++;
+    }
+    k_scale<T>(w, dst, nullptr, len, P2, nch, hbuf_, (size_t)hs, nv);
+    if (second || opt_.outer_dgks == 0) {
+      fetch_h((size_t)B * hs);
+      for (int b = 0; b < B; ++b)
+        for (int i = 0; i < nv; ++i) h[(size_t)b * nv + i] = to_cd(hhost_[(size_t)b * hs + i]);
+      for (int b = 0; b < B; ++b) nrm[b] = std::sqrt(std::max(0.0, to_cd(hhost_[(size_t)b * hs + nv]).real()));
+    } else {
+      for (int b = 0; b < B; ++b) nrm[b] = std::sqrt(std::max(0.0, n2[b]));
     }
   }
 
@@ -1079,7 +1133,7 @@ class BatchSolver {
   double solve_op(const T *rhs, T *xsol, int &iters_out, const std::vector<char> *skip = nullptr, const std::vector<double> *tolv = nullptr) {
     if (opt_.inner_mode == 0) return fgmres(rhs, xsol, iters_out, skip, tolv);
     auto tol_of = [&](int b) { return tolv ? (*tolv)[b] : opt_.inner_tol; };
-    bool ir = kMixed && !tensor_ && opt_.inner_ir != 0;
+    bool ir = kMixed && !tensor_ && !masked_ && opt_.inner_ir != 0;  // the fp32 twin of the operator keeps the PEC model: no masking
     std::vector<char> done(B, 0);
     if (skip) done = *skip;
     std::vector<unsigned char> hskip(B);
@@ -1174,6 +1228,12 @@ class BatchSolver {
       rcur = rhs_;
     }
     (void)verified;
+    if (opt_.verbose >= 2) {
+      double wr = 0.0;
+      for (int b = 0; b < B; ++b)
+        if (!skip || !(*skip)[b]) wr = std::max(wr, resrel[b]);
+      fprintf(stderr, "[b200ms]   solve_op: cycles %d steps %d worst %.2e tol0 %.1e ir %d\n", cyc, total, wr, tol_of(0), (int)ir);
+    }
     iters_out = total;
     stats.inner_iters += total;
     stats.inner_cycles += cyc;
@@ -1208,6 +1268,7 @@ class BatchSolver {
     for (int b = 0; b < B; ++b)
       CUDA_CHECK(cudaMemcpyAsync(rhs_ + (size_t)b * len, hv.data(), len * sizeof(T), cudaMemcpyHostToDevice, st_));
     CUDA_CHECK(cudaStreamSynchronize(st_));
+    if (!tensor_) mask_E(rhs_, len);  // solver.py:507: vec_init = dnz * vec_init
     dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
     scale_inv_norm(rhs_, Vout_, hbuf_, hstride());
   }
@@ -1234,7 +1295,7 @@ class BatchSolver {
         double worst = solve_op(vj, w, its, &done, &tolv);
         stats.op_applies++;
         if (!(worst <= 1e-3)) stats.inner_failures++;
-        if (opt_.inner_mode != 0 && j + 2 < kGsMaxCoef) orthonormalise_dev(Vout_, j + 1, w, w, h, nrm);
+        if (opt_.inner_mode != 0 && j + 2 < kGsMaxCoef) orthonormalise_dev(Vout_, j + 1, w, w, h, nrm, &done);
         else orthonormalise(Vout_, j + 1, w, w, h, nrm);
         for (int b = 0; b < B; ++b) {
           if (done[b]) continue;

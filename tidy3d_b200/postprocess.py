@@ -1,0 +1,85 @@
+"""Host-side half of the post-processing seam.
+
+The heavy per-cell work -- gauge, colocation, flux normalisation and the modal overlap matrices between adjacent
+frequencies -- runs on the GPU while the fields are still in HBM (``compute_modes_batch(..., post=(...))``,
+``csrc/post.cuh``).  What is left for the host is the bookkeeping of ``ModeData.overlap_sort``
+(tidy3d/components/data/monitor_data.py:1295-1505) on F x M x M numbers: which mode of frequency i+1 continues which mode
+of frequency i, and the phase that makes the continuation smooth.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def _closest_pairs(amps: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Greedy pairing of rows and columns by decreasing |overlap| (``_find_closest_pairs``, monitor_data.py:1421-1440)."""
+    n = amps.shape[0]
+    mag = np.abs(amps).astype(float)
+    pairs = np.full(n, -1, dtype=int)
+    values = np.zeros(n, dtype=complex)
+    for _ in range(n):
+        i, j = divmod(int(np.argmax(mag)), n)
+        pairs[i], values[i] = j, amps[i, j]
+        mag[i, :] = -1.0
+        mag[:, j] = -1.0
+    return pairs, values
+
+
+def _ordering_one_step(amps: np.ndarray, thresh: float) -> Tuple[np.ndarray, np.ndarray]:
+    """``_find_ordering_one_freq`` (monitor_data.py:1378-1419): modes already matching their own index stay put."""
+    m = amps.shape[0]
+    pairs = np.arange(m)
+    diag = np.diag(amps).astype(complex).copy()
+    loose = np.flatnonzero(np.abs(diag) < thresh)
+    if loose.size > 1:
+        sub_pairs, sub_vals = _closest_pairs(amps[np.ix_(loose, loose)])
+        pairs[loose] = loose[sub_pairs]
+        diag[loose] = sub_vals
+    return pairs, diag
+
+
+def overlap_sort(overlap_prev: Sequence[np.ndarray], track_freq: str = "central", overlap_thresh: float = 0.9, direction: str = "+"):
+    """Mode tracking across a frequency sweep from the device-computed overlap matrices.
+
+    ``overlap_prev[i]`` (i >= 1) = dot(modes at f_{i-1}, modes at f_i), what ``compute_modes_batch(post=("normalize",
+    "overlaps"))`` returns per problem as ``info["overlap_prev"]`` (entry 0 is ignored).  Returns ``(sorting, phase,
+    overlap)`` of shape (F, M) with the meaning of the reference's arrays: mode ``k`` of the sorted data at frequency i is
+    mode ``sorting[i, k]`` of the unsorted data multiplied by ``exp(-1j * phase[i, k])`` (monitor_data.py:1442-1478).
+    """
+    nf = len(overlap_prev)
+    m = np.asarray(overlap_prev[-1]).shape[0]
+    base = {"lowest": 0, "highest": nf - 1, "central": nf // 2}[track_freq]
+    sign = -1.0 if direction == "-" else 1.0  # store_fields_direction == "-" flips the overlaps (monitor_data.py:1391-1392)
+    sorting = np.full((nf, m), -1, dtype=int)
+    overlap = np.zeros((nf, m))
+    phase = np.zeros((nf, m))
+    sorting[base] = np.arange(m)
+    overlap[base] = 1.0
+    for step in (-1, 1):
+        i = base + step
+        while 0 <= i < nf:
+            prev = i - step
+            # dot(template = prev, to_sort = i).  Marching down in frequency needs dot(f_{i+1}, f_i) = conj(dot(f_i, f_{i+1}))^T
+            amps = sign * (np.asarray(overlap_prev[i]) if step == 1 else np.conj(np.asarray(overlap_prev[i + 1])).T)
+            one, vals = _ordering_one_step(amps, overlap_thresh)
+            sorting[i] = one[sorting[prev]]
+            overlap[i] = np.abs(vals[sorting[prev]])
+            phase[i] = phase[prev] + np.angle(vals[sorting[prev]])
+            i += step
+    return sorting, phase, overlap
+
+
+def apply_sorting(n_complex: Sequence[np.ndarray], fields: Sequence[np.ndarray], sorting: np.ndarray, phase: np.ndarray):
+    """``_reorder_modes`` (monitor_data.py:1442-1478) on per-frequency arrays: returns re-ordered copies of ``n_complex``
+    (list of (M,)) and ``fields`` (list of (2,3,Nx,Ny,1,M) or None entries)."""
+    n_out: List[np.ndarray] = []
+    f_out: List = []
+    for i, (n, f) in enumerate(zip(n_complex, fields)):
+        n_out.append(np.asarray(n)[sorting[i]])
+        if f is None:
+            f_out.append(None)
+        else:
+            f_out.append((np.asarray(f)[..., sorting[i]] * np.exp(-1j * phase[i])).astype(np.asarray(f).dtype))
+    return n_out, f_out

@@ -57,21 +57,6 @@ def _raise_for(rc: int, handle, where="", msg=None):
 PEC_VAL = -1e8  # tidy3d/constants.py
 
 
-def _has_pec(eps_cross) -> bool:
-    return any(bool(np.any(np.abs(np.asarray(eps_cross[i])) >= 0.9 * abs(PEC_VAL))) for i in (0, 4, 8))
-
-
-def _check_unsupported(eps_cross, mu_cross, split_curl_scaling):
-    """``mu_cross`` / ``split_curl_scaling`` switch the reference to its incidence-matrix formulation (solver.py:93,
-    441-449, 474-477, 506-508), which only differs from the plain one when PEC-valued cells are present: that
-    combination is not built."""
-    if (mu_cross is not None or split_curl_scaling is not None) and _has_pec(eps_cross):
-        raise NotImplementedError(
-            "tidy3d_b200: mu_cross / split_curl_scaling together with PEC-valued permittivity (incidence matrices, "
-            "solver.py:441-449) is not built"
-        )
-
-
 def _apply_split_curl(eps_cross, split):
     """solver.py:122-124: eps_rr -> eps_rr / scaling_r outside PEC (scaling == 0 marks PEC)."""
     eps = [np.array(eps_cross[i], dtype=np.complex128, copy=True) for i in range(9)]
@@ -93,7 +78,7 @@ def _undo_split_curl(fields, split):
 
 def compute_modes_batch(
     problems: Sequence[dict], device: int = -1, want_fields: bool = True, return_info: bool = False, handle=None,
-    fields_ptrs=None,
+    fields_ptrs=None, post: Optional[Sequence[str]] = None,
 ):
     """Solve many independent mode problems in one device call.
 
@@ -103,7 +88,18 @@ def compute_modes_batch(
     plus a list of per-problem info dicts when ``return_info``.  ``fields_ptrs`` (list of raw addresses, host or device
     memory) makes the library write each problem's fields there instead (``fields`` is then None): used to keep the
     fields in HBM for the NCCL gather of ``tidy3d_b200.sharding`` / on-device post-processing.
+
+    ``post``: on-device post-processing applied to the fields before they are delivered (``tidy3d_b200.postprocess``):
+    any of ``"gauge"`` (mode_solver.py:802-810), ``"normalize"`` (flux normalisation, mode_solver.py:517-521), ``"flux"``
+    (report each mode's flux in the info dict) and ``"overlaps"`` (M x M modal overlap matrix with the previous problem of
+    the call, monitor_data.py:640-697, in the info dict as ``overlap_prev``; the input of ``postprocess.overlap_sort``).
+    With ``want_fields=False`` only ``n_complex`` and these small results leave the GPU.
     """
+    post = tuple(post or ())
+    unknown = set(post) - {"gauge", "normalize", "flux", "overlaps"}
+    if unknown:
+        raise ValueError(f"unknown post-processing step(s): {sorted(unknown)}")
+    post_flags = (1 if "gauge" in post else 0) | (2 if "normalize" in post else 0)
     packed, cache = [], {}
     for p in problems:
         split = p.get("split_curl_scaling")
@@ -113,7 +109,6 @@ def compute_modes_batch(
             # permittivity BEFORE the split-curl division (format_medium_data copies, solver.py:900)
             ec = np.array([np.asarray(c) for c in p["eps_cross"]])
             target_override = float(np.sqrt(np.max(np.abs(ec[np.abs(ec) < abs(PEC_VAL)]))))
-        _check_unsupported(p["eps_cross"], p.get("mu_cross"), split)
         if split is not None and p.get("solver_basis_fields") is not None:
             raise RuntimeError("Split curl not yet implemented for relative mode solver.")  # solver.py:938
         key = id(p["eps_cross"])
@@ -122,6 +117,8 @@ def compute_modes_batch(
             eps_in, p["coords"], p["freq"], p["mode_spec"], p.get("symmetry", (0, 0)), p.get("direction", "+"),
             eps_packed=None if split is not None else cache.get(key), basis_fields=p.get("solver_basis_fields"),
             mu_cross=p.get("mu_cross"), target_override=target_override,
+            incidence=(split is not None or p.get("mu_cross") is not None),  # solver.py:93
+            post=post_flags,
         )  # fmt: skip
         if split is None:
             cache[key] = pk.eps
@@ -134,7 +131,9 @@ def compute_modes_batch(
         packed.append(pk)
     h = handle or get_handle(device)  # after input validation: argument errors do not need a GPU
     with h.lock:
-        rc, fields, ncs, results = h.solve_batch(packed, want_fields, fields_ptrs)
+        rc, fields, ncs, results = h.solve_batch(packed, want_fields, fields_ptrs, want_flux=("flux" in post or "normalize" in post),
+                                                 want_overlaps="overlaps" in post)
+        flux_out, ov_out = h.last_flux, h.last_overlaps
         err = h.last_error() if rc != _cabi.OK else ""
     if rc != _cabi.OK:
         bad = [i for i in range(len(packed)) if results[i].status != _cabi.OK]
@@ -151,6 +150,10 @@ def compute_modes_batch(
                  stencil_applies=r.stencil_applies, is_complex=bool(r.is_complex), solve_ms=r.solve_ms, total_ms=r.total_ms,
                  max_residual=r.max_residual)
         )  # fmt: skip
+        if flux_out:
+            infos[-1]["flux"] = flux_out[i]
+        if ov_out:
+            infos[-1]["overlap_prev"] = ov_out[i]
     return (out, infos) if return_info else out
 
 

@@ -43,3 +43,24 @@ if "a" in which:
     for kw in (dict(mg_nu=1), dict(mg_nu=3), dict(mg_nu_growth=1), dict(mg_omega=0.7), dict(mg_cycles=2), dict(inner_relax=3.0), dict(inner_relax=10.0),
                dict(inner_relax_cap=1e-3), dict(gmres_cgs2=0), dict(gmres_cgs2=1), dict(use_graph=0)):
         run(16, "legacy", inner_mode=0, **kw)
+if "b" in which:
+    for nb in (64,):
+        run(nb, "new default")
+        run(nb, "new txr32", stencil_variant=2)
+        run(nb, "new no-dgks", outer_dgks=0)
+        run(nb, "new floor2e-5", ir_floor=2e-5)
+        run(nb, "legacy", inner_mode=0)
+    run(16, "new default")
+    run(16, "new txr32", stencil_variant=2)
+if "pec" in which:
+    from tests.golden.cases import CASES
+    fac, kw, _ = CASES["pec_block_40"]
+    wl = fac()
+    for opts in (dict(inner_mode=1), dict(inner_mode=0), dict(inner_mode=1, inner_ir=0)):
+        h = _cabi.Handle(**{**REF, **opts, "verbose": 2})
+        try:
+            out = compute_modes_batch([dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], handle=h)
+            print("pec", opts, out[0][1], flush=True)
+        except Exception as e:  # noqa: BLE001
+            print("pec", opts, "FAILED", e, flush=True)
+        h.close()
