@@ -48,6 +48,21 @@ enum { B200MS_SPEC_DIAGONAL = 0, B200MS_SPEC_TENSORIAL_REAL = 1, B200MS_SPEC_TEN
 
 typedef struct b200ms_handle b200ms_handle;
 
+/* A cross-section described by geometry instead of a sampled permittivity array: what ModeSolver._solver_eps builds on the
+ * host with nine Simulation.epsilon_on_grid calls per frequency (mode_solver.py:587-653, simulation.py:1135-1241) is
+ * rasterised on the device.  Axis-aligned rectangles in the solver plane (the cut of Box structures), later entries
+ * override earlier ones, staircased at the Yee E-sites exactly like epsilon_on_grid (eps_xx, eps_xy, eps_xz at the Ex site
+ * (cell centre in x, lower boundary in y), eps_y* at the Ey site, eps_z* at the Ez site). */
+typedef struct {
+  int nrect;
+  const double *rects;     /* nrect x 4: center_x, center_y, size_x, size_y; a site is inside when |x - cx| <= sx/2 and
+                              |y - cy| <= sy/2 (Box.inside, components/geometry/base.py:2042-2068) */
+  const int *medium;       /* nrect: row of eps_table used inside each rectangle */
+  int nmedia;              /* rows of eps_table; row 0 is the background medium */
+  const double *eps_table; /* nmedia x 9 complex128 (re,im): relative permittivity tensor (xx,xy,...,zz) of each medium AT THIS
+                              PROBLEM'S FREQUENCY (dispersive media are evaluated by the caller: 9 numbers per medium) */
+} b200ms_section;
+
 /* One eigenproblem == one compute_modes call (one plane, one frequency). */
 typedef struct {
   int nx, ny;            /* eps_cross[i].shape */
@@ -69,11 +84,12 @@ typedef struct {
   double bend_radius;    /* NaN == None */
   double angle_theta, angle_phi;
   const double *eps;     /* 9*nx*ny complex128 as interleaved (re,im), component-major xx,xy,...,zz,
-                            each component C-order with y fastest (solver.py:890-901) */
+                            each component C-order with y fastest (solver.py:890-901); NULL when `section` is given */
   const double *coords_x; /* nx+1 */
   const double *coords_y; /* ny+1 */
   const double *mu;      /* NULL (identity), or the relative permeability `mu_cross` (solver.py:62-66, 128-136) in the same
                             9*nx*ny complex128 layout as eps */
+  const b200ms_section *section; /* NULL, or the geometric description the permittivity is rasterised from (eps == NULL) */
   const double *basis_e; /* NULL, or the in-plane E part of `solver_basis_fields` (solver.py:219-236, 750-776):
                             2*nx*ny*num_modes complex128 (re,im) laid out [Ex|Ey][ix][iy][mode]; the modes are then
                             computed as linear combinations of this basis (relative mode solver) */

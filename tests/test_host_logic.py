@@ -35,7 +35,7 @@ def test_ctypes_structs_mirror_the_header(built_lib):
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
         for decl in body.split(";"):
-            m = re.search(r"(?:const\s+)?(?:double|int|long long)\s*\*?\s*([a-z_0-9,\s\*\[\]]+)$", decl.strip())
+            m = re.search(r"(?:const\s+)?(?:double|int|long long|b200ms_section)\s*\*?\s*([a-z_0-9,\s\*\[\]]+)$", decl.strip())
             if m:
                 for part in m.group(1).split(","):
                     names.append(re.sub(r"[\*\s]|\[\d+\]", "", part))

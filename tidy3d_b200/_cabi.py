@@ -24,13 +24,17 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 
+class SectionStruct(C.Structure):
+    _fields_ = [("nrect", C.c_int), ("rects", _dp), ("medium", _ip), ("nmedia", C.c_int), ("eps_table", _dp)]
+
+
 class Problem(C.Structure):
     _fields_ = [
         ("nx", C.c_int), ("ny", C.c_int), ("num_modes", C.c_int), ("num_pml", C.c_int * 2),
         ("symmetry", C.c_int * 2), ("bend_axis", C.c_int), ("direction", C.c_int), ("precision", C.c_int), ("incidence", C.c_int), ("post", C.c_int),
         ("freq", C.c_double), ("target_neff", C.c_double), ("bend_radius", C.c_double),
         ("angle_theta", C.c_double), ("angle_phi", C.c_double),
-        ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp), ("mu", _dp), ("basis_e", _dp),
+        ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp), ("mu", _dp), ("section", C.POINTER(SectionStruct)), ("basis_e", _dp),
     ]  # fmt: skip
 
 
@@ -114,8 +118,12 @@ class PackedProblem:
     """Owns the contiguous arrays a ``Problem`` struct points to."""
 
     def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None, basis_fields=None,
-                 mu_cross=None, target_override=None, incidence=False, post=0):
-        if eps_packed is not None:
+                 mu_cross=None, target_override=None, incidence=False, post=0, section=None):
+        self.section = None
+        if section is not None:  # geometric cross-section rasterised on the device (tidy3d_b200/sections.py); no eps array
+            self.section, self._section_arrays = section.pack(float(freq))
+            eps = None
+        elif eps_packed is not None:
             eps = eps_packed
         elif isinstance(eps_cross, np.ndarray) and eps_cross.dtype == np.complex128 and eps_cross.flags.c_contiguous and eps_cross.ndim == 3:
             # what ModeSolver._solver_eps returns (mode_solver.py:647-653): used in place, no host copy
@@ -132,12 +140,15 @@ class PackedProblem:
                     raise ValueError("Wrong input to mode solver pemittivity/permeability!")
                 comps = list(eps_cross)
             eps = np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.complex128) for c in comps]))
-        if eps.ndim != 3:
-            raise ValueError("Wrong input to mode solver pemittivity/permeability!")
-        self.eps = eps
-        self.nx, self.ny = eps.shape[1], eps.shape[2]
         self.cx = np.ascontiguousarray(coords[0], dtype=np.float64)
         self.cy = np.ascontiguousarray(coords[1], dtype=np.float64)
+        if eps is None:
+            self.nx, self.ny = self.cx.size - 1, self.cy.size - 1
+        else:
+            if eps.ndim != 3:
+                raise ValueError("Wrong input to mode solver pemittivity/permeability!")
+            self.nx, self.ny = eps.shape[1], eps.shape[2]
+        self.eps = eps
         if self.cx.size != self.nx + 1 or self.cy.size != self.ny + 1:
             raise ValueError("Mismatch between 'coords' and 'esp_cross' shapes.")
         p = Problem()
@@ -159,7 +170,11 @@ class PackedProblem:
         p.target_neff = math.nan if tn is None else float(tn)
         p.angle_theta = float(getattr(mode_spec, "angle_theta", 0.0))
         p.angle_phi = float(getattr(mode_spec, "angle_phi", 0.0))
-        p.eps, p.coords_x, p.coords_y = _ptr(self.eps.view(np.float64)), _ptr(self.cx), _ptr(self.cy)
+        p.coords_x, p.coords_y = _ptr(self.cx), _ptr(self.cy)
+        if self.eps is not None:
+            p.eps = _ptr(self.eps.view(np.float64))
+        else:
+            p.section = C.pointer(self.section)
         self.mu = None
         if mu_cross is not None:
             if isinstance(mu_cross, np.ndarray):
@@ -169,7 +184,7 @@ class PackedProblem:
                     raise ValueError("Wrong input to mode solver pemittivity/permeability!")
                 mcomps = list(mu_cross)
             self.mu = np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.complex128) for c in mcomps]))
-            if self.mu.shape != self.eps.shape:
+            if self.mu.shape != (9, self.nx, self.ny):
                 raise ValueError("Wrong input to mode solver pemittivity/permeability!")
             p.mu = _ptr(self.mu.view(np.float64))
         self.basis = None

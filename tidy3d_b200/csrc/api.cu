@@ -202,14 +202,14 @@ void prepare_window(b200ms_handle *h, const b200ms_problem *prob, int i0, int i1
   W.slot.assign(n, -1);
   W.h2d_bytes = 0;
   std::vector<std::pair<MediumKey, int>> seen;  // key -> first problem with that medium
-  std::vector<size_t> off_eps(n, 0), off_mu(n, 0), off_d(n, 0);
+  std::vector<size_t> off_eps(n, 0), off_mu(n, 0), off_d(n, 0), off_sec(n, 0);
   size_t total = 0;
   for (int q = 0; q < n; ++q) {
     const b200ms_problem &p = prob[i0 + q];
     ProblemSetup &s = W.setups[q];
     setup_geometry(p, s);
     if (s.status != B200MS_OK) continue;
-    MediumKey mk{p.eps, p.mu, p.coords_x, p.coords_y, p.nx, p.ny, p.num_pml[0], p.num_pml[1], p.bend_axis, p.incidence ? 1 : 0,
+    MediumKey mk{p.eps ? p.eps : reinterpret_cast<const double *>(p.section), p.mu, p.coords_x, p.coords_y, p.nx, p.ny, p.num_pml[0], p.num_pml[1], p.bend_axis, p.incidence ? 1 : 0,
                  p.bend_radius, p.angle_theta, p.angle_phi};
     auto it = std::find_if(seen.begin(), seen.end(), [&](const std::pair<MediumKey, int> &e) { return e.first == mk; });
     if (it != seen.end()) {
@@ -229,6 +229,12 @@ void prepare_window(b200ms_handle *h, const b200ms_problem *prob, int i0, int i1
       off_d[q] = total;
       total += align256(2 * s.jz_e.size() * sizeof(double));
     }
+    if (!p.eps) {  // geometric cross-section: rectangles, medium ids, eps table, cell boundaries
+      const b200ms_section &sec = *p.section;
+      off_sec[q] = total;
+      total += align256((size_t)sec.nrect * 4 * sizeof(double)) + align256((size_t)sec.nrect * sizeof(int)) +
+               align256((size_t)sec.nmedia * 9 * sizeof(cplx)) + align256((size_t)(p.nx + p.ny + 2) * sizeof(double));
+    }
   }
   const int nslot = (int)seen.size();
   raw.reserve(std::max<size_t>(total, 256));
@@ -245,8 +251,27 @@ void prepare_window(b200ms_handle *h, const b200ms_problem *prob, int i0, int i1
     const size_t N = (size_t)p.nx * p.ny;
     MediumRef r;
     r.eps = reinterpret_cast<const cplx *>(raw.p + off_eps[q]);
-    CUDA_CHECK(cudaMemcpyAsync(raw.p + off_eps[q], p.eps, 9 * N * sizeof(cplx), cudaMemcpyDefault, st));
-    W.h2d_bytes += 9 * N * sizeof(cplx);
+    if (p.eps) {
+      CUDA_CHECK(cudaMemcpyAsync(raw.p + off_eps[q], p.eps, 9 * N * sizeof(cplx), cudaMemcpyDefault, st));
+      W.h2d_bytes += 9 * N * sizeof(cplx);
+    } else {  // rasterise the geometric cross-section on the device (f-2: replaces nine epsilon_on_grid calls + a 9N upload)
+      const b200ms_section &sec = *p.section;
+      unsigned char *b0 = raw.p + off_sec[q];
+      double *d_rects = reinterpret_cast<double *>(b0);
+      int *d_med = reinterpret_cast<int *>(b0 + align256((size_t)sec.nrect * 4 * sizeof(double)));
+      cplx *d_tab = reinterpret_cast<cplx *>(reinterpret_cast<unsigned char *>(d_med) + align256((size_t)sec.nrect * sizeof(int)));
+      double *d_xy = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(d_tab) + align256((size_t)sec.nmedia * 9 * sizeof(cplx)));
+      if (sec.nrect > 0) {
+        CUDA_CHECK(cudaMemcpyAsync(d_rects, sec.rects, (size_t)sec.nrect * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(d_med, sec.medium, (size_t)sec.nrect * sizeof(int), cudaMemcpyHostToDevice, st));
+      }
+      CUDA_CHECK(cudaMemcpyAsync(d_tab, sec.eps_table, (size_t)sec.nmedia * 9 * sizeof(cplx), cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(d_xy, p.coords_x, (size_t)(p.nx + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(d_xy + p.nx + 1, p.coords_y, (size_t)(p.ny + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+      W.h2d_bytes += (size_t)sec.nrect * 36 + (size_t)sec.nmedia * 144 + (size_t)(p.nx + p.ny + 2) * 8;
+      SectionDev sd{sec.nrect, d_rects, d_med, d_tab, d_xy, d_xy + p.nx + 1};
+      section_raster_kernel<<<(unsigned)std::min<size_t>((N + 255) / 256, 2048), 256, 0, st>>>(sd, p.nx, p.ny, const_cast<cplx *>(r.eps));
+    }
     r.mu = nullptr;
     if (p.mu) {
       r.mu = reinterpret_cast<const cplx *>(raw.p + off_mu[q]);

@@ -163,7 +163,7 @@ inline void setup_geometry(const b200ms_problem &p, ProblemSetup &s) {
   s.ny = ny;
   s.num_modes = p.num_modes;
   s.direction = p.direction < 0 ? -1 : 1;
-  if (nx < 1 || ny < 1 || !p.eps || !p.coords_x || !p.coords_y || p.num_modes < 1) {
+  if (nx < 1 || ny < 1 || (!p.eps && !p.section) || !p.coords_x || !p.coords_y || p.num_modes < 1) {
     s.status = B200MS_ERR_ARG;
     s.error = "bad problem description";
     return;
@@ -313,9 +313,19 @@ inline void fill_fields_host(const b200ms_problem &p, ProblemSetup &s) {
     }
 }
 
-inline void setup_problem(const b200ms_problem &p, ProblemSetup &s) {
-  setup_geometry(p, s);
+inline void setup_problem(const b200ms_problem &pin, ProblemSetup &s) {
+  setup_geometry(pin, s);
   if (s.status != B200MS_OK) return;
+  b200ms_problem p = pin;
+  std::vector<cplx> raster;
+  if (!p.eps && p.section) {  // host mirror of section_raster_kernel
+    const b200ms_section &q = *p.section;
+    raster.resize((size_t)9 * p.nx * p.ny);
+    SectionDev sd{q.nrect, q.rects, q.medium, reinterpret_cast<const cplx *>(q.eps_table), p.coords_x, p.coords_y};
+    for (int ix = 0; ix < p.nx; ++ix)
+      for (int iy = 0; iy < p.ny; ++iy) section_cell(sd, p.nx, p.ny, ix, iy, raster.data());
+    p.eps = reinterpret_cast<const double *>(raster.data());
+  }
   MediumScan sc;
   scan_medium_host(p, s, sc);
   finish_setup(p, s, sc);

@@ -257,6 +257,34 @@ __global__ void __launch_bounds__(256) tensor_fields_kernel(const MediumRef *med
   }
 }
 
+// ---- rasterisation of a geometric cross-section (b200ms_section) into the raw eps layout [9][nx][ny] ------------------------
+struct SectionDev {
+  int nrect;
+  const double *rects;  // nrect x 4: cx, cy, sx, sy
+  const int *medium;    // nrect
+  const cplx *table;    // nmedia x 9
+  const double *xs, *ys;  // cell boundaries, nx+1 / ny+1
+};
+HD int section_medium_at(const SectionDev &s, double x, double y) {
+  int med = 0;
+  for (int r = 0; r < s.nrect; ++r) {
+    const double *q = s.rects + 4 * r;
+    if (fabs(x - q[0]) <= q[2] / 2 && fabs(y - q[1]) <= q[3] / 2) med = s.medium[r];  // later structures override (simulation.py:1199-1226)
+  }
+  return med;
+}
+HD void section_cell(const SectionDev &s, int nx, int ny, int ix, int iy, cplx *eps) {
+  const size_t n = (size_t)nx * ny, c = (size_t)ix * ny + iy;
+  const double xb = s.xs[ix], yb = s.ys[iy], xc = (s.xs[ix] + s.xs[ix + 1]) / 2, yc = (s.ys[iy] + s.ys[iy + 1]) / 2;
+  const int med[3] = {section_medium_at(s, xc, yb), section_medium_at(s, xb, yc), section_medium_at(s, xb, yb)};  // Ex, Ey, Ez sites
+  for (int row = 0; row < 3; ++row)
+    for (int col = 0; col < 3; ++col) eps[(size_t)(3 * row + col) * n + c] = s.table[(size_t)med[row] * 9 + 3 * row + col];
+}
+__global__ void __launch_bounds__(256) section_raster_kernel(SectionDev s, int nx, int ny, cplx *eps) {
+  const size_t n = (size_t)nx * ny;
+  for (size_t c = (size_t)blockIdx.x * 256 + threadIdx.x; c < n; c += (size_t)gridDim.x * 256) section_cell(s, nx, ny, (int)(c / ny), (int)(c % ny), eps);
+}
+
 // y1 = 0 where exx == 0, y2 = 0 where eyy == 0 (the markers of removed PEC unknowns); strided two-component fields
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) mask_kernel(T *y, size_t y_bstride, const C *fields, size_t f_bstride, size_t n) {

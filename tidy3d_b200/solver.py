@@ -104,25 +104,29 @@ def compute_modes_batch(
     for p in problems:
         split = p.get("split_curl_scaling")
         target_override = None
-        if split is not None and getattr(p["mode_spec"], "target_neff", None) is None and not isinstance(p["eps_cross"], np.ndarray):
+        if split is not None and getattr(p["mode_spec"], "target_neff", None) is None and not isinstance(p.get("eps_cross"), np.ndarray):
             # solver.py:204-207: the default target comes from `eps_cross` as passed; for a list/tuple input that is the
             # permittivity BEFORE the split-curl division (format_medium_data copies, solver.py:900)
             ec = np.array([np.asarray(c) for c in p["eps_cross"]])
             target_override = float(np.sqrt(np.max(np.abs(ec[np.abs(ec) < abs(PEC_VAL)]))))
         if split is not None and p.get("solver_basis_fields") is not None:
             raise RuntimeError("Split curl not yet implemented for relative mode solver.")  # solver.py:938
-        key = id(p["eps_cross"])
-        eps_in = _apply_split_curl(p["eps_cross"], split) if split is not None else p["eps_cross"]
+        section = p.get("section")
+        if section is not None and (split is not None or p.get("eps_cross") is not None):
+            raise ValueError("give either 'eps_cross' or 'section' (a section cannot be combined with split_curl_scaling)")
+        key = id(p.get("eps_cross"))
+        eps_in = None if section is not None else (_apply_split_curl(p["eps_cross"], split) if split is not None else p["eps_cross"])
         pk = _cabi.PackedProblem(
             eps_in, p["coords"], p["freq"], p["mode_spec"], p.get("symmetry", (0, 0)), p.get("direction", "+"),
-            eps_packed=None if split is not None else cache.get(key), basis_fields=p.get("solver_basis_fields"),
+            eps_packed=None if (split is not None or section is not None) else cache.get(key), basis_fields=p.get("solver_basis_fields"),
+            section=section,
             mu_cross=p.get("mu_cross"), target_override=target_override,
             incidence=(split is not None or p.get("mu_cross") is not None),  # solver.py:93
             post=post_flags,
         )  # fmt: skip
-        if split is None:
+        if split is None and section is None:
             cache[key] = pk.eps
-        if key in cache and len(packed) and packed[-1].eps is pk.eps:
+        if section is None and key in cache and len(packed) and packed[-1].eps is pk.eps:
             # share the coordinate arrays too so the library can detect identical cross-sections
             prev = packed[-1]
             if np.array_equal(prev.cx, pk.cx) and np.array_equal(prev.cy, pk.cy):
