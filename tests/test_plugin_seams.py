@@ -21,12 +21,22 @@ def _fake_tidy3d(monkeypatch):
         def _postprocess_solver_fields(self, solver_fields):
             return {"Ex": solver_fields[0, 0], "Hz": solver_fields[1, 2]}
 
+        def _postprocess_solver_fields_inverse(self, fields):
+            return np.stack([fields["Ex"]] * 6)
+
         def _solve_all_freqs(self, coords, symmetry):
             raise AssertionError("reference loop should have been replaced")
 
+        def _solve_all_freqs_relative(self, coords, symmetry, basis_fields):
+            raise AssertionError("reference loop should have been replaced")
+
         @property
-        def data(self):
-            return self._solve_all_freqs(coords=[np.arange(5.0), np.arange(6.0)], symmetry=(0, 0))
+        def data(self):  # like data_raw: the group-index variant solves a copy with 3x the frequencies (mode_solver.py:283-299)
+            solver = self
+            if getattr(self, "group_index_step", 0):
+                solver = ModeSolver(list(np.outer(self.freqs, (1 - self.group_index_step, 1, 1 + self.group_index_step)).flatten()),
+                                    self.mode_spec.num_modes)
+            return solver._solve_all_freqs(coords=[np.arange(5.0), np.arange(6.0)], symmetry=(0, 0))
 
     ms = types.ModuleType("tidy3d.plugins.mode.mode_solver")
     ms.ModeSolver = ModeSolver
@@ -51,7 +61,7 @@ def test_install_rebinds_both_seams(monkeypatch):
     seen = []
 
     def fake_batch(problems):
-        seen.append(problems)
+        seen.append(list(problems))
         out = []
         for p in problems:
             m = p["mode_spec"].num_modes
@@ -69,6 +79,34 @@ def test_install_rebinds_both_seams(monkeypatch):
     assert all(p["symmetry"] == (0, 1) and p["direction"] == "+" for p in seen[0])
     assert eps_spec == ["diagonal"] * 3 and len(n_complex) == 3
     assert fields[1]["Ex"].shape == (4, 5, 1, 2) and np.allclose(fields[1]["Ex"], 2.0)
-    # run_batch mirrors web.api.mode.run_batch: a list of ModeSolver -> list of .data
-    res = plugin.run_batch([cls(freqs=[2.0e14], num_modes=1), cls(freqs=[1.5e14, 1.6e14], num_modes=3)])
-    assert len(res) == 2 and len(res[1][0]) == 2
+    # relative seam (mode_solver.py:674-693): one device call, basis passed through _postprocess_solver_fields_inverse
+    basis = [{"Ex": np.zeros((4, 5, 1, 2))}] * 3
+    seen.clear()
+    solver._solve_all_freqs_relative(coords=[np.arange(5.0), np.arange(6.0)], symmetry=(0, 0), basis_fields=basis)
+    assert len(seen) == 1 and all(p["solver_basis_fields"].shape == (6, 4, 5, 1, 2) for p in seen[0])
+    # run_batch mirrors web.api.mode.run_batch: a list of ModeSolver -> list of .data, with ONE device call for all of
+    # them, including the 3x frequency copy of a group-index solver
+    seen.clear()
+    gi = cls(freqs=[1.5e14, 1.6e14], num_modes=3)
+    gi.group_index_step = 0.01
+    res = plugin.run_batch([cls(freqs=[2.0e14], num_modes=1), gi, cls(freqs=[1.9e14], num_modes=2)])
+    assert len(seen) == 1 and [len(p) for p in seen] == [1 + 6 + 1]
+    assert len(res) == 3 and len(res[0][0]) == 1 and len(res[1][0]) == 6 and len(res[2][0]) == 1
+    assert np.allclose(res[1][1][4]["Ex"], 1.6)  # second base frequency, centre of its triple
+    assert cls._solve_all_freqs is plugin.solve_all_freqs_batched  # the patch is restored
+
+
+def test_group_index_formula():
+    """monitor_data.py:1507-1548 on an analytic dispersion n(f) = a + b f + c f^2: n_g = n + f dn/df exactly recovered."""
+    import tidy3d_b200.plugin as plugin
+
+    a, b, c = 2.0, 1e-15, 3e-30
+    f0 = np.array([1.9e14, 2.0e14])
+    step = 0.005
+    f = np.outer(f0, (1 - step, 1, 1 + step)).flatten()
+    n = (a + b * f + c * f**2)[:, None] * np.ones((1, 2))
+    fc, nc, ng, disp = plugin.group_index(n, f, step)
+    assert np.allclose(fc, f0) and np.allclose(nc[:, 0], a + b * f0 + c * f0**2)
+    assert np.allclose(ng[:, 0], a + 2 * b * f0 + 3 * c * f0**2, rtol=1e-12)
+    d2 = 2 * c
+    assert np.allclose(disp[:, 0], -(f0 / 2.99792458e14) ** 2 * (2 * (b + 2 * c * f0) + f0 * d2) * 1e18, rtol=1e-6)

@@ -193,6 +193,28 @@ inline CMat tri_eigvecs(const CMat &t, int k) {
   return s;
 }
 
+// Condition numbers of the eigenvalues of an upper-triangular T from its (unit-norm, upper-triangular) eigenvector matrix S:
+// kappa_i = ||row i of S^-1||_2 (* ||column i of S||_2 = 1), i.e. 1 / |y_i^H x_i| for unit left/right eigenvectors.
+inline std::vector<double> eig_condition(const CMat &s, int k) {
+  // inverse of an upper-triangular matrix by back-substitution, row by row from the bottom
+  CMat inv(k, k);
+  for (int i = k - 1; i >= 0; --i) {
+    inv(i, i) = 1.0 / s(i, i);
+    for (int j = i + 1; j < k; ++j) {
+      cd acc = 0.0;
+      for (int l = i + 1; l <= j; ++l) acc += s(i, l) * inv(l, j);
+      inv(i, j) = -acc / s(i, i);
+    }
+  }
+  std::vector<double> kappa(k);
+  for (int i = 0; i < k; ++i) {
+    double r = 0.0;
+    for (int j = i; j < k; ++j) r += std::norm(inv(i, j));
+    kappa[i] = std::sqrt(r);
+  }
+  return kappa;
+}
+
 inline CMat matmul(const CMat &a, const CMat &b) {
   CMat c(a.rows, b.cols);
   for (int i = 0; i < a.rows; ++i)

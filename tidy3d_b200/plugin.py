@@ -1,33 +1,55 @@
 """Seams into a real ``tidy3d`` install (not importable in this image: xarray/shapely/... are absent).
 
 Seam 1 (exact drop-in, one solve per call): ``tidy3d.plugins.mode.mode_solver`` imports the module-level name
-``compute_modes`` (mode_solver.py:59-65) and calls it at :725; ``install()`` rebinds that name.
+``compute_modes`` (mode_solver.py:59-65) and calls it at :725 and :776; ``install()`` rebinds that name.
 
 Seam 2 (batched, where the speed is): ``ModeSolver._solve_all_freqs(self, coords, symmetry)`` (mode_solver.py:655-672)
-loops ``_solve_single_freq`` over ``self.freqs``; ``solve_all_freqs_batched`` gathers ``self._solver_eps(f)`` for every
-frequency, runs ONE device call and reuses the reference's own ``_postprocess_solver_fields`` (:695).  ``run_batch``
-mirrors ``tidy3d.web.api.mode.run_batch(mode_solvers)`` (web/api/mode.py:147-158) for many mode planes.
+and ``ModeSolver._solve_all_freqs_relative(self, coords, symmetry, basis_fields)`` (:674-693) loop the single-frequency
+solve over ``self.freqs``; the replacements gather ``self._solver_eps(f)`` for every frequency, run ONE device call and
+reuse the reference's own ``_postprocess_solver_fields`` (:695).
+
+Seam 3 (many mode planes): ``run_batch(mode_solvers)`` mirrors ``tidy3d.web.api.mode.run_batch``
+(web/api/mode.py:147-158) locally: the problems of ALL solvers -- including the 3x frequency copies the reference makes
+for the group index (mode_solver.py:267-299) and EME cell planes (components/eme/simulation.py:521-540 build one
+ModeSolver per cell) -- are collected first and solved in a single batched device call, then every ``ModeSolver.data``
+is assembled by the reference's own code from the precomputed results.
 """
 from __future__ import annotations
 
 from typing import List
 
+import numpy as np
+
 from .solver import compute_modes, compute_modes_batch
+
+
+def _problems(ms, coords, symmetry, basis_fields=None):
+    out = []
+    for k, freq in enumerate(ms.freqs):
+        p = dict(eps_cross=ms._solver_eps(freq), coords=coords, freq=freq, mode_spec=ms.mode_spec, symmetry=symmetry, direction=ms.direction)
+        if basis_fields is not None:
+            p["solver_basis_fields"] = ms._postprocess_solver_fields_inverse(basis_fields[k])  # mode_solver.py:774
+        out.append(p)
+    return out
+
+
+def _assemble(ms, results):
+    n_complex, fields, eps_spec = [], [], []
+    for solver_fields, n_freq, spec in results:
+        fields.append(ms._postprocess_solver_fields(solver_fields))
+        n_complex.append(n_freq)
+        eps_spec.append(spec)
+    return n_complex, fields, eps_spec
 
 
 def solve_all_freqs_batched(self, coords, symmetry):
     """Replacement body for ``ModeSolver._solve_all_freqs`` (same signature and return value)."""
-    problems = [
-        dict(eps_cross=self._solver_eps(freq), coords=coords, freq=freq, mode_spec=self.mode_spec, symmetry=symmetry,
-             direction=self.direction)
-        for freq in self.freqs
-    ]  # fmt: skip
-    n_complex, fields, eps_spec = [], [], []
-    for solver_fields, n_freq, spec in compute_modes_batch(problems):
-        fields.append(self._postprocess_solver_fields(solver_fields))
-        n_complex.append(n_freq)
-        eps_spec.append(spec)
-    return n_complex, fields, eps_spec
+    return _assemble(self, compute_modes_batch(_problems(self, coords, symmetry)))
+
+
+def solve_all_freqs_relative_batched(self, coords, symmetry, basis_fields):
+    """Replacement body for ``ModeSolver._solve_all_freqs_relative`` (mode_solver.py:674-693)."""
+    return _assemble(self, compute_modes_batch(_problems(self, coords, symmetry, basis_fields)))
 
 
 def install(batched: bool = True):
@@ -38,11 +60,71 @@ def install(batched: bool = True):
     ms.LOCAL_SOLVER_IMPORTED = True
     if batched:
         ms.ModeSolver._solve_all_freqs = solve_all_freqs_batched
+        ms.ModeSolver._solve_all_freqs_relative = solve_all_freqs_relative_batched
     return ms.ModeSolver
 
 
+class _Collected(Exception):
+    """Raised by the recording pass of ``run_batch`` to leave ``ModeSolver.data`` once its problems are known."""
+
+
 def run_batch(mode_solvers: List, **kwargs) -> List:
-    """Local analogue of ``tidy3d.web.api.mode.run_batch``: ``[ms.data for ms in mode_solvers]`` with the solver
-    routed through the GPU (each ``ModeSolver.data`` triggers one batched device call over its frequencies)."""
-    install(batched=True)
-    return [ms.data for ms in mode_solvers]
+    """Local analogue of ``tidy3d.web.api.mode.run_batch(mode_solvers) -> List[ModeSolverData]`` with ONE device call for
+    all planes and frequencies.
+
+    Pass 1 runs every ``ModeSolver.data`` with ``_solve_all_freqs`` replaced by a recorder: the reference's own code
+    decides coordinates, symmetry, reduced simulation copies and the extra group-index frequencies, the recorder notes the
+    resulting problems and aborts.  The problems of all solvers then go to the GPU together, and pass 2 re-runs
+    ``ModeSolver.data`` with ``_solve_all_freqs`` replaying the precomputed results, so everything downstream of the
+    solve (colocation, normalisation, mode tracking, group index; mode_solver.py:300-343) is the reference's own code.
+    """
+    ModeSolver = install(batched=True)
+    recorded: List[list] = []
+
+    def record(self, coords, symmetry):
+        recorded.append(_problems(self, coords, symmetry))
+        raise _Collected
+
+    saved = ModeSolver._solve_all_freqs
+    ModeSolver._solve_all_freqs = record
+    try:
+        for ms in mode_solvers:
+            try:
+                ms.data  # noqa: B018  (cached_property: nothing is cached when the recorder aborts)
+            except _Collected:
+                pass
+    finally:
+        ModeSolver._solve_all_freqs = saved
+    if len(recorded) != len(mode_solvers):
+        raise RuntimeError("run_batch: a ModeSolver did not reach its solve (already cached?)")
+    flat = [p for plist in recorded for p in plist]
+    results = compute_modes_batch(flat)
+    queue, pos = [], 0
+    for plist in recorded:
+        queue.append(results[pos : pos + len(plist)])
+        pos += len(plist)
+
+    def replay(self, coords, symmetry):
+        return _assemble(self, queue.pop(0))
+
+    ModeSolver._solve_all_freqs = replay
+    try:
+        return [ms.data for ms in mode_solvers]
+    finally:
+        ModeSolver._solve_all_freqs = saved
+
+
+def group_index(n_complex, freqs, step: float):
+    """Group index and dispersion from a sweep solved at the frequencies of ``ModeSolver._freqs_for_group_index``
+    (``np.outer(freqs0, (1 - step, 1, 1 + step)).flatten()``, mode_solver.py:267-271), for callers that drive
+    ``compute_modes_batch`` directly: the formulas of ``ModeData._group_index_post_process`` (monitor_data.py:1507-1548).
+    ``n_complex``: (3 F, M).  Returns ``(freqs0, n_complex0, n_group, dispersion)`` with dispersion in ps/(nm km)."""
+    n = np.asarray(n_complex).real
+    f = np.asarray(freqs, float)
+    back, center, fwd = n[0::3], n[1::3], n[2::3]
+    f0 = f[1::3]
+    inv = 1.0 / step
+    n_group = center + (fwd - back) * inv * 0.5
+    c0 = 2.99792458e14
+    dispersion = (fwd * (inv + 1) + back * (inv - 1) - center * inv * 2) * f0.reshape(-1, 1) * (-1e18 * inv / c0**2)
+    return f0, np.asarray(n_complex)[1::3], n_group, dispersion
