@@ -153,6 +153,8 @@ typedef struct {
                             refinement (needs mg_precision == 1; diagonal path); 0: fp64 cycles */
   double ir_floor;       /* smallest residual reduction asked of one fp32 cycle (default 1e-4) */
   double ir_trust;       /* solves whose tolerance is >= this accept the fp32 residual estimate without an fp64 check (3e-5) */
+  int stencil_async;     /* 1: stencil rows staged with cp.async (LDGSTS) into a shared-memory ring instead of prefetch registers (4/8-byte
+                            element types, no mu fields); 0: register-prefetch marching kernel */
   double kappa_cap;      /* the Ritz residual of a wanted pair is weighted by min(kappa, kappa_cap), kappa = condition number of the
                             Ritz value in the projected problem, before the comparison with eig_tol (default 1e4; 1 = ARPACK's test) */
   int outer_dgks;        /* 1 (default): Krylov-Schur orthogonalisation reorthogonalises only when ARPACK's DGKS test asks for it;

@@ -465,6 +465,15 @@ class BatchSolver {
   template <typename TT, typename CC, int TXR>
   void launch_march(const Level &v, int mode, const StencilArgs<TT, CC> &a, bool have_dinv) {
     dim3 blk(kMarchCols), grd((v.ny + kMarchOut - 1) / kMarchOut, (v.nx + TXR - 1) / TXR, B);
+    if constexpr (sizeof(TT) <= 8 && sizeof(CC) <= 8) {
+      // cp.async (LDGSTS) variant: the multigrid hot path -- stored-diagonal sweep, residual, apply -- without mu fields
+      if (opt_.stencil_async && !has_mu && (mode != MODE_JACOBI || have_dinv)) {
+        if (mode == MODE_JACOBI) stencil_march_async_kernel<TT, CC, MODE_JACOBI_D, TXR><<<grd, blk, 0, st_>>>(a);
+        else if (mode == MODE_RESID) stencil_march_async_kernel<TT, CC, MODE_RESID, TXR><<<grd, blk, 0, st_>>>(a);
+        else stencil_march_async_kernel<TT, CC, MODE_APPLY, TXR><<<grd, blk, 0, st_>>>(a);
+        return;
+      }
+    }
     if (mode == MODE_JACOBI && have_dinv) {  // stored-diagonal sweep: fewer registers and instructions than recomputing it
       if (has_mu) stencil_march_kernel<TT, CC, MODE_JACOBI_D, true, TXR><<<grd, blk, 0, st_>>>(a);
       else stencil_march_kernel<TT, CC, MODE_JACOBI_D, false, TXR><<<grd, blk, 0, st_>>>(a);

@@ -64,3 +64,20 @@ if "pec" in which:
         except Exception as e:  # noqa: BLE001
             print("pec", opts, "FAILED", e, flush=True)
         h.close()
+if "c" in which:
+    for nb in (64, 16):
+        run(nb, "async0", stencil_async=0)
+        run(nb, "async1", stencil_async=1)
+    run(64, "async1 txr32", stencil_async=1, stencil_variant=2)
+    run(64, "kappa1 (ARPACK test)", kappa_cap=1.0)
+    for name in ("c3_512", "c4_512"):
+        from tests.golden.cases import CASES
+        fac, kw, _ = CASES[name]
+        wl = fac()
+        gg = np.load(f"/root/repo/tests/golden/{name}.npz")
+        for opts in (dict(stencil_async=0), dict(stencil_async=1)):
+            h = _cabi.Handle(**{**REF, **opts})
+            t0 = time.time()
+            out, info = compute_modes_batch([dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], return_info=True, handle=h)
+            print(f"## {name} {opts}: |dn| {np.abs(out[0][1] - gg['n_tight']).max():.1e} inner {info[0]['inner_iters']} dev_ms {h.last_stats()['device_ms']:.0f} wall {time.time()-t0:.2f}", flush=True)
+            h.close()
