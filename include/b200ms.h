@@ -153,6 +153,8 @@ typedef struct {
                             refinement (needs mg_precision == 1; diagonal path); 0: fp64 cycles */
   double ir_floor;       /* smallest residual reduction asked of one fp32 cycle (default 1e-4) */
   double ir_trust;       /* solves whose tolerance is >= this accept the fp32 residual estimate without an fp64 check (3e-5) */
+  int mg_fused_tail;     /* 1 (default): the multigrid levels that fit in shared memory together (<= 64^2 cells) run as one kernel, one
+                            CTA per problem (csrc/coarse_kernel.cuh); 0: one kernel per operation on every level */
   int stencil_async;     /* 1: stencil rows staged with cp.async (LDGSTS) into a shared-memory ring instead of prefetch registers (4/8-byte
                             element types, no mu fields); 0: register-prefetch marching kernel */
   double kappa_cap;      /* the Ritz residual of a wanted pair is weighted by min(kappa, kappa_cap), kappa = condition number of the

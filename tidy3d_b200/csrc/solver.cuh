@@ -16,6 +16,7 @@
 #include "host_setup.hpp"
 #include "kernels.cuh"
 #include "krylov_kernels.cuh"
+#include "coarse_kernel.cuh"
 
 namespace b200ms {
 
@@ -409,6 +410,7 @@ class BatchSolver {
     dinv_ready_ = true;
     CUDA_CHECK(cudaStreamSynchronize(st_));
     CUDA_CHECK(cudaGetLastError());
+    plan_fused_tail();
     capture_precondition_graph();
   }
 
@@ -661,9 +663,50 @@ class BatchSolver {
     if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
   }
 
+  // Levels [fused_l0_, L) run as one kernel (csrc/coarse_kernel.cuh) when they fit in shared memory together: the
+  // largest tail whose level vectors (8 N elements per level) stay under ~200 KB, starting at <= 64^2 cells.
+  void plan_fused_tail() {
+    fused_l0_ = -1;
+    const int L = (int)lv.size();
+    if (!opt_.mg_fused_tail || coarse_krylov_ || opt_.mg_nu_growth != 0) return;
+    int l0 = L;
+    size_t elems = 0;
+    while (l0 > 0 && L - (l0 - 1) <= kFusedMaxLevels) {
+      const size_t add = (size_t)8 * lv[l0 - 1].N;
+      if (lv[l0 - 1].N > 4096 || (elems + add) * sizeof(P) > (size_t)200 * 1024) break;
+      elems += add;
+      --l0;
+    }
+    if (l0 >= L || L - l0 < 2) return;  // nothing worth fusing
+    fused_l0_ = l0;
+    fused_smem_ = elems * sizeof(P);
+    if (has_mu) CUDA_CHECK(cudaFuncSetAttribute(fused_vcycle_kernel<P, PC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_));
+    else CUDA_CHECK(cudaFuncSetAttribute(fused_vcycle_kernel<P, PC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_));
+  }
+  void launch_fused_tail(const P *rin, P *xout) {
+    const int L = (int)lv.size();
+    FusedArgs<P, PC> a;
+    a.nl = L - fused_l0_;
+    a.nu = std::max(1, opt_.mg_nu);
+    a.ncoarse = std::max(2, opt_.mg_coarse_iters);
+    for (int q = 0; q < a.nl; ++q) {
+      const Level &v = lv[fused_l0_ + q];
+      a.lv[q].nx = v.nx; a.lv[q].ny = v.ny; a.lv[q].fields = v.fields; a.lv[q].fbstride = v.fbstride;
+      a.lv[q].cx = v.cx; a.lv[q].cy = v.cy; a.lv[q].dinv = v.dinv; a.lv[q].tr = v.tr;
+    }
+    a.rin = rin; a.xout = xout; a.sigma = sigma_p_;
+    stats.launches++;
+    if (has_mu) fused_vcycle_kernel<P, PC, true><<<B, 512, fused_smem_, st_>>>(a);
+    else fused_vcycle_kernel<P, PC, false><<<B, 512, fused_smem_, st_>>>(a);
+  }
+
   // -- multigrid V-cycle: z = M^-1 rin on level l.  Result lands in `out` (or lv[l].x if null). ----
   void vcycle(int l, const P *rin, P *out) {
     Level &v = lv[l];
+    if (l == fused_l0_) {
+      launch_fused_tail(rin, out ? out : v.x);
+      return;
+    }
     const int L = (int)lv.size();
     const int nu = std::max(1, opt_.mg_nu + l * opt_.mg_nu_growth);  // optional variable V-cycle: more sweeps on coarser levels
     P *cur = v.x, *oth = v.tmp;
@@ -1363,6 +1406,9 @@ class BatchSolver {
           double rel = std::abs(acc) / std::max(std::abs(Tm(i, i)), 1e-300);
           worst = std::max(worst, rel);
           if (rel * std::min(std::max(kappa[i], 1.0), opt_.kappa_cap) <= opt_.eig_tol) ++nconv;
+          if (opt_.verbose >= 2 && b == 0)
+            fprintf(stderr, "[b200ms]   restart %d ritz %d: theta (%.9e, %.9e) rel %.2e kappa %.2e tol_inner %.1e\n", rst, q, Tm(i, i).real(), Tm(i, i).imag(), rel,
+                    kappa[i], tolv[b]);
         }
         out.nconv[b] = nconv;
         out.resid[b] = worst;
@@ -1716,6 +1762,8 @@ class BatchSolver {
   double *tol_dev_ = nullptr, *res_dev_ = nullptr, *n2_dev_ = nullptr, *bn2_dev_ = nullptr;
   int *jused_dev_ = nullptr;
   unsigned char *skip_dev_ = nullptr;
+  int fused_l0_ = -1;      // first level of the fused multigrid tail (-1: none)
+  size_t fused_smem_ = 0;
   double rho_ = 0.2;  // convergence factor per Arnoldi step seen in the last cycle (plans the next one)
 };
 

@@ -81,3 +81,33 @@ if "c" in which:
             out, info = compute_modes_batch([dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], return_info=True, handle=h)
             print(f"## {name} {opts}: |dn| {np.abs(out[0][1] - gg['n_tight']).max():.1e} inner {info[0]['inner_iters']} dev_ms {h.last_stats()['device_ms']:.0f} wall {time.time()-t0:.2f}", flush=True)
             h.close()
+if "pml" in which:
+    from tests.golden.cases import CASES
+    fac, kw, _ = CASES["pml_none_128"]
+    wl = fac()
+    gg = np.load("/root/repo/tests/golden/pml_none_128.npz")
+    for label, opts in (("ref", dict(REF)), ("tight", dict(eig_tol=1e-9, inner_tol=1e-10)), ("ref-norelax", dict(REF, inner_relax=0.0)), ("ref-kappa1", dict(REF, kappa_cap=1.0))):
+        h = _cabi.Handle(**{**opts, "verbose": 2 if label == "ref" else 0})
+        t0 = time.time()
+        out, info = compute_modes_batch([dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], return_info=True, handle=h)
+        print(f"## pml_none_128 {label}: dn {np.abs(out[0][1] - gg['n_tight'])} op {info[0]['op_applies']} inner {info[0]['inner_iters']} rst {info[0]['restarts']} wall {time.time()-t0:.2f}", flush=True)
+        h.close()
+if "fused" in which:
+    for nb in (64, 16, 1):
+        run(nb, "fused1", mg_fused_tail=1)
+        run(nb, "fused0", mg_fused_tail=0)
+    from tests.golden.cases import CASES
+    for name in ("c1_64", "strip_128_m4", "c3_96", "c4_96", "lossy_48", "nonuniform_56", "slab1d_x1", "c3_512"):
+        fac, kw, _ = CASES[name]
+        wl = fac()
+        gg = np.load(f"/root/repo/tests/golden/{name}.npz")
+        for opts in (dict(mg_fused_tail=1), dict(mg_fused_tail=0)):
+            h = _cabi.Handle(**{**REF, **opts})
+            try:
+                compute_modes_batch([dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], handle=h)
+                t0 = time.time()
+                out, info = compute_modes_batch([dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], return_info=True, handle=h)
+                print(f"## {name} {opts}: |dn| {np.abs(out[0][1] - gg['n_tight']).max():.1e} inner {info[0]['inner_iters']} dev_ms {h.last_stats()['device_ms']:.1f} wall {time.time()-t0:.3f}", flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(f"## {name} {opts}: FAILED {e}", flush=True)
+            h.close()
