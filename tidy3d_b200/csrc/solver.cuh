@@ -1414,7 +1414,19 @@ class BatchSolver {
         out.resid[b] = worst;
         // the first-order tensorial operator is far from normal (eigenvalue errors follow the residual linearly): its
         // shift-invert solves are not relaxed (measured on angled_phi_48: |dn| 4e-8 relaxed vs 1e-10 exact)
-        if (opt_.inner_relax > 0 && !tensor_)
+        // The relaxation bound of inexact Arnoldi carries the spectral gap of the wanted Ritz value as a factor (Simoncini
+        // 2005): harmless for guided modes, fatal for a nearly degenerate non-normal pair (pml_none_128: two PML modes 3e-5
+        // apart in theta; with the relaxed 1e-4 solves |dn| was 6e-5, with unrelaxed 1e-8 solves 4e-8).  A wanted Ritz value
+        // closer than cluster_gap (relative) to any other Ritz value switches the relaxation off for that problem.
+        double min_gap = 1e300;
+        for (int q = 0; q < k; ++q) {
+          const cd ti = Tm(w[q], w[q]);
+          for (int j = 0; j < m; ++j)
+            if (j != w[q]) min_gap = std::min(min_gap, std::abs(Tm(j, j) - ti) / std::max(std::abs(ti), 1e-300));
+        }
+        const bool clustered = min_gap < opt_.cluster_gap;
+        if (clustered) tolv[b] = opt_.inner_tol;
+        if (opt_.inner_relax > 0 && !tensor_ && !clustered)
           tolv[b] = std::min(opt_.inner_relax_cap, std::max(opt_.inner_tol, opt_.inner_relax * opt_.inner_tol / std::max(worst, 1e-300)));
         if (nconv == k || rst == opt_.max_restarts) {
           done[b] = 1;
