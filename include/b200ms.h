@@ -153,6 +153,7 @@ typedef struct {
                             refinement (needs mg_precision == 1; diagonal path); 0: fp64 cycles */
   double ir_floor;       /* smallest residual reduction asked of one fp32 cycle (default 1e-4) */
   double ir_trust;       /* solves whose tolerance is >= this accept the fp32 residual estimate without an fp64 check (3e-5) */
+  double inner_relax_complex; /* complex-arithmetic problems: loosest inner tolerance = this x inner_tol (default 50) */
   double cluster_gap;    /* a wanted Ritz value closer than this (relative) to another Ritz value disables the relaxation of the inner
                             tolerance for that problem (default 1e-3) */
   int mg_fused_tail;     /* 1 (default): the multigrid levels that fit in shared memory together (<= 64^2 cells) run as one kernel, one

@@ -85,6 +85,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->inner_ir = 1;
   o->ir_floor = 1e-4;
   o->ir_trust = 3e-5;
+  o->inner_relax_complex = 50.0;
   o->cluster_gap = 1e-3;
   o->mg_fused_tail = 1;
   o->stencil_async = 0;
