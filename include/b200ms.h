@@ -154,6 +154,10 @@ typedef struct {
   double ir_floor;       /* smallest residual reduction asked of one fp32 cycle (default 1e-4) */
   double ir_trust;       /* solves whose tolerance is >= this accept the fp32 residual estimate without an fp64 check (3e-5) */
   double inner_relax_complex; /* complex-arithmetic problems: loosest inner tolerance = this x inner_tol (default 50) */
+  int transfer_tiled;    /* 1 (default): shared-memory tiled restriction kernel on levels with >= 64 coarse columns; 0: per-thread gathers */
+  int warm_start;        /* 1: within one call, each device batch starts its Krylov spaces from the wanted Ritz vectors of the previous
+                            batch of the same shape (neighbouring frequencies of a sweep); 0 (default): seeded random start vector
+                            like the reference (solver.py:822-857) */
   double cluster_gap;    /* a wanted Ritz value closer than this (relative) to another Ritz value disables the relaxation of the inner
                             tolerance for that problem (default 1e-3) */
   int mg_fused_tail;     /* 1 (default): the multigrid levels that fit in shared memory together (<= 64^2 cells) run as one kernel, one

@@ -48,6 +48,11 @@ struct b200ms_handle {
   DevBuf scan;        // reduction scratch + per-medium results of prepare_window
   DevBuf refs;        // MediumRef array of the batch being built
   DevBuf post;        // interpolation tables / partials / results of the on-device post-processing
+  DevBuf warm;        // sorted Ritz vectors of the previous device batch of this call ([k][B][len]): warm start of the next one
+  int warm_B = 0, warm_k = 0, warm_tsize = 0;
+  size_t warm_len = 0;
+  bool warm_valid = false;
+  long long warm_key[16];
   b200ms_options opt;
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -87,6 +92,8 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->ir_trust = 3e-5;
   o->inner_relax_complex = 50.0;
   o->cluster_gap = 1e-3;
+  o->transfer_tiled = 1;
+  o->warm_start = 0;
   o->mg_fused_tail = 1;
   o->stencil_async = 0;
   o->kappa_cap = 1e4;
@@ -127,6 +134,7 @@ extern "C" int b200ms_destroy(b200ms_handle *h) {
   h->scan.release();
   h->refs.release();
   h->post.release();
+  h->warm.release();
   if (h->io_stream) cudaStreamDestroy(h->io_stream);
   if (h->dl_stream) cudaStreamDestroy(h->dl_stream);
   if (h->flush_buf) cudaFree(h->flush_buf);
@@ -575,7 +583,14 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W,
     eig.nconv.assign(B, k);
     eig.resid.assign(B, 0.0);
   } else {
-    S.init_start_vector(0);
+    // consecutive device batches of one call are neighbouring slices of a sweep: start each problem's Krylov space from the
+    // wanted Ritz vectors of the problem at the same position of the previous batch (same group key, same shapes)
+    long long key[16] = {S.nx, S.ny, k, (long long)sizeof(T), S.tensor_ ? 1 : 0, S.has_mu ? 1 : 0, ps[0]->ax[0].pmc, ps[0]->ax[1].pmc,
+                         ps[0]->direction, ps[0]->masked ? 1 : 0, (long long)S.len, 0, 0, 0, 0, 0};
+    const bool warm = h->opt.warm_start && h->warm_valid && h->warm_B >= B && h->warm_k == k && h->warm_len == S.len &&
+                      h->warm_tsize == (int)sizeof(T) && std::memcmp(key, h->warm_key, sizeof(key)) == 0;
+    if (warm) S.init_start_from(reinterpret_cast<const T *>(h->warm.p), h->warm_B);
+    else S.init_start_vector(0);
     eig = S.krylov_schur(real_arith);
   }
   // eigenvalues of A: lambda = sigma + 1/theta; n = sqrt(-lambda) (principal root, solver.py:884)
@@ -622,6 +637,16 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W,
       auto r = S.eigen_residuals(q, lq);
       for (int b = 0; b < B; ++b) maxres[b] = std::max(maxres[b], r[b]);
     }
+  }
+  if (h->opt.warm_start && !relative) {  // keep the sorted Ritz vectors for the next batch of this call
+    long long key[16] = {S.nx, S.ny, k, (long long)sizeof(T), S.tensor_ ? 1 : 0, S.has_mu ? 1 : 0, ps[0]->ax[0].pmc, ps[0]->ax[1].pmc,
+                         ps[0]->direction, ps[0]->masked ? 1 : 0, (long long)S.len, 0, 0, 0, 0, 0};
+    const size_t bytes = (size_t)k * S.vstride * sizeof(T);
+    h->warm.reserve(bytes + 256);
+    CUDA_CHECK(cudaMemcpyAsync(h->warm.p, S.ritz_ptr(), bytes, cudaMemcpyDeviceToDevice, h->stream));
+    std::memcpy(h->warm_key, key, sizeof(key));
+    h->warm_B = B; h->warm_k = k; h->warm_len = S.len; h->warm_tsize = (int)sizeof(T);
+    h->warm_valid = true;
   }
   CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   CUDA_CHECK(cudaEventSynchronize(h->ev1));
@@ -708,6 +733,7 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
   h->err.clear();
   std::memset(&h->stats, 0, sizeof(h->stats));
   h->stats.nprob = nprob;
+  h->warm_valid = false;  // warm starts never cross calls: a call's results depend on its own inputs only
   const auto call0 = std::chrono::steady_clock::now();
   int first_err = B200MS_OK;
   try {

@@ -752,6 +752,62 @@ __global__ void __launch_bounds__(256) restrict_kernel(TransferArgs a, const T *
   coarse[((size_t)b * 2 + comp) * Nc + (size_t)I * a.nyc + J] = acc;
 }
 
+// Shared-memory tiled restriction (element types of <= 8 bytes): a CTA produces an 8 x 64 tile of coarse values of one
+// component of one problem.  The fine window the tile depends on (<= 28 x 200 values for aggregates of <= 3 cells) is loaded
+// once with coalesced row reads; every coarse value is then a <= 4 x 4 weighted sum out of shared memory.  The per-thread
+// version above reads every fine value up to four times through L1 with stride-2 addresses and was the second largest
+// kernel of a V-cycle (162 us at 64 x 512^2 for 134 MB of input, profiles/r02_launch_shares.txt).
+constexpr int kRtI = 8, kRtJ = 64, kRtRows = 28, kRtCols = 200;
+template <typename T>
+__global__ void __launch_bounds__(256) restrict_tiled_kernel(TransferArgs a, const T *fine, T *coarse) {
+  __shared__ T tile[kRtRows][kRtCols];
+  __shared__ int win[4];
+  const int J0 = blockIdx.x * kRtJ, I0 = blockIdx.y * kRtI;
+  const int comp = blockIdx.z & 1, b = blockIdx.z >> 1;
+  const Transfer1DDev &tx = comp == 0 ? a.xe : a.xn;
+  const Transfer1DDev &ty = comp == 0 ? a.yn : a.ye;
+  const size_t Nf = (size_t)a.nxf * a.nyf, Nc = (size_t)a.nxc * a.nyc;
+  const T *f = fine + ((size_t)b * 2 + comp) * Nf;
+  const int tid = threadIdx.y * 64 + threadIdx.x;
+  const int I1 = min(I0 + kRtI, a.nxc), J1 = min(J0 + kRtJ, a.nyc);
+  if (tid == 0) {  // fine window of the tile (the lists are ascending in the fine index)
+    const int kx0 = tx.r_ptr[I0], kx1 = tx.r_ptr[I1], ky0 = ty.r_ptr[J0], ky1 = ty.r_ptr[J1];
+    win[0] = kx1 > kx0 ? tx.r_idx[kx0] : 0;
+    win[1] = kx1 > kx0 ? tx.r_idx[kx1 - 1] + 1 : 0;
+    win[2] = ky1 > ky0 ? ty.r_idx[ky0] : 0;
+    win[3] = ky1 > ky0 ? ty.r_idx[ky1 - 1] + 1 : 0;
+  }
+  __syncthreads();
+  const int r0 = win[0], nr = win[1] - win[0], c0 = win[2], nc = win[3] - win[2];
+  const bool fits = nr <= kRtRows && nc <= kRtCols;  // uniform over the CTA
+  if (fits) {
+    for (int e = tid; e < nr * nc; e += 256) {
+      const int r = e / nc, c = e % nc;
+      tile[r][c] = ldg(f + (size_t)(r0 + r) * a.nyf + c0 + c);
+    }
+  }
+  __syncthreads();
+  const int J = J0 + threadIdx.x;
+  for (int q = threadIdx.y; q < kRtI; q += 4) {
+    const int I = I0 + q;
+    if (I >= a.nxc || J >= a.nyc) continue;
+    T acc = zero_of<T>();
+    const int kx0 = tx.r_ptr[I], kx1 = tx.r_ptr[I + 1], ky0 = ty.r_ptr[J], ky1 = ty.r_ptr[J + 1];
+    for (int kx = kx0; kx < kx1; ++kx) {
+      const int fr = tx.r_idx[kx];
+      T racc = zero_of<T>();
+      if (fits) {
+        for (int ky = ky0; ky < ky1; ++ky) racc += ty.r_w[ky] * tile[fr - r0][ty.r_idx[ky] - c0];
+      } else {
+        for (int ky = ky0; ky < ky1; ++ky) racc += ty.r_w[ky] * ldg(f + (size_t)fr * a.nyf + ty.r_idx[ky]);
+      }
+      acc += tx.r_w[kx] * racc;
+    }
+    if ((comp == 0 && a.mask_y && J == 0 && a.nyc > 1) || (comp == 1 && a.mask_x && I == 0 && a.nxc > 1)) acc = zero_of<T>();
+    coarse[((size_t)b * 2 + comp) * Nc + (size_t)I * a.nyc + J] = acc;
+  }
+}
+
 // fine[b][comp] += P coarse[b][comp].  All index / weight loads and the four coarse loads are independent and issued
 // before the read-modify-write of the fine value.
 template <typename T>

@@ -736,8 +736,19 @@ class BatchSolver {
     apply(l, MODE_RESID, cur, rin, v.r);
     {
       const TransferArgs &t = v.tr;
-      dim3 blk(64, 4), grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, 2 * B);
-      restrict_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+      dim3 blk(64, 4);
+      if constexpr (sizeof(P) <= 8) {
+        if (opt_.transfer_tiled && t.nyc >= 64) {
+          dim3 grd((t.nyc + kRtJ - 1) / kRtJ, (t.nxc + kRtI - 1) / kRtI, 2 * B);
+          restrict_tiled_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+        } else {
+          dim3 grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, 2 * B);
+          restrict_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+        }
+      } else {
+        dim3 grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, 2 * B);
+        restrict_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+      }
       stats.launches += 2;
     }
     vcycle(l + 1, lv[l + 1].b, nullptr);
@@ -1323,6 +1334,25 @@ class BatchSolver {
     if (!tensor_) mask_E(rhs_, len);  // solver.py:507: vec_init = dnz * vec_init
     dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
     scale_inv_norm(rhs_, Vout_, hbuf_, hstride());
+  }
+
+  // Start vector = normalised sum of the k Ritz vectors of another batch of the same shape (device, [k][Bw][len]): the
+  // Krylov space starts inside the wanted invariant subspace of a neighbouring frequency instead of at a random vector.
+  void init_start_from(const T *warm, int Bw) {
+    std::vector<T> ones((size_t)B * k, from_real<T>(1.0));
+    CUDA_CHECK(cudaMemcpyAsync(qbuf_, ones.data(), ones.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+    if (Bw == B) {
+      dim3 grd(vec_blocks(), B);
+      lincomb_kernel<T><<<grd, 256, (size_t)k * sizeof(T), st_>>>(warm, vstride, len, qbuf_, k, 1, 1, rhs_, vstride);
+    } else {  // a shorter last window: problem b starts from problem b of the previous window (Bw >= B)
+      dim3 grd(vec_blocks(), B);
+      lincomb_kernel<T><<<grd, 256, (size_t)k * sizeof(T), st_>>>(warm, (size_t)Bw * len, len, qbuf_, k, 1, 1, rhs_, vstride);
+    }
+    stats.launches++;
+    if (!tensor_) mask_E(rhs_, len);
+    dots(rhs_, 1, rhs_, hbuf_, hstride(), 0, false);
+    scale_inv_norm(rhs_, Vout_, hbuf_, hstride());
+    CUDA_CHECK(cudaStreamSynchronize(st_));
   }
 
   EigResult krylov_schur(bool real_arith) {

@@ -111,3 +111,20 @@ if "fused" in which:
             except Exception as e:  # noqa: BLE001
                 print(f"## {name} {opts}: FAILED {e}", flush=True)
             h.close()
+if "d" in which:
+    run(64, "default")
+    run(64, "transfer_tiled0", transfer_tiled=0)
+    run(16, "default")
+    run(16, "transfer_tiled0", transfer_tiled=0)
+    # warm start across windows: 128 problems = two windows of 64
+    for ws in (0, 1):
+        wl = W.headline(nf=256)
+        h = _cabi.Handle(**{**REF, "max_batch": 64, "warm_start": ws})
+        probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=f, mode_spec=wl.mode_spec) for f in wl.freqs[:128]]
+        t0 = time.time()
+        out, info = compute_modes_batch(probs, return_info=True, handle=h, want_fields=False)
+        st = h.last_stats()
+        gs = np.load("/root/repo/tests/golden/headline_512_sweep.npz")
+        dn = max(np.abs(out[int(i)][1] - gs["n_ref"][j]).max() for j, i in enumerate(gs["idx"]) if i < 128)
+        print(f"## warm_start={ws}: 128 problems dev_ms {st['device_ms']:.0f} op/solve {st['op_applies']/128:.1f} inner/solve {st['inner_iters']/128:.0f} max|dn| vs golden {dn:.1e} wall {time.time()-t0:.1f}", flush=True)
+        h.close()
