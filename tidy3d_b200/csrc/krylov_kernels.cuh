@@ -106,19 +106,33 @@ __global__ void __launch_bounds__(256) gs_dots_kernel(const U *__restrict__ V, s
   U acc[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) acc[k] = zero_of<U>();
+  if (ng == NG) {  // full group: no predicates, all NG + 1 loads of a step issued back to back
 #pragma unroll(NG >= 8 ? 1 : (NG >= 4 ? 2 : 4))
-  for (size_t p = p0 + threadIdx.x; p < p1; p += 256) {
-    const Pack<U, EPV> wv = ld_pack<U, EPV>(wb + p * EPV);
-    Pack<U, EPV> vv[NG];
+    for (size_t p = p0 + threadIdx.x; p < p1; p += 256) {
+      const Pack<U, EPV> wv = ld_pack<U, EPV>(wb + p * EPV);
+      Pack<U, EPV> vv[NG];
 #pragma unroll
-    for (int k = 0; k < NG; ++k)
-      if (k < ng) vv[k] = ld_pack<U, EPV>(vb + (size_t)k * vstride + p * EPV);
+      for (int k = 0; k < NG; ++k) vv[k] = ld_pack<U, EPV>(vb + (size_t)k * vstride + p * EPV);
 #pragma unroll
-    for (int k = 0; k < NG; ++k)
-      if (k < ng) {
+      for (int k = 0; k < NG; ++k) {
 #pragma unroll
         for (int e = 0; e < EPV; ++e) acc[k] += cj(vv[k].v[e]) * wv.v[e];
       }
+    }
+  } else {
+    for (size_t p = p0 + threadIdx.x; p < p1; p += 256) {
+      const Pack<U, EPV> wv = ld_pack<U, EPV>(wb + p * EPV);
+      Pack<U, EPV> vv[NG];
+#pragma unroll
+      for (int k = 0; k < NG; ++k)
+        if (k < ng) vv[k] = ld_pack<U, EPV>(vb + (size_t)k * vstride + p * EPV);
+#pragma unroll
+      for (int k = 0; k < NG; ++k)
+        if (k < ng) {
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) acc[k] += cj(vv[k].v[e]) * wv.v[e];
+        }
+    }
   }
   block_reduce_store<U, NG>(acc, ng, partial + ((size_t)b * nchunk + chunk) * pstride + poff);
 }
