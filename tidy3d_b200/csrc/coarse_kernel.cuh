@@ -104,8 +104,8 @@ struct FusedOps {
       for (int kx = tx.r_ptr[I]; kx < tx.r_ptr[I + 1]; ++kx) {
         const P *row = f + (size_t)tx.r_idx[kx] * a.nyf;
         P racc = zero_of<P>();
-        for (int ky = ty.r_ptr[J]; ky < ty.r_ptr[J + 1]; ++ky) racc += ty.r_w[ky] * row[ty.r_idx[ky]];
-        acc += tx.r_w[kx] * racc;
+        for (int ky = ty.r_ptr[J]; ky < ty.r_ptr[J + 1]; ++ky) racc += (typename RealOf<P>::type)ty.r_w[ky] * row[ty.r_idx[ky]];
+        acc += (typename RealOf<P>::type)tx.r_w[kx] * racc;
       }
       if ((comp == 0 && a.mask_y && J == 0 && a.nyc > 1) || (comp == 1 && a.mask_x && I == 0 && a.nxc > 1)) acc = zero_of<P>();
       coarse[e] = acc;
@@ -120,7 +120,8 @@ struct FusedOps {
       const Transfer1DDev &ty = comp == 0 ? a.yn : a.ye;
       const P *c = coarse + (size_t)comp * Nc;
       const int I0 = tx.p_i0[i], I1 = tx.p_i1[i], J0 = ty.p_i0[j], J1 = ty.p_i1[j];
-      const double wx0 = tx.p_w0[i], wx1 = tx.p_w1[i], wy0 = ty.p_w0[j], wy1 = ty.p_w1[j];
+      using R = typename RealOf<P>::type;
+      const R wx0 = (R)tx.p_w0[i], wx1 = (R)tx.p_w1[i], wy0 = (R)ty.p_w0[j], wy1 = (R)ty.p_w1[j];
       fine[e] = fine[e] + (wx0 * (wy0 * c[(size_t)I0 * a.nyc + J0] + wy1 * c[(size_t)I0 * a.nyc + J1]) +
                            wx1 * (wy0 * c[(size_t)I1 * a.nyc + J0] + wy1 * c[(size_t)I1 * a.nyc + J1]));
     }

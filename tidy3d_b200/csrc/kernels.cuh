@@ -67,6 +67,12 @@ HD void convert(cplx s, cplxf &d) { d = mkf((float)s.re, (float)s.im); }
 HD void convert(cplxf s, cplx &d) { d = mk(s.re, s.im); }
 HD void convert(cplxf s, cplxf &d) { d = s; }
 
+// real scalar type matching a vector element type (transfer weights are converted to it once per thread: with double
+// weights the fp32 transfer kernels were instruction-bound on F2F conversions and DFMAs, profiles/r02_restrict_ncu.txt)
+template <typename T> struct RealOf { using type = double; };
+template <> struct RealOf<float> { using type = float; };
+template <> struct RealOf<cplxf> { using type = float; };
+
 template <typename T> HD T zero_of();
 template <> HD float zero_of<float>() { return 0.0f; }
 template <> HD cplxf zero_of<cplxf>() { return mkf(0.0f, 0.0f); }
@@ -717,21 +723,23 @@ __global__ void __launch_bounds__(256) restrict_kernel(TransferArgs a, const T *
   T acc = zero_of<T>();
   const int kx0 = __ldg(tx.r_ptr + I), kx1 = __ldg(tx.r_ptr + I + 1), ky0 = __ldg(ty.r_ptr + J), ky1 = __ldg(ty.r_ptr + J + 1);
   if (kx1 - kx0 <= 4 && ky1 - ky0 <= 4) {
-    int ix[4], iy[4];
-    double wx[4], wy[4];
+    using R = typename RealOf<T>::type;
+    int iy[4];
+    const T *rowp[4];
+    R wx[4], wy[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const bool vx = kx0 + q < kx1, vy = ky0 + q < ky1;
-      ix[q] = vx ? __ldg(tx.r_idx + kx0 + q) : 0;
-      wx[q] = vx ? __ldg(tx.r_w + kx0 + q) : 0.0;
+      rowp[q] = f + (size_t)(vx ? __ldg(tx.r_idx + kx0 + q) : 0) * a.nyf;
+      wx[q] = vx ? (R)__ldg(tx.r_w + kx0 + q) : (R)0;
       iy[q] = vy ? __ldg(ty.r_idx + ky0 + q) : 0;
-      wy[q] = vy ? __ldg(ty.r_w + ky0 + q) : 0.0;
+      wy[q] = vy ? (R)__ldg(ty.r_w + ky0 + q) : (R)0;
     }
     T v[4][4];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[p][q] = (kx0 + p < kx1 && ky0 + q < ky1) ? ldg(f + (size_t)ix[p] * a.nyf + iy[q]) : zero_of<T>();
+      for (int q = 0; q < 4; ++q) v[p][q] = (kx0 + p < kx1 && ky0 + q < ky1) ? ldg(rowp[p] + iy[q]) : zero_of<T>();
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       T racc = zero_of<T>();
@@ -822,7 +830,8 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(TransferArgs a, const 
   const T *c = coarse + ((size_t)b * 2 + comp) * Nc;
   T *f = fine + ((size_t)b * 2 + comp) * Nf + (size_t)i * a.nyf + j;
   const int I0 = __ldg(tx.p_i0 + i), I1 = __ldg(tx.p_i1 + i), J0 = __ldg(ty.p_i0 + j), J1 = __ldg(ty.p_i1 + j);
-  const double wx0 = __ldg(tx.p_w0 + i), wx1 = __ldg(tx.p_w1 + i), wy0 = __ldg(ty.p_w0 + j), wy1 = __ldg(ty.p_w1 + j);
+  using R = typename RealOf<T>::type;
+  const R wx0 = (R)__ldg(tx.p_w0 + i), wx1 = (R)__ldg(tx.p_w1 + i), wy0 = (R)__ldg(ty.p_w0 + j), wy1 = (R)__ldg(ty.p_w1 + j);
   const T fv = *f;
   const T c00 = ldg(c + (size_t)I0 * a.nyc + J0), c01 = ldg(c + (size_t)I0 * a.nyc + J1);
   const T c10 = ldg(c + (size_t)I1 * a.nyc + J0), c11 = ldg(c + (size_t)I1 * a.nyc + J1);
