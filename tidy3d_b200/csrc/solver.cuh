@@ -754,8 +754,13 @@ class BatchSolver {
     vcycle(l + 1, lv[l + 1].b, nullptr);
     {
       const TransferArgs &t = v.tr;
-      dim3 blk(64, 4), grd((t.nyf + 63) / 64, (t.nxf + 3) / 4, 2 * B);
-      prolong_add_kernel<P><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
+      if (t.nyf >= 256 && opt_.transfer_tiled != 2) {  // four fine columns per thread
+        dim3 blk(64, 4), grd((t.nyf + 255) / 256, (t.nxf + 3) / 4, 2 * B);
+        prolong_add4_kernel<P><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
+      } else {
+        dim3 blk(64, 4), grd((t.nyf + 63) / 64, (t.nxf + 3) / 4, 2 * B);
+        prolong_add_kernel<P><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
+      }
     }
     for (int s = 0; s < nu; ++s) {
       P *dst = (s == nu - 1 && out) ? out : oth;
