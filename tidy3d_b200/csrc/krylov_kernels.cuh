@@ -83,13 +83,16 @@ __device__ __forceinline__ void block_reduce_store(U (&acc)[NG], int ng, U *dst)
   __syncthreads();
 }
 
-// sum over chunks of partial[b][chunk][off + k], k < n  -> sh[k]  (double accumulation)
+// sum over chunks of partial[b][chunk][off + k], k < n  -> sh[k]  (double accumulation).  One warp per coefficient: the
+// chunk loop is a strided warp reduction instead of a serial chain of up to 64 dependent loads in every CTA's prologue.
 template <typename U>
 __device__ __forceinline__ void reduce_partials(const U *partial, int b, int nchunk, int pstride, int off, int n, U *sh) {
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int k = warp; k < n; k += nwarps) {
     cplx s = mk(0.0, 0.0);
-    for (int c = 0; c < nchunk; ++c) s += to_cplx_any(partial[((size_t)b * nchunk + c) * pstride + off + k]);
-    sh[k] = from_cplx_any<U>(s);
+    for (int c = lane; c < nchunk; c += 32) s += to_cplx_any(partial[((size_t)b * nchunk + c) * pstride + off + k]);
+    s = warp_sum(s);
+    if (lane == 0) sh[k] = from_cplx_any<U>(s);
   }
 }
 

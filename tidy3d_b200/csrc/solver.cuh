@@ -1009,6 +1009,10 @@ class BatchSolver {
     const size_t packs = std::max<size_t>(1, ln / 2);
     return (int)std::max<size_t>(1, std::min<size_t>({(size_t)kDotChunks, packs / 1024 + 1, (size_t)(1184 + B - 1) / B}));
   }
+  // CTAs per problem for the streaming kernels with a reduction prologue (scale, ir_begin, ir_update): ~8 per SM in total
+  int stream_blocks(size_t ln) const {
+    return (int)std::max<size_t>(1, std::min<size_t>({(size_t)256, ln / 2048 + 1, (size_t)(148 * 8 + B - 1) / B}));
+  }
   template <typename U>
   U *gpart(int region) { return reinterpret_cast<U *>(gpart_) + (size_t)region * B * kDotChunks * pstride(); }
 
@@ -1045,7 +1049,7 @@ class BatchSolver {
   }
   template <typename U>
   void k_scale(const U *w, U *y, U *y2, size_t ln, const U *pin, int nch, U *hexp, size_t hstride, int hoff) {
-    dim3 grd((unsigned)std::min<size_t>((ln / 4 + 255) / 256 + 1, 2048), B);
+    dim3 grd((unsigned)stream_blocks(ln), B);  // few fat CTAs: every CTA pays the prologue reduction once
     stats.launches++;
     if (vec_ok<U>(ln)) gs_scale_kernel<U, PackTraits<U>::EPV><<<grd, 256, 0, st_>>>(w, y, y2, ln, pin, nch, pstride(), 0, hexp, hstride, hoff);
     else gs_scale_kernel<U, 1><<<grd, 256, 0, st_>>>(w, y, y2, ln, pin, nch, pstride(), 0, hexp, hstride, hoff);
@@ -1212,7 +1216,7 @@ class BatchSolver {
     const int nch = gs_chunks(len);
     int total = 0, cyc = 0;
     bool verified = true;
-    const dim3 egrd((unsigned)std::min<size_t>((len / 4 + 255) / 256 + 1, 2048), B);
+    const dim3 egrd((unsigned)stream_blocks(len), B);
     while (true) {
       // ||r||^2 of the current residual (partials; reduced inside ir_begin)
       k_dots<T>(rcur, vstride, len, rcur, 1, gpart<T>(0), 0, nch);
@@ -1374,7 +1378,7 @@ class BatchSolver {
     // (tol_j ~ eps / ||r_{j-1}||, Bouras & Fraysse / Simoncini); capped and with a safety factor
     std::vector<double> tolv(B, opt_.inner_tol);
     int nkeep = 0;
-    const int keep_target = std::min(m - 1, k + std::max(1, (m - k) / 2));
+    const int keep_target = opt_.ks_keep > 0 ? std::min(m - 1, std::max(k + 1, opt_.ks_keep)) : std::min(m - 1, k + std::max(1, (m - k) / 2));
     for (int rst = 0; rst <= opt_.max_restarts; ++rst) {
       for (int j = nkeep; j < m; ++j) {
         T *vj = Vout_ + (size_t)j * vstride, *w = Vout_ + (size_t)(j + 1) * vstride;

@@ -128,3 +128,10 @@ if "d" in which:
         dn = max(np.abs(out[int(i)][1] - gs["n_ref"][j]).max() for j, i in enumerate(gs["idx"]) if i < 128)
         print(f"## warm_start={ws}: 128 problems dev_ms {st['device_ms']:.0f} op/solve {st['op_applies']/128:.1f} inner/solve {st['inner_iters']/128:.0f} max|dn| vs golden {dn:.1e} wall {time.time()-t0:.1f}", flush=True)
         h.close()
+if "e" in which:
+    run(64, "default")
+    run(16, "default")
+    for kk in (8, 10, 14, 16):
+        run(16, "ks_keep", ks_keep=kk)
+    run(16, "inner_tol 3e-8", inner_tol=3e-8)
+    run(16, "ncv 16", ncv=16)
