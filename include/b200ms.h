@@ -154,6 +154,7 @@ typedef struct {
   double ir_floor;       /* smallest residual reduction asked of one fp32 cycle (default 1e-4) */
   double ir_trust;       /* solves whose tolerance is >= this accept the fp32 residual estimate without an fp64 check (3e-5) */
   double inner_relax_complex; /* complex-arithmetic problems: loosest inner tolerance = this x inner_tol (default 50) */
+  int mg_fuse_first;     /* 1 (default): the first two pre-smoothing sweeps (from the zero guess) run as one kernel pass */
   int ks_keep;           /* Krylov-Schur: Ritz vectors kept at a restart; 0 (default) = k + (ncv - k) / 2 */
   int transfer_tiled;    /* 1: shared-memory tiled restriction kernel on levels with >= 64 coarse columns (measured: no faster); 0 (default): per-thread gathers */
   int warm_start;        /* 1: within one call, each device batch starts its Krylov spaces from the wanted Ritz vectors of the previous

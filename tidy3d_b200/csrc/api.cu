@@ -92,6 +92,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->ir_trust = 3e-5;
   o->inner_relax_complex = 50.0;
   o->cluster_gap = 1e-3;
+  o->mg_fuse_first = 1;
   o->ks_keep = 0;
   o->transfer_tiled = 0;
   o->warm_start = 0;

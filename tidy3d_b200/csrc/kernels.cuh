@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(256) convert_kernel(size_t total, const S *src
 // ------------------------------------------------------------------------------------------------
 // fused curl-curl stencil
 // ------------------------------------------------------------------------------------------------
-enum { MODE_APPLY = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_JACOBI_D = 3 };  // _D: stored omega/diag
+// _D: stored omega/diag.  _D0: two sweeps from a zero guess in one pass, x' = x0 + dinv (rhs - (A-sigma) x0) with x0 = dinv rhs formed
+// while the rows are loaded (replaces the separate dinv*rhs product kernel and the x read of the first sweep)
+enum { MODE_APPLY = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_JACOBI_D = 3, MODE_JACOBI_D0 = 4 };
 
 template <typename T, typename C>
 struct StencilArgs {
@@ -393,6 +395,8 @@ __global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T
   const T sg = ldg(a.sigma + b);
   T *y1 = a.y + (size_t)b * 2 * N, *y2 = y1 + N;
   const T *r1 = (MODE != MODE_APPLY) ? a.rhs + (size_t)b * 2 * N : nullptr;
+  const T *dv0 = (MODE == MODE_JACOBI_D || MODE == MODE_JACOBI_D0) ? a.dinv + (size_t)b * 2 * N : nullptr;
+  constexpr bool DSTORED = (MODE == MODE_JACOBI_D || MODE == MODE_JACOBI_D0);
 
   // prefetch registers (raw row), rows k+2 / k+1 / k
   T pv1 = zT, pv2 = zT;
@@ -408,7 +412,12 @@ __global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T
     if (HAS_MU) { pim = C(); pmx = C(); pmy = C(); }
     if (colv && gi >= 0 && gi < nx && gi >= i0 - 1 && gi <= i0 + TXR) {
       const size_t g = (size_t)gi * ny + gj;
-      pv1 = ldg(x1 + g); pv2 = ldg(x2 + g);
+      if (MODE == MODE_JACOBI_D0) {  // x0 = dinv * rhs formed on the fly
+        pv1 = ldg(dv0 + g) * ldg(r1 + g);
+        pv2 = ldg(dv0 + N + g) * ldg(r1 + N + g);
+      } else {
+        pv1 = ldg(x1 + g); pv2 = ldg(x2 + g);
+      }
       pex = ldg(exx + g); pey = ldg(eyy + g); pie = ldg(iez + g);
       if (HAS_MU) { pim = ldg(imz + g); pmx = ldg(mxx + g); pmy = ldg(myy + g); }
     }
@@ -430,10 +439,7 @@ __global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T
       if (outc && k + 1 >= i0 && k + 1 < iend) {
         const size_t g = (size_t)(k + 1) * ny + gj;
         nr1 = ldg(r1 + g); nr2 = ldg(r1 + N + g);
-        if (MODE == MODE_JACOBI_D) {
-          const T *dv = a.dinv + (size_t)b * 2 * N;
-          nd1 = ldg(dv + g); nd2 = ldg(dv + N + g);
-        }
+        if (DSTORED) { nd1 = ldg(dv0 + g); nd2 = ldg(dv0 + N + g); }
       }
     }
     // step 1
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(kMarchCols) stencil_march_kernel(StencilArgs<T
         y1[g] = o1; y2[g] = o2;
       } else if (MODE == MODE_RESID) {
         y1[g] = cr1 - o1; y2[g] = cr2 - o2;
-      } else if (MODE == MODE_JACOBI_D) {
+      } else if (DSTORED) {
         y1[g] = v10 + cd1 * (cr1 - o1); y2[g] = v20 + cd2 * (cr2 - o2);
       } else {
         const T xbm_n = sX[3][xr + 1], xf1_p = sX[1][xr - 1 >= 0 ? xr - 1 : 0];

@@ -469,12 +469,17 @@ class BatchSolver {
     dim3 blk(kMarchCols), grd((v.ny + kMarchOut - 1) / kMarchOut, (v.nx + TXR - 1) / TXR, B);
     if constexpr (sizeof(TT) <= 8 && sizeof(CC) <= 8) {
       // cp.async (LDGSTS) variant: the multigrid hot path -- stored-diagonal sweep, residual, apply -- without mu fields
-      if (opt_.stencil_async && !has_mu && (mode != MODE_JACOBI || have_dinv)) {
+      if (opt_.stencil_async && !has_mu && mode != MODE_JACOBI_D0 && (mode != MODE_JACOBI || have_dinv)) {
         if (mode == MODE_JACOBI) stencil_march_async_kernel<TT, CC, MODE_JACOBI_D, TXR><<<grd, blk, 0, st_>>>(a);
         else if (mode == MODE_RESID) stencil_march_async_kernel<TT, CC, MODE_RESID, TXR><<<grd, blk, 0, st_>>>(a);
         else stencil_march_async_kernel<TT, CC, MODE_APPLY, TXR><<<grd, blk, 0, st_>>>(a);
         return;
       }
+    }
+    if (mode == MODE_JACOBI_D0) {  // two sweeps from zero in one pass (needs the stored diagonal)
+      if (has_mu) stencil_march_kernel<TT, CC, MODE_JACOBI_D0, true, TXR><<<grd, blk, 0, st_>>>(a);
+      else stencil_march_kernel<TT, CC, MODE_JACOBI_D0, false, TXR><<<grd, blk, 0, st_>>>(a);
+      return;
     }
     if (mode == MODE_JACOBI && have_dinv) {  // stored-diagonal sweep: fewer registers and instructions than recomputing it
       if (has_mu) stencil_march_kernel<TT, CC, MODE_JACOBI_D, true, TXR><<<grd, blk, 0, st_>>>(a);
@@ -728,10 +733,18 @@ class BatchSolver {
       if (!out) { v.x = cur; v.tmp = oth; }
       return;
     }
-    jacobi0(l, rin, cur);
-    for (int s = 1; s < nu; ++s) {
-      sweep(oth);
-      std::swap(cur, oth);
+    if (nu >= 2 && dinv_ready_ && opt_.mg_fuse_first && opt_.stencil_variant != 1 && v.nx >= 32 && v.ny >= 2) {
+      apply(l, MODE_JACOBI_D0, cur, rin, cur);  // sweeps 1 and 2 from the zero guess in one pass (x argument unused)
+      for (int s = 2; s < nu; ++s) {
+        sweep(oth);
+        std::swap(cur, oth);
+      }
+    } else {
+      jacobi0(l, rin, cur);
+      for (int s = 1; s < nu; ++s) {
+        sweep(oth);
+        std::swap(cur, oth);
+      }
     }
     apply(l, MODE_RESID, cur, rin, v.r);
     {

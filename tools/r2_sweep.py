@@ -135,3 +135,18 @@ if "e" in which:
         run(16, "ks_keep", ks_keep=kk)
     run(16, "inner_tol 3e-8", inner_tol=3e-8)
     run(16, "ncv 16", ncv=16)
+if "f" in which:
+    run(64, "default")
+    run(64, "mg_fuse_first0", mg_fuse_first=0)
+    run(16, "default")
+    run(16, "mg_fuse_first0", mg_fuse_first=0)
+    from tests.golden.cases import CASES
+    for name in ("c3_128", "c4_128", "nonuniform_56", "c3_512"):
+        fac, kw, _ = CASES[name]
+        wl = fac()
+        gg = np.load(f"/root/repo/tests/golden/{name}.npz")
+        for opts in (dict(mg_fuse_first=1), dict(mg_fuse_first=0)):
+            h = _cabi.Handle(**{**REF, **opts})
+            out, info = compute_modes_batch([dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], return_info=True, handle=h)
+            print(f"## {name} {opts}: |dn| {np.abs(out[0][1] - gg['n_tight']).max():.1e} inner {info[0]['inner_iters']} dev_ms {h.last_stats()['device_ms']:.1f}", flush=True)
+            h.close()
