@@ -126,7 +126,7 @@ typedef struct {
                             the "tight" setting used by the parity tests is 1e-9 */
   double inner_tol;      /* relative residual of the shift-invert solves before relaxation (default 1e-8; tight 1e-10) */
   int ncv;               /* Krylov subspace size, 0 = max(2k+1, 20) like scipy (solver.py:744) */
-  int max_restarts;      /* default 100 */
+  int max_restarts;      /* default 500 */
   int gmres_restart;     /* default 40 */
   int gmres_maxit;       /* default 400 */
   int mg_nu;             /* Jacobi pre/post sweeps (default 2) */

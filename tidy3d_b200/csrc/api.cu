@@ -67,7 +67,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->eig_tol = kFpEps;   // the reference's ARPACK tolerance (TOL_EIGS = fp_eps, solver.py:20)
   o->inner_tol = 1e-8;
   o->ncv = 0;
-  o->max_restarts = 100;
+  o->max_restarts = 500;  // scipy: maxiter = 10 n restarts; the PML-cluster case needs ~80-110
   o->gmres_restart = 40;
   o->gmres_maxit = 400;
   o->mg_nu = 2;
