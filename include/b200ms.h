@@ -102,6 +102,9 @@ typedef struct {
   double *n_complex;     /* caller-allocated num_modes complex128 (re,im): n_eff + i k_eff */
   double *flux;          /* NULL, or caller-allocated num_modes doubles: flux of every mode BEFORE normalisation (colocated
                             tangential fields, trapezoid weights; monitor_data.py:523-539, 425-467, 582-618) */
+  double *te_fraction;   /* NULL, or caller-allocated num_modes doubles: TE polarisation fraction int|E1|^2 / int(|E1|^2+|E2|^2) of the
+                            colocated field (ModeData.pol_fraction, monitor_data.py:1625-1652), the input of the filter_pol re-ordering
+                            (mode_solver.py:523-549) */
   double *overlap_prev;  /* NULL, or caller-allocated num_modes^2 complex128 (re,im), row-major [m_prev][m]: modal overlap
                             dot(mode m_prev of the PREVIOUS problem of this call, mode m of this one) (monitor_data.py:640-697,
                             after gauge/normalisation), the input of overlap_sort (monitor_data.py:1295-1375).  Zeros when

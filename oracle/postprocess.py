@@ -106,6 +106,15 @@ def flux(fields, coords, symmetry=(0, 0)):
     return mult * np.einsum("xym,xy->m", s, diff_area(coords, symmetry))
 
 
+def pol_fraction(fields, coords, symmetry=(0, 0)):
+    """monitor_data.py:1625-1652: TE fraction = int |E1|^2 dS / int (|E1|^2 + |E2|^2) dS of the colocated field."""
+    c = colocate(fields, coords, symmetry)
+    da = diff_area(coords, symmetry)
+    te = np.einsum("xym,xy->m", np.abs(c["Ex"]) ** 2, da)
+    tm = np.einsum("xym,xy->m", np.abs(c["Ey"]) ** 2, da)
+    return te / (te + tm)
+
+
 def normalize(fields, coords, symmetry=(0, 0)):
     """mode_solver.py:517-521: all six components divided by sqrt(|flux|)."""
     fl = flux(fields, coords, symmetry)

@@ -32,6 +32,9 @@ def test_gauge_flux_normalisation_and_overlaps_match_the_restatement():
         g, _ = OP.gauge(f_raw)
         fn, fl = OP.normalize(g, wl.coords)
         assert np.abs(info[i]["flux"] - fl).max() < 1e-10 * np.abs(fl).max()
+        te = OP.pol_fraction(f_raw, wl.coords)
+        assert np.abs(info[i]["te_fraction"] - te).max() < 1e-10
+        assert list(PP.filter_polarization(info[i]["te_fraction"], "tm")) == list(np.concatenate((np.where(te <= 0.5)[0], np.where(te > 0.5)[0])))
         assert np.abs(f_post - fn).max() < 1e-9 * np.abs(fn).max()
         for m in range(fn.shape[-1]):  # gauge: the largest in-plane E entry is real positive (mode_solver.py:806-810)
             e = f_post[0, :2, ..., m]

@@ -73,3 +73,10 @@ def test_product_overlap_sort_matches_restatement():
     assert list(pairs) == [1, 0, 2] and np.allclose(vals, [0.9, 0.8, 0.7])
     n_sorted, f_sorted = PP.apply_sorting([np.arange(m) + 10 * i for i in range(nf)], [None] * nf, s1, p1)
     assert all(np.array_equal(n_sorted[i], (np.arange(m) + 10 * i)[s1[i]]) for i in range(nf))
+
+
+def test_filter_polarization_order():
+    """mode_solver.py:523-549: requested polarisation first, NaN fractions last."""
+    te = np.array([0.9, 0.2, np.nan, 0.5, 0.7])
+    assert list(PP.filter_polarization(te, "te")) == [0, 3, 4, 1, 2]
+    assert list(PP.filter_polarization(te, "tm")) == [1, 3, 0, 4, 2]

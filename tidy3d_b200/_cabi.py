@@ -40,7 +40,7 @@ class Problem(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [
-        ("fields", _dp), ("n_complex", _dp), ("flux", _dp), ("overlap_prev", _dp), ("eps_spec", C.c_int), ("status", C.c_int), ("converged", C.c_int),
+        ("fields", _dp), ("n_complex", _dp), ("flux", _dp), ("te_fraction", _dp), ("overlap_prev", _dp), ("eps_spec", C.c_int), ("status", C.c_int), ("converged", C.c_int),
         ("outer_iters", C.c_int), ("op_applies", C.c_int), ("inner_iters", C.c_int), ("stencil_applies", C.c_int),
         ("is_complex", C.c_int), ("solve_ms", C.c_double), ("total_ms", C.c_double), ("max_residual", C.c_double),
     ]  # fmt: skip
@@ -299,15 +299,17 @@ class Handle:
         probs = (Problem * n)(*[p.struct for p in packed])
         results = (Result * n)()
         fields, ncs = [], []
-        self.last_flux, self.last_overlaps = [], []
+        self.last_flux, self.last_te, self.last_overlaps = [], [], []
         for i, p in enumerate(packed):
             nc = np.zeros(p.num_modes, dtype=np.complex128)
             ncs.append(nc)
             results[i].n_complex = _ptr(nc.view(np.float64))
             if want_flux:
-                fl = np.zeros(p.num_modes)
+                fl, te = np.zeros(p.num_modes), np.zeros(p.num_modes)
                 self.last_flux.append(fl)
+                self.last_te.append(te)
                 results[i].flux = _ptr(fl)
+                results[i].te_fraction = _ptr(te)
             if want_overlaps:
                 ov = np.zeros((p.num_modes, p.num_modes), dtype=np.complex128)
                 self.last_overlaps.append(ov)

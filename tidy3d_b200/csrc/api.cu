@@ -389,9 +389,9 @@ void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, 
   const int nx = p0.nx, ny = p0.ny, M = p0.num_modes;
   bool any = false;
   for (int b = 0; b < B; ++b)
-    if (prob[W.i0 + ids[b]].post || res[W.i0 + ids[b]].flux) any = true;
+    if (prob[W.i0 + ids[b]].post || res[W.i0 + ids[b]].flux || res[W.i0 + ids[b]].te_fraction) any = true;
   if (!any) return;
-  if (M > kPostMaxModes) throw std::runtime_error("post-processing supports at most 64 modes");
+  if (M > kPostMaxModes) throw std::invalid_argument("post-processing supports at most 64 modes");
   // pack the tables of all problems into one upload
   std::vector<HostAxisTables> tx(B), ty(B);
   size_t ints = 0, dbls = 0;
@@ -404,8 +404,8 @@ void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, 
   }
   const size_t off_d = align256(ints * sizeof(int)), off_pp = off_d + align256(dbls * sizeof(double));
   const size_t off_part = off_pp + align256((size_t)B * sizeof(PostProblem));
-  const size_t off_flux = off_part + align256((size_t)B * kPostChunks * M * 5 * sizeof(double));
-  const size_t off_scal = off_flux + align256((size_t)B * M * sizeof(double));
+  const size_t off_flux = off_part + align256((size_t)B * kPostChunks * M * kPostSlots * sizeof(double));
+  const size_t off_scal = off_flux + align256((size_t)2 * B * M * sizeof(double));
   const size_t total = off_scal + align256((size_t)B * M * sizeof(cplx));
   h->post.reserve(total + 4096);
   std::vector<int> hi(ints);
@@ -444,19 +444,23 @@ void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, 
   dim3 g1(nch, B);
   if (single) post_scan_kernel<cplxf><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
   else post_scan_kernel<cplx><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
-  post_final_kernel<<<B, std::max(32, ((M + 31) / 32) * 32), 0, st>>>(dpp, dpart, nch, M, dflux, dscal);
+  post_final_kernel<<<B, std::max(32, ((M + 31) / 32) * 32), 0, st>>>(dpp, dpart, nch, M, dflux, dscal, dflux + (size_t)B * M);
   if (do_gauge || do_norm) {
     dim3 g2((unsigned)std::min<size_t>(((size_t)6 * nx * ny * M + 255) / 256, 2048), B);
     if (single) post_apply_kernel<cplxf><<<g2, 256, 0, st>>>(dpp, (size_t)6 * nx * ny, M, dscal);
     else post_apply_kernel<cplx><<<g2, 256, 0, st>>>(dpp, (size_t)6 * nx * ny, M, dscal);
   }
-  std::vector<double> hflux((size_t)B * M);
+  std::vector<double> hflux((size_t)2 * B * M);
   CUDA_CHECK(cudaMemcpyAsync(hflux.data(), dflux, hflux.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   CUDA_CHECK(cudaGetLastError());
   h->stats.launches += 3;
   for (int b = 0; b < B; ++b)
+  {
     if (res[W.i0 + ids[b]].flux) std::copy(hflux.begin() + (size_t)b * M, hflux.begin() + (size_t)(b + 1) * M, res[W.i0 + ids[b]].flux);
+    if (res[W.i0 + ids[b]].te_fraction)
+      std::copy(hflux.begin() + (size_t)(B + b) * M, hflux.begin() + (size_t)(B + b + 1) * M, res[W.i0 + ids[b]].te_fraction);
+  }
 }
 
 // Modal overlaps between consecutive problems of the call (result.overlap_prev) for the problems [i0, i1); dev_fields[i] is
@@ -626,7 +630,7 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W,
   bool want_fields = false;
   for (int b = 0; b < B; ++b) {
     const b200ms_result &rb = res[W.i0 + ids[b]];
-    if (rb.fields || rb.flux || rb.overlap_prev || prob[W.i0 + ids[b]].post) want_fields = true;  // post-processing needs them in HBM
+    if (rb.fields || rb.flux || rb.te_fraction || rb.overlap_prev || prob[W.i0 + ids[b]].post) want_fields = true;  // post-processing needs them in HBM
   }
   S.epilogue(nsorted, perm, ps, nullptr, want_fields);
   // true residuals on the sorted Ritz vectors (they sit in the FGMRES Z scratch after the permutation)
@@ -836,7 +840,10 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
       if (up_f.valid()) h->stats.setup_ms += up_f.get();
     }
     if (dl_f.valid()) h->stats.download_ms += dl_f.get();
-  } catch (const std::exception &e) {
+  } catch (const std::invalid_argument &e) {
+    h->err = e.what();
+    return B200MS_ERR_ARG;
+  } catch (const std::exception &e) {  // CUDA runtime failures, device memory exhaustion
     h->err = e.what();
     return B200MS_ERR_CUDA;
   }

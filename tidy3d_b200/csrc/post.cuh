@@ -50,16 +50,18 @@ __device__ __forceinline__ cplx colocated(const F *f, int comp, bool xc, bool yc
   return wx0 * (wy0 * v00 + wy1 * v01) + wx1 * (wy0 * v10 + wy1 * v11);
 }
 
-// partial[b][chunk][m] = {flux partial, max |E_inplane|^2, its raveled index (as double), re, im of that entry}
+// partial[b][chunk][m] = {flux partial, max |E_inplane|^2, its raveled index (as double), re, im of that entry,
+//                        int |E1|^2 dS, int |E2|^2 dS of the colocated field (pol_fraction, monitor_data.py:1625-1652)}
+constexpr int kPostSlots = 7;
 template <typename F>
 __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, int nx, int ny, int M, double *partial) {
   const PostProblem P = pp[blockIdx.y];
   const F *f = reinterpret_cast<const F *>(P.fields);
   const int chunk = blockIdx.x, nchunk = gridDim.x;
   const size_t N = (size_t)nx * ny;
-  __shared__ double red[8][5];
+  __shared__ double red[8][kPostSlots];
   for (int m = 0; m < M; ++m) {
-    double fl = 0.0, best = -1.0, bidx = 0.0, bre = 0.0, bim = 0.0;
+    double fl = 0.0, best = -1.0, bidx = 0.0, bre = 0.0, bim = 0.0, te = 0.0, tm = 0.0;
     const size_t npts = (size_t)P.ax.P * P.ay.P;
     for (size_t t = (size_t)chunk * 256 + threadIdx.x; t < npts; t += (size_t)nchunk * 256) {
       const int p = (int)(t / P.ay.P), q = (int)(t % P.ay.P);
@@ -68,7 +70,10 @@ __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, i
       const cplx hx = colocated(f, 3, false, true, P.ax, P.ay, nx, ny, M, p, q, m);
       const cplx hy = colocated(f, 4, true, false, P.ax, P.ay, nx, ny, M, p, q, m);
       const cplx s = ex * cj(hy) - ey * cj(hx);
-      fl += 0.5 * s.re * P.ax.area[p] * P.ay.area[q];
+      const double da = P.ax.area[p] * P.ay.area[q];
+      fl += 0.5 * s.re * da;
+      te += abs2(ex) * da;
+      tm += abs2(ey) * da;
     }
     for (size_t c = (size_t)chunk * 256 + threadIdx.x; c < 2 * N; c += (size_t)nchunk * 256) {  // E[:2] raveled: comp, ix, iy
       const cplx v = ldf(f + c * M + m);
@@ -78,40 +83,47 @@ __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, i
     // block reduction: flux by sum; gauge entry by (larger |.|^2, then smaller index)
     for (int o = 16; o > 0; o >>= 1) {
       fl += __shfl_down_sync(0xffffffffu, fl, o);
+      te += __shfl_down_sync(0xffffffffu, te, o);
+      tm += __shfl_down_sync(0xffffffffu, tm, o);
       const double ob = __shfl_down_sync(0xffffffffu, best, o), oi = __shfl_down_sync(0xffffffffu, bidx, o);
       const double orr = __shfl_down_sync(0xffffffffu, bre, o), oim = __shfl_down_sync(0xffffffffu, bim, o);
       if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bre = orr; bim = oim; }
     }
     if ((threadIdx.x & 31) == 0) {
       double *r = red[threadIdx.x >> 5];
-      r[0] = fl; r[1] = best; r[2] = bidx; r[3] = bre; r[4] = bim;
+      r[0] = fl; r[1] = best; r[2] = bidx; r[3] = bre; r[4] = bim; r[5] = te; r[6] = tm;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int w = 1; w < 8; ++w) {
         fl += red[w][0];
+        te += red[w][5];
+        tm += red[w][6];
         if (red[w][1] > best || (red[w][1] == best && red[w][2] < bidx)) { best = red[w][1]; bidx = red[w][2]; bre = red[w][3]; bim = red[w][4]; }
       }
-      double *o = partial + (((size_t)blockIdx.y * nchunk + chunk) * M + m) * 5;
-      o[0] = fl; o[1] = best; o[2] = bidx; o[3] = bre; o[4] = bim;
+      double *o = partial + (((size_t)blockIdx.y * nchunk + chunk) * M + m) * kPostSlots;
+      o[0] = fl; o[1] = best; o[2] = bidx; o[3] = bre; o[4] = bim; o[5] = te; o[6] = tm;
     }
     __syncthreads();
   }
 }
 
 // flux[b][m], scal[b][m] = exp(-i phi) / sqrt(|flux|)  (either factor optional)
-__global__ void post_final_kernel(const PostProblem *pp, const double *partial, int nchunk, int M, double *flux, cplx *scal) {
+__global__ void post_final_kernel(const PostProblem *pp, const double *partial, int nchunk, int M, double *flux, cplx *scal, double *te_frac) {
   const int b = blockIdx.x, m = threadIdx.x;
   if (m >= M) return;
   const int do_gauge = pp[b].flags & 1, do_norm = pp[b].flags & 2;
-  double fl = 0.0, best = -1.0, bidx = 0.0, bre = 1.0, bim = 0.0;
+  double fl = 0.0, best = -1.0, bidx = 0.0, bre = 1.0, bim = 0.0, te = 0.0, tm = 0.0;
   for (int c = 0; c < nchunk; ++c) {
-    const double *o = partial + (((size_t)b * nchunk + c) * M + m) * 5;
+    const double *o = partial + (((size_t)b * nchunk + c) * M + m) * kPostSlots;
     fl += o[0];
+    te += o[5];
+    tm += o[6];
     if (o[1] > best || (o[1] == best && o[2] < bidx)) { best = o[1]; bidx = o[2]; bre = o[3]; bim = o[4]; }
   }
   fl *= pp[b].mult;
   flux[(size_t)b * M + m] = fl;
+  te_frac[(size_t)b * M + m] = te / (te + tm);  // NaN for an all-zero field, like the reference
   cplx s = mk(1.0, 0.0);
   if (do_gauge && best > 0.0) {
     const double inv = rsqrt(best);

@@ -83,3 +83,16 @@ def apply_sorting(n_complex: Sequence[np.ndarray], fields: Sequence[np.ndarray],
         else:
             f_out.append((np.asarray(f)[..., sorting[i]] * np.exp(-1j * phase[i])).astype(np.asarray(f).dtype))
     return n_out, f_out
+
+
+def filter_polarization(te_fraction: np.ndarray, filter_pol: str) -> np.ndarray:
+    """Mode order of ``ModeSolver._filter_polarization`` (mode_solver.py:523-549) for one frequency from the device-computed
+    TE fractions (``info["te_fraction"]``): modes of the requested polarisation first, the others after, NaN last."""
+    te = np.asarray(te_fraction, float)
+    if filter_pol == "te":
+        parts = (np.where(te >= 0.5)[0], np.where(te < 0.5)[0], np.where(np.isnan(te))[0])
+    elif filter_pol == "tm":
+        parts = (np.where(te <= 0.5)[0], np.where(te > 0.5)[0], np.where(np.isnan(te))[0])
+    else:
+        raise ValueError("filter_pol must be 'te' or 'tm'")
+    return np.concatenate(parts)

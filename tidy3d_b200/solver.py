@@ -91,7 +91,7 @@ def compute_modes_batch(
 
     ``post``: on-device post-processing applied to the fields before they are delivered (``tidy3d_b200.postprocess``):
     any of ``"gauge"`` (mode_solver.py:802-810), ``"normalize"`` (flux normalisation, mode_solver.py:517-521), ``"flux"``
-    (report each mode's flux in the info dict) and ``"overlaps"`` (M x M modal overlap matrix with the previous problem of
+    (report each mode's flux and TE polarisation fraction in the info dict) and ``"overlaps"`` (M x M modal overlap matrix with the previous problem of
     the call, monitor_data.py:640-697, in the info dict as ``overlap_prev``; the input of ``postprocess.overlap_sort``).
     With ``want_fields=False`` only ``n_complex`` and these small results leave the GPU.
     """
@@ -137,7 +137,7 @@ def compute_modes_batch(
     with h.lock:
         rc, fields, ncs, results = h.solve_batch(packed, want_fields, fields_ptrs, want_flux=("flux" in post or "normalize" in post),
                                                  want_overlaps="overlaps" in post)
-        flux_out, ov_out = h.last_flux, h.last_overlaps
+        flux_out, te_out, ov_out = h.last_flux, h.last_te, h.last_overlaps
         err = h.last_error() if rc != _cabi.OK else ""
     if rc != _cabi.OK:
         bad = [i for i in range(len(packed)) if results[i].status != _cabi.OK]
@@ -156,6 +156,7 @@ def compute_modes_batch(
         )  # fmt: skip
         if flux_out:
             infos[-1]["flux"] = flux_out[i]
+            infos[-1]["te_fraction"] = te_out[i]
         if ov_out:
             infos[-1]["overlap_prev"] = ov_out[i]
     return (out, infos) if return_info else out
