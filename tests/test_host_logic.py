@@ -145,3 +145,38 @@ def test_input_validation(built_lib):
         built_lib.PackedProblem(wl.eps_cross[:8], wl.coords, wl.freqs[0], wl.mode_spec)
     with pytest.raises(ValueError, match="Wrong input to mode solver"):
         built_lib.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, mu_cross=wl.eps_cross[:5])
+
+
+def test_section_rasterisation_host_mirror(built_lib):
+    """The host mirror of section_raster_kernel (csrc/medium.cuh section_cell, shared by the device kernel) against the
+    numpy restatement of epsilon_on_grid for boxes: the set-up of a `section` problem equals the set-up of the sampled
+    eps_cross of the same cross-section."""
+    from oracle import sections as OS
+    from tidy3d_b200 import workloads as W
+    from tidy3d_b200.sections import Medium, Rect, Section
+
+    x = np.linspace(-1.0, 1.2, 24)
+    y = np.cumsum(np.r_[-0.8, np.random.default_rng(3).uniform(0.04, 0.09, 30)])
+    sec = Section(background=Medium(1.44**2 + 0.01j), structures=[
+        (Rect((0.0, 0.1), (0.9, 0.3)), Medium([4.0, 4.2, 3.9])),
+        (Rect((0.1, 0.1), (0.4, 0.2)), Medium(lambda f: 12.0 + 1e-15 * f)),
+        (Rect((x[5], y[7]), (2 * (x[9] - x[5]), 2 * (y[12] - y[7]))), Medium(2.0)),  # edges exactly on Yee sites: inclusive test
+    ])
+    spec = W.ModeSpecLike(num_modes=2, num_pml=(3, 4))
+    freq = W.C_0 / 1.3
+    eps = OS.eps_on_grid(sec, [x, y], freq)
+    outs = []
+    for pk in (built_lib.PackedProblem(None, [x, y], freq, spec, section=sec), built_lib.PackedProblem(eps, [x, y], freq, spec)):
+        nx, ny = pk.nx, pk.ny
+        sigma = np.zeros(2)
+        flags = (C.c_int * 4)()
+        tgt, kn = C.c_double(), C.c_double()
+        cx, cy, f = np.zeros(4 * nx, complex), np.zeros(4 * ny, complex), np.zeros((6, nx * ny), complex)
+        rc = built_lib.lib().b200ms_debug_setup(C.byref(pk.struct), built_lib._ptr(sigma), flags, C.byref(tgt), C.byref(kn),
+                                                built_lib._ptr(cx.view(float)), built_lib._ptr(cy.view(float)), built_lib._ptr(f.view(float)))
+        assert rc == 0
+        outs.append((sigma.copy(), list(flags), tgt.value, cx, cy, f))
+    a, b = outs
+    assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0], b[0])
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+    assert np.abs(b[5][0].reshape(23, 30) - eps[0]).max() < 1e-14  # exx of the set-up is the sampled eps_xx (no Jacobian here)
