@@ -145,7 +145,8 @@ typedef struct {
   int gmres_cgs2;        /* inner FGMRES Gram-Schmidt: 1 always two passes (CGS2); 0 one pass (+ a second on cancellation; measured 3x more
                             iterations at tol 1e-10); 2 (default) one pass while all residuals are > 3e-6, CGS2 below */
   int stencil_variant;   /* 0: marching kernel, rows per CTA chosen by level size (default); 1: shared-memory tiled kernel (reference
-                            implementation); 2: marching kernel with 32 rows per CTA on every level (round-1 behaviour) */
+                            implementation); 2: marching kernel with 32 rows per CTA on every level (round-1 behaviour); 3: like 0 without the wave-quantisation
+                            rule for the fine level */
   int mg_nu_growth;      /* extra Jacobi sweeps per coarser level (variable V-cycle), default 0 */
   int use_graph;         /* 1 (default): replay the multigrid V-cycle as one CUDA graph (fp32 multigrid only) */
   int mg_cycles;         /* V-cycles per preconditioner application (default 1) */

@@ -447,7 +447,17 @@ class BatchSolver {
     if (opt_.stencil_variant != 1 && v.nx >= 32 && v.ny >= 2) {
       // rows marched per CTA: the march is a serial chain of (TXR + 3) row steps, each waiting on one global-load
       // round trip, so small levels (few CTAs per SM, nothing to hide that latency behind) get short chains
-      if (v.nx >= 384 || opt_.stencil_variant == 2) launch_march<TT, CC, 32>(v, mode, a, dinv != nullptr);
+      bool rows32 = v.nx >= 384;
+      if (rows32 && opt_.stencil_variant != 2 && opt_.stencil_variant != 3) {
+        // wave quantisation: 7 CTAs of 128 threads per SM are resident; when 32-row CTAs leave the last wave mostly empty
+        // (e.g. 32 problems of 512^2: 2.47 waves) 16-row CTAs fill it at the price of 9 % more halo rows
+        const double per_wave = 148.0 * 7.0;
+        const double c32 = (double)((v.ny + kMarchOut - 1) / kMarchOut) * ((v.nx + 31) / 32) * B / per_wave;
+        const double c16 = (double)((v.ny + kMarchOut - 1) / kMarchOut) * ((v.nx + 15) / 16) * B / per_wave;
+        const double t32 = std::ceil(c32) * 35.0, t16 = std::ceil(c16) * 19.0;  // waves x row steps per CTA
+        if (t16 < 0.97 * t32) rows32 = false;
+      }
+      if (rows32 || opt_.stencil_variant == 2) launch_march<TT, CC, 32>(v, mode, a, dinv != nullptr);
       else if (v.nx >= 192) launch_march<TT, CC, 16>(v, mode, a, dinv != nullptr);
       else launch_march<TT, CC, 8>(v, mode, a, dinv != nullptr);
       return;

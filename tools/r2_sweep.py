@@ -150,3 +150,7 @@ if "f" in which:
             out, info = compute_modes_batch([dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)], return_info=True, handle=h)
             print(f"## {name} {opts}: |dn| {np.abs(out[0][1] - gg['n_tight']).max():.1e} inner {info[0]['inner_iters']} dev_ms {h.last_stats()['device_ms']:.1f}", flush=True)
             h.close()
+if "g" in which:
+    for nb in (32, 16, 64):
+        run(nb, "wave rule")
+        run(nb, "no wave rule", stencil_variant=3)
