@@ -73,3 +73,27 @@ def cluster_overlaps(f, g, n, gap=1e-4):
         qb, _ = np.linalg.qr(Bm)
         out.append((c, np.linalg.svd(qa.conj().T @ qb, compute_uv=False).min()))
     return out
+
+
+SKETCH_K, SKETCH_SEED, ETA_0 = 16, 20260923, 376.73031366686166
+
+
+def sketch(fields):
+    """(K, M) complex random sketch of a (2,3,Nx,Ny,1,M) field array (H block scaled by ETA_0 so both blocks weigh equally);
+    see tests/golden/make_sketch_golden.py.  Row by row: the K x 6N Gaussian matrix is never materialised."""
+    f = np.asarray(fields, dtype=np.complex128).copy()
+    f[1] *= ETA_0
+    m = f.shape[-1]
+    v = f.reshape(-1, m)
+    rng = np.random.default_rng(SKETCH_SEED)
+    out = np.zeros((SKETCH_K, m), complex)
+    for k in range(SKETCH_K):
+        p = rng.standard_normal(v.shape[0]) + 1j * rng.standard_normal(v.shape[0])
+        out[k] = p @ v
+    return out / np.linalg.norm(v, axis=0)
+
+
+def sketch_similarity(a, b):
+    """Per mode |<a, b>| / (|a| |b|) of two (K, M) sketches: 1 - O(err^2) when the underlying unit vectors agree up to a
+    global phase, ~ 1/sqrt(K) for unrelated vectors."""
+    return np.abs(np.sum(np.conj(a) * b, axis=0)) / (np.linalg.norm(a, axis=0) * np.linalg.norm(b, axis=0))
