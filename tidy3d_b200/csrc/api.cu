@@ -100,6 +100,8 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->stencil_async = 0;
   o->kappa_cap = 1e4;
   o->outer_dgks = 1;
+  o->stencil_pair = 0;
+  o->stencil_pair_rows = 0;
 }
 
 extern "C" int b200ms_create(int device, b200ms_handle **out) {
@@ -1065,7 +1067,12 @@ int debug_run(b200ms_handle *h, const Window &W, int what, int level, int mode, 
   std::vector<MediumRef> refs(1, W.refs[0]);
   BatchSolver<T, C, P, PC> S(h->arena, h->stream, h->opt);
   S.build(ps, false, upload_refs(h, refs, h->stream));
-  if (what == 0 && (level > 0 || mode == 3)) {  // multigrid operator of level `level` in preconditioner precision
+  if (what == 0 && mode >= 16) {  // mode + 16: the multigrid operator (preconditioner precision) also on level 0
+    mode -= 16;
+    if (level == 0 && mode != 3) level = -1000;
+  }
+  if (what == 0 && (level > 0 || level == -1000 || mode == 3)) {  // multigrid operator of level `level` in preconditioner precision
+    if (level == -1000) level = 0;
     if (level < 0 || level >= (int)S.lv.size()) return B200MS_ERR_ARG;
     const size_t n2 = 2 * S.lv[level].N;
     std::vector<P> a(n2), b(n2), o(n2);

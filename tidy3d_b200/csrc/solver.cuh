@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -17,6 +18,7 @@
 #include "kernels.cuh"
 #include "krylov_kernels.cuh"
 #include "coarse_kernel.cuh"
+#include "march2.cuh"
 
 namespace b200ms {
 
@@ -410,6 +412,7 @@ class BatchSolver {
     dinv_ready_ = true;
     CUDA_CHECK(cudaStreamSynchronize(st_));
     CUDA_CHECK(cudaGetLastError());
+    prime_march2();
     plan_fused_tail();
     capture_precondition_graph();
   }
@@ -444,6 +447,7 @@ class BatchSolver {
     a.omega = opt_.mg_omega;
     a.dinv = dinv;
     stats.launches++;
+    if (launch_march2<TT, CC>(v, mode, a, dinv != nullptr)) return;
     if (opt_.stencil_variant != 1 && v.nx >= 32 && v.ny >= 2) {
       // rows marched per CTA: the march is a serial chain of (TXR + 3) row steps, each waiting on one global-load
       // round trip, so small levels (few CTAs per SM, nothing to hide that latency behind) get short chains
@@ -473,6 +477,73 @@ class BatchSolver {
       else if (mode == MODE_RESID) stencil_kernel<TT, CC, MODE_RESID, false><<<grd, blk, 0, st_>>>(a);
       else stencil_kernel<TT, CC, MODE_JACOBI, false><<<grd, blk, 0, st_>>>(a);
     }
+  }
+  // pair-marching kernel (csrc/march2.cuh): real fp32 multigrid operators without mu fields on even-width levels
+  using March2Fn = void (*)(StencilArgs<float, float>, int);
+  static March2Fn march2_kernel_for(int md, int pf) {
+    if (pf == 1) {
+      if (md == MODE_APPLY) return stencil_march2_kernel<float, MODE_APPLY, 1>;
+      if (md == MODE_RESID) return stencil_march2_kernel<float, MODE_RESID, 1>;
+      if (md == MODE_JACOBI_D) return stencil_march2_kernel<float, MODE_JACOBI_D, 1>;
+      if (md == MODE_JACOBI_D0) return stencil_march2_kernel<float, MODE_JACOBI_D0, 1>;
+    } else {
+      if (md == MODE_APPLY) return stencil_march2_kernel<float, MODE_APPLY, 2>;
+      if (md == MODE_RESID) return stencil_march2_kernel<float, MODE_RESID, 2>;
+      if (md == MODE_JACOBI_D) return stencil_march2_kernel<float, MODE_JACOBI_D, 2>;
+      if (md == MODE_JACOBI_D0) return stencil_march2_kernel<float, MODE_JACOBI_D0, 2>;
+    }
+    return nullptr;
+  }
+  bool march2_eligible(const Level &v) const {
+    return opt_.stencil_pair > 0 && opt_.stencil_variant != 1 && !has_mu && !(v.ny & 1) && v.ny >= 8 && v.nx >= 32;
+  }
+  int march2_resident(March2Fn kern, int md, int pf, int W) {
+    const long key = ((long)md * 4 + pf) * 1024 + W;
+    auto it = m2_resident_.find(key);
+    if (it == m2_resident_.end()) {
+      int per_sm = 0, dev = 0, sms = 148;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W, 0));
+      CUDA_CHECK(cudaGetDevice(&dev));
+      CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      it = m2_resident_.emplace(key, std::max(1, per_sm) * sms).first;
+    }
+    return it->second;
+  }
+  // occupancy queries happen here, before the V-cycle is captured into a CUDA graph
+  void prime_march2() {
+    if constexpr (std::is_same<P, float>::value && std::is_same<PC, float>::value) {
+      const int pf = opt_.stencil_pair >= 2 ? 2 : 1;
+      for (const Level &v : lv) {
+        if (!march2_eligible(v)) continue;
+        int W = 0, nstrips = 0;
+        march2_strips(v.ny, W, nstrips);
+        for (int md : {MODE_APPLY, MODE_RESID, MODE_JACOBI_D, MODE_JACOBI_D0}) march2_resident(march2_kernel_for(md, pf), md, pf, W);
+      }
+    }
+  }
+  template <typename TT, typename CC>
+  bool launch_march2(const Level &v, int mode, const StencilArgs<TT, CC> &a, bool have_dinv) {
+    if constexpr (std::is_same<TT, float>::value && std::is_same<CC, float>::value) {
+      if (!march2_eligible(v)) return false;
+      int md = mode;
+      if (mode == MODE_JACOBI) {
+        if (!have_dinv) return false;
+        md = MODE_JACOBI_D;
+      }
+      if (md == MODE_JACOBI_D0 && !have_dinv) return false;
+      const int pf = opt_.stencil_pair >= 2 ? 2 : 1;
+      March2Fn kern = march2_kernel_for(md, pf);
+      if (!kern) return false;
+      int W = 0, nstrips = 0;
+      march2_strips(v.ny, W, nstrips);
+      const int resident = march2_resident(kern, md, pf, W);
+      const int rows = opt_.stencil_pair_rows > 0 ? std::min(kM2MaxSteps - 3, 6 * ((opt_.stencil_pair_rows + 3 + 5) / 6) - 3)
+                                                  : march2_rows(v.nx, nstrips, B, resident);
+      dim3 grd(nstrips, (v.nx + rows - 1) / rows, B);
+      kern<<<grd, W, 0, st_>>>(a, rows);
+      return true;
+    }
+    return false;
   }
   template <typename TT, typename CC, int TXR>
   void launch_march(const Level &v, int mode, const StencilArgs<TT, CC> &a, bool have_dinv) {
@@ -1826,6 +1897,7 @@ class BatchSolver {
   cplx *tcoef_ = nullptr;
   std::vector<cd> sig_mg_host_;
   bool dinv_ready_ = false;
+  std::map<long, int> m2_resident_;  // pair-marching kernel: resident CTAs on the device per (mode, prefetch depth, CTA width)
   cudaGraphExec_t graph_exec_ = nullptr;
   P *graph_result_ = nullptr;
   long graph_nodes_ = 0, graph_fine_applies_ = 0;
