@@ -174,9 +174,11 @@ typedef struct {
                             Ritz value in the projected problem, before the comparison with eig_tol (default 1e4; 1 = ARPACK's test) */
   int outer_dgks;        /* 1 (default): Krylov-Schur orthogonalisation reorthogonalises only when ARPACK's DGKS test asks for it;
                             0: always two Gram-Schmidt passes */
-  int stencil_pair;      /* pair-marching stencil kernel (csrc/march2.cuh: two columns per thread, 64-bit loads, CTA width fitted to the row,
-                            six-fold unrolled row loop) for the real fp32 multigrid operators on even-width levels: 1 = one row of
-                            prefetch registers, 2 = two rows; 0 = the one-column marching kernel everywhere */
+  int stencil_pair;      /* pair-marching stencil kernels for the real fp32 multigrid operators on even-width levels (two columns per thread,
+                            64-bit accesses, CTA width fitted to the row, six-fold unrolled row loop): 1 / 2 = rows prefetched into one / two
+                            sets of registers (csrc/march2.cuh); 3 / 4 = rows staged by TMA bulk copies (cp.async.bulk + mbarrier, ring of
+                            three stages, csrc/march2_tma.cuh) where ny % 4 == 0, the register version 1 / 2 elsewhere; 5 = TMA, two
+                            stages; 0 = the one-column marching kernel everywhere */
   int stencil_pair_rows; /* rows marched per CTA by the pair kernel (rounded to 6 m - 3); 0 (default) = chosen per level from the
                             number of resident CTAs */
 } b200ms_options;

@@ -100,7 +100,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->stencil_async = 0;
   o->kappa_cap = 1e4;
   o->outer_dgks = 1;
-  o->stencil_pair = 0;
+  o->stencil_pair = 2;
   o->stencil_pair_rows = 0;
 }
 

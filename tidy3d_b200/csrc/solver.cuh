@@ -19,6 +19,7 @@
 #include "krylov_kernels.cuh"
 #include "coarse_kernel.cuh"
 #include "march2.cuh"
+#include "march2_tma.cuh"
 
 namespace b200ms {
 
@@ -478,46 +479,78 @@ class BatchSolver {
       else stencil_kernel<TT, CC, MODE_JACOBI, false><<<grd, blk, 0, st_>>>(a);
     }
   }
-  // pair-marching kernel (csrc/march2.cuh): real fp32 multigrid operators without mu fields on even-width levels
+  // pair-marching kernels (csrc/march2.cuh, csrc/march2_tma.cuh): real fp32 multigrid operators without mu fields on even-width
+  // levels.  stencil_pair: 1 / 2 = register version with one / two rows of prefetch registers; 3 / 4 = TMA row staging (ring of
+  // three stages) where it applies (ny % 4 == 0, not the fused first sweeps), register version 1 / 2 elsewhere; 5 = TMA with two stages.
   using March2Fn = void (*)(StencilArgs<float, float>, int);
-  static March2Fn march2_kernel_for(int md, int pf) {
-    if (pf == 1) {
-      if (md == MODE_APPLY) return stencil_march2_kernel<float, MODE_APPLY, 1>;
-      if (md == MODE_RESID) return stencil_march2_kernel<float, MODE_RESID, 1>;
-      if (md == MODE_JACOBI_D) return stencil_march2_kernel<float, MODE_JACOBI_D, 1>;
-      if (md == MODE_JACOBI_D0) return stencil_march2_kernel<float, MODE_JACOBI_D0, 1>;
-    } else {
-      if (md == MODE_APPLY) return stencil_march2_kernel<float, MODE_APPLY, 2>;
-      if (md == MODE_RESID) return stencil_march2_kernel<float, MODE_RESID, 2>;
-      if (md == MODE_JACOBI_D) return stencil_march2_kernel<float, MODE_JACOBI_D, 2>;
-      if (md == MODE_JACOBI_D0) return stencil_march2_kernel<float, MODE_JACOBI_D0, 2>;
+  struct March2Pick {
+    March2Fn fn = nullptr;
+    int stages = 0, narr = 0, id = 0;  // stages > 0: TMA version with that ring depth
+  };
+  March2Pick march2_pick(int md, int ny) const {
+    March2Pick p;
+    const int sp = opt_.stencil_pair;
+    const int pf = (sp == 2 || sp == 4) ? 2 : 1;
+    const int stages = (sp == 3 || sp == 4) ? 3 : (sp == 5 ? 2 : 0);
+    if (stages > 0 && (ny % 4) == 0 && md != MODE_JACOBI_D0) {
+      p.stages = stages;
+      p.narr = md == MODE_APPLY ? 5 : (md == MODE_RESID ? 7 : 9);
+      p.id = 16 + stages;
+      if (stages == 3) {
+        if (md == MODE_APPLY) p.fn = stencil_march2_tma_kernel<MODE_APPLY, 3>;
+        else if (md == MODE_RESID) p.fn = stencil_march2_tma_kernel<MODE_RESID, 3>;
+        else if (md == MODE_JACOBI_D) p.fn = stencil_march2_tma_kernel<MODE_JACOBI_D, 3>;
+      } else {
+        if (md == MODE_APPLY) p.fn = stencil_march2_tma_kernel<MODE_APPLY, 2>;
+        else if (md == MODE_RESID) p.fn = stencil_march2_tma_kernel<MODE_RESID, 2>;
+        else if (md == MODE_JACOBI_D) p.fn = stencil_march2_tma_kernel<MODE_JACOBI_D, 2>;
+      }
+      return p;
     }
-    return nullptr;
+    p.id = pf;
+    if (pf == 1) {
+      if (md == MODE_APPLY) p.fn = stencil_march2_kernel<float, MODE_APPLY, 1>;
+      else if (md == MODE_RESID) p.fn = stencil_march2_kernel<float, MODE_RESID, 1>;
+      else if (md == MODE_JACOBI_D) p.fn = stencil_march2_kernel<float, MODE_JACOBI_D, 1>;
+      else if (md == MODE_JACOBI_D0) p.fn = stencil_march2_kernel<float, MODE_JACOBI_D0, 1>;
+    } else {
+      if (md == MODE_APPLY) p.fn = stencil_march2_kernel<float, MODE_APPLY, 2>;
+      else if (md == MODE_RESID) p.fn = stencil_march2_kernel<float, MODE_RESID, 2>;
+      else if (md == MODE_JACOBI_D) p.fn = stencil_march2_kernel<float, MODE_JACOBI_D, 2>;
+      else if (md == MODE_JACOBI_D0) p.fn = stencil_march2_kernel<float, MODE_JACOBI_D0, 2>;
+    }
+    return p;
   }
   bool march2_eligible(const Level &v) const {
     return opt_.stencil_pair > 0 && opt_.stencil_variant != 1 && !has_mu && !(v.ny & 1) && v.ny >= 8 && v.nx >= 32;
   }
-  int march2_resident(March2Fn kern, int md, int pf, int W) {
-    const long key = ((long)md * 4 + pf) * 1024 + W;
+  static size_t march2_smem(const March2Pick &p, int W) { return (size_t)p.stages * p.narr * W * sizeof(float2); }
+  // resident CTAs on the device for this kernel at this CTA width; also raises the kernel's dynamic shared-memory limit once
+  int march2_resident(const March2Pick &p, int md, int W) {
+    const long key = ((long)md * 32 + p.id) * 1024 + W;
     auto it = m2_resident_.find(key);
     if (it == m2_resident_.end()) {
       int per_sm = 0, dev = 0, sms = 148;
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W, 0));
+      if (p.stages > 0)
+        CUDA_CHECK(cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march2_smem(p, kM2MaxW)));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.fn, W, march2_smem(p, W)));
       CUDA_CHECK(cudaGetDevice(&dev));
       CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       it = m2_resident_.emplace(key, std::max(1, per_sm) * sms).first;
     }
     return it->second;
   }
-  // occupancy queries happen here, before the V-cycle is captured into a CUDA graph
+  // occupancy queries and attribute changes happen here, before the V-cycle is captured into a CUDA graph
   void prime_march2() {
     if constexpr (std::is_same<P, float>::value && std::is_same<PC, float>::value) {
-      const int pf = opt_.stencil_pair >= 2 ? 2 : 1;
       for (const Level &v : lv) {
         if (!march2_eligible(v)) continue;
         int W = 0, nstrips = 0;
         march2_strips(v.ny, W, nstrips);
-        for (int md : {MODE_APPLY, MODE_RESID, MODE_JACOBI_D, MODE_JACOBI_D0}) march2_resident(march2_kernel_for(md, pf), md, pf, W);
+        for (int md : {MODE_APPLY, MODE_RESID, MODE_JACOBI_D, MODE_JACOBI_D0}) {
+          const March2Pick p = march2_pick(md, v.ny);
+          if (p.fn) march2_resident(p, md, W);
+        }
       }
     }
   }
@@ -531,16 +564,15 @@ class BatchSolver {
         md = MODE_JACOBI_D;
       }
       if (md == MODE_JACOBI_D0 && !have_dinv) return false;
-      const int pf = opt_.stencil_pair >= 2 ? 2 : 1;
-      March2Fn kern = march2_kernel_for(md, pf);
-      if (!kern) return false;
+      const March2Pick p = march2_pick(md, v.ny);
+      if (!p.fn) return false;
       int W = 0, nstrips = 0;
       march2_strips(v.ny, W, nstrips);
-      const int resident = march2_resident(kern, md, pf, W);
+      const int resident = march2_resident(p, md, W);
       const int rows = opt_.stencil_pair_rows > 0 ? std::min(kM2MaxSteps - 3, 6 * ((opt_.stencil_pair_rows + 3 + 5) / 6) - 3)
                                                   : march2_rows(v.nx, nstrips, B, resident);
       dim3 grd(nstrips, (v.nx + rows - 1) / rows, B);
-      kern<<<grd, W, 0, st_>>>(a, rows);
+      p.fn<<<grd, W, march2_smem(p, W), st_>>>(a, rows);
       return true;
     }
     return false;
