@@ -181,6 +181,11 @@ typedef struct {
                             stages; 0 = the one-column marching kernel everywhere */
   int stencil_pair_rows; /* rows marched per CTA by the pair kernel (rounded to 6 m - 3); 0 (default) = chosen per level from the
                             number of resident CTAs */
+  int transfer_vec;      /* multigrid transfers: bit 0 = the prolongation reads / writes its four fine values as one 128-bit access (fp32 vectors,
+                            nyf % 4 == 0); bit 1 = the restriction reads each fine row of its patch as aligned 64-bit pairs when the patch is
+                            contiguous */
+  int tensor_mg_cycles;  /* tensorial path: V-cycles (defect correction on the multigrid operator) per application of the E-block inverse inside
+                            the block preconditioner; 0 = mg_cycles.  Default 3 (see csrc/solver.cuh mg_cycles_ and tools/proto_tensor.py) */
 } b200ms_options;
 
 /* Counters of the most recent b200ms_solve_batch call on a handle (all its device batches together). */

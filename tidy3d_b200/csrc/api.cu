@@ -100,8 +100,10 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->stencil_async = 0;
   o->kappa_cap = 1e4;
   o->outer_dgks = 1;
-  o->stencil_pair = 2;
+  o->stencil_pair = 4;
   o->stencil_pair_rows = 0;
+  o->transfer_vec = 0;
+  o->tensor_mg_cycles = 3;
 }
 
 extern "C" int b200ms_create(int device, b200ms_handle **out) {

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 namespace b200ms {
 
@@ -847,7 +848,10 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(TransferArgs a, const 
 // Four consecutive fine columns per thread: the x-lists and the two coarse row pointers are shared by the four outputs and
 // the y-lists are read as 16-byte vectors; the one-output-per-thread version above is instruction-bound on the fine level
 // (33.5 M outputs x ~60 instructions at 64 x 512^2).
-template <typename T>
+// VEC (fp32 vectors, nyf % 4 == 0): the four fine values are read and written as one 128-bit access.  With scalar accesses every
+// load / store instruction of a warp touches 4 of every 16 bytes over a 512-byte span, so each fine sector is visited by four load
+// and four (partial-sector) store instructions.
+template <typename T, bool VEC = false>
 __global__ void __launch_bounds__(256) prolong_add4_kernel(TransferArgs a, const T *coarse, T *fine) {
   using R = typename RealOf<T>::type;
   const int j4 = blockIdx.x * 64 + threadIdx.x, i = blockIdx.y * 4 + threadIdx.y;
@@ -883,6 +887,23 @@ __global__ void __launch_bounds__(256) prolong_add4_kernel(TransferArgs a, const
     }
   }
   T fv[4], cv[4][4];
+  if constexpr (VEC && std::is_same<T, float>::value) {
+    if (nq == 4) {
+      const float4 f4 = *reinterpret_cast<const float4 *>(f);
+      fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z; fv[3] = f4.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        cv[q][0] = ldg(c0 + J0[q]); cv[q][1] = ldg(c0 + J1[q]); cv[q][2] = ldg(c1 + J0[q]); cv[q][3] = ldg(c1 + J1[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (comp == 0 && a.mask_y && j0 + q == 0 && a.nyf > 1) continue;
+        fv[q] = fv[q] + (wx0 * (wy0[q] * cv[q][0] + wy1[q] * cv[q][1]) + wx1 * (wy0[q] * cv[q][2] + wy1[q] * cv[q][3]));
+      }
+      *reinterpret_cast<float4 *>(f) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+      return;
+    }
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (q < nq) {

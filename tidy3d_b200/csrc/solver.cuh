@@ -707,7 +707,7 @@ class BatchSolver {
   }
   // z = B_E v on two-component fields with batch strides v_bs / z_bs (== lenE for plain batched vectors)
   void precondition_E(const T *v, size_t v_bs, T *z, size_t z_bs) {
-    const int ncyc = std::max(1, opt_.mg_cycles);
+    const int ncyc = mg_cycles_();
     dim3 cg((unsigned)std::min<size_t>((lenE + 255) / 256, 1024), B);
     if constexpr (kMixed) {
       convert_strided_kernel<T, P><<<cg, 256, 0, st_>>>(lenE, v, v_bs, lv[0].b, lenE);
@@ -732,6 +732,12 @@ class BatchSolver {
       }
     }
   }
+  // V-cycles per application of the E-block inverse.  The tensorial block preconditioner needs an accurate one: its H block is
+  // -(1/s)(I - Q B_E P), the difference of two O(K^2) terms (K = 1/(k0 h)) whose exact value is O(K^-2), so a B_E with the ~0.15
+  // relative error of one V-cycle leaves an O(0.15 K^2) error there and the outer FGMRES count grows with the resolution
+  // (tools/proto_tensor.py: 25 / 52 / 90 / > 200 iterations at 64^2 / 96^2 / 128^2 / 192^2, against 17 at 128^2 and 49 at 256^2
+  // with three defect-correction cycles in both blocks).
+  int mg_cycles_() const { return (tensor_ && opt_.tensor_mg_cycles > 0) ? opt_.tensor_mg_cycles : std::max(1, opt_.mg_cycles); }
   // rin -> M^-1 rin in multigrid precision.  out == nullptr: result in lv[0].x (one cycle) or pre_b_ (several)
   void precondition_body(const P *rin, P *out, int ncyc) {
     const unsigned nb = (unsigned)std::min<size_t>((vsE + 255) / 256, 8192);
@@ -753,7 +759,7 @@ class BatchSolver {
   void capture_precondition_graph() {
     if constexpr (kMixed) {
       if (!opt_.use_graph) return;
-      const int ncyc = std::max(1, opt_.mg_cycles);
+      const int ncyc = mg_cycles_();
       const long l0 = stats.launches, a0 = stats.stencil_applies;
       cudaGraph_t graph = nullptr;
       CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -883,7 +889,8 @@ class BatchSolver {
       const TransferArgs &t = v.tr;
       if (t.nyf >= 256 && opt_.transfer_tiled != 2) {  // four fine columns per thread
         dim3 blk(64, 4), grd((t.nyf + 255) / 256, (t.nxf + 3) / 4, 2 * B);
-        prolong_add4_kernel<P><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
+        if ((opt_.transfer_vec & 1) && std::is_same<P, float>::value && (t.nyf % 4) == 0) prolong_add4_kernel<P, true><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
+        else prolong_add4_kernel<P, false><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
       } else {
         dim3 blk(64, 4), grd((t.nyf + 63) / 64, (t.nxf + 3) / 4, 2 * B);
         prolong_add_kernel<P><<<grd, blk, 0, st_>>>(t, lv[l + 1].x, cur);
@@ -1258,7 +1265,7 @@ class BatchSolver {
       precondition(v, z);
     } else {
       if (!input_staged) CUDA_CHECK(cudaMemcpyAsync(lv[0].b, v, vsE * sizeof(P), cudaMemcpyDeviceToDevice, st_));
-      const int ncyc = std::max(1, opt_.mg_cycles);
+      const int ncyc = mg_cycles_();
       if (graph_exec_) {
         CUDA_CHECK(cudaGraphLaunch(graph_exec_, st_));
         stats.launches += graph_nodes_;
