@@ -55,3 +55,34 @@ def test_pair_and_tma_kernels_match_the_one_column_kernel(shape, symmetry):
     finally:
         for h in hs.values():
             h.close()
+
+
+@pytest.mark.parametrize("shape,symmetry", [((256, 256), (0, 0)), ((150, 300), (0, 0)), ((96, 128), (1, -1))])
+def test_vcycle_is_the_same_with_every_kernel_family(shape, symmetry):
+    """One multigrid V-cycle (b200ms_debug_vcycle) with the round-2 kernels everywhere (one-column stencil, per-range restriction,
+    scalar prolongation) against the defaults (TMA pair stencil, packed-list restriction, 128-bit prolongation): same operator,
+    same summation order in the transfers."""
+    wl = _rect(*shape, symmetry=symmetry)
+    pk = _cabi.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, wl.symmetry, "+")
+    nx, ny = shape
+    rng = np.random.default_rng(3)
+    r = rng.standard_normal((2, nx, ny)) + 0j
+    if symmetry[1] != 1 and ny > 1:
+        r[0][:, 0] = 0  # PEC wall rows are held at zero (the V-cycle's input never has them)
+    if symmetry[0] != 1 and nx > 1:
+        r[1][0, :] = 0
+    ra = np.ascontiguousarray(r.ravel())
+    zs = {}
+    for name, opts in (("round2", dict(stencil_pair=0, transfer_vec=0)), ("default", {}), ("pair_only", dict(stencil_pair=2, transfer_vec=0)),
+                       ("transfers_only", dict(stencil_pair=0, transfer_vec=3))):
+        h = _cabi.Handle(**opts)
+        z = np.zeros(ra.size, complex)
+        rc = _cabi.lib().b200ms_debug_vcycle(h._h, C.byref(pk.struct), _cabi._ptr(ra.view(float)), _cabi._ptr(z.view(float)))
+        assert rc == 0, (rc, h.last_error())
+        h.close()
+        zs[name] = z
+    scale = np.abs(zs["round2"]).max()
+    assert np.isfinite(scale) and scale > 0
+    assert np.abs(zs["transfers_only"] - zs["round2"]).max() <= 2e-6 * scale  # same expressions, same order
+    for name in ("default", "pair_only"):
+        assert np.abs(zs[name] - zs["round2"]).max() <= 2e-5 * scale, name

@@ -102,7 +102,7 @@ extern "C" void b200ms_default_options(b200ms_options *o) {
   o->outer_dgks = 1;
   o->stencil_pair = 4;
   o->stencil_pair_rows = 0;
-  o->transfer_vec = 0;
+  o->transfer_vec = 3;
   o->tensor_mg_cycles = 3;
 }
 

@@ -701,11 +701,19 @@ __global__ void __launch_bounds__(256) jacobi0_kernel(StencilArgs<T, C> a) {
 // ------------------------------------------------------------------------------------------------
 // grid transfer (tensor product of 1-D lists, see host_setup.hpp)
 // ------------------------------------------------------------------------------------------------
+// packed restriction list of one coarse index: up to four (fine index, weight) entries; unused entries repeat a valid index
+// with weight zero, so the kernel needs no predicates
+struct __align__(16) RList4 {
+  int idx[4];
+  float w[4];
+};
 struct Transfer1DDev {
   const int *p_i0, *p_i1;
   const double *p_w0, *p_w1;
   const int *r_ptr, *r_idx;
   const double *r_w;
+  const float *p_w0f, *p_w1f;  // the prolongation weights in single precision (fp32 multigrid: no F2F per weight and thread)
+  const RList4 *r4;            // packed restriction lists, nullptr when some coarse index has more than four entries
 };
 struct TransferArgs {
   int nxf, nyf, nxc, nyc;
@@ -762,6 +770,43 @@ __global__ void __launch_bounds__(256) restrict_kernel(TransferArgs a, const T *
       for (int ky = ky0; ky < ky1; ++ky) racc += ty.r_w[ky] * ldg(row + ty.r_idx[ky]);
       acc += wxk * racc;
     }
+  }
+  if ((comp == 0 && a.mask_y && J == 0 && a.nyc > 1) || (comp == 1 && a.mask_x && I == 0 && a.nxc > 1)) acc = zero_of<T>();
+  coarse[((size_t)b * 2 + comp) * Nc + (size_t)I * a.nyc + J] = acc;
+}
+
+// Restriction from packed lists (fp32 multigrid).  ncu on restrict_kernel at 64 x 512^2 (profiles/r02_transfers_ncu.txt): 370
+// thread instructions per coarse value, issue slots 71 % busy, DRAM at 1.2 TB/s -- the loads of the four list ranges, sixteen
+// double -> float weight conversions and the per-term predicates, not the sixteen gathers, set the pace.  Here a coarse index'
+// list is one 32-byte record (two 128-bit loads), the weights are fp32, unused entries carry weight zero and a valid index, and the
+// sixteen gathers are unconditional.  Same summation order as restrict_kernel, so the results are identical.
+template <typename T>
+__global__ void __launch_bounds__(256) restrict4_kernel(TransferArgs a, const T *fine, T *coarse) {
+  const int J = blockIdx.x * 64 + threadIdx.x, I = blockIdx.y * 4 + threadIdx.y;
+  const int comp = blockIdx.z & 1, b = blockIdx.z >> 1;
+  if (I >= a.nxc || J >= a.nyc) return;
+  const Transfer1DDev &tx = comp == 0 ? a.xe : a.xn;
+  const Transfer1DDev &ty = comp == 0 ? a.yn : a.ye;
+  const size_t Nf = (size_t)a.nxf * a.nyf, Nc = (size_t)a.nxc * a.nyc;
+  const T *f = fine + ((size_t)b * 2 + comp) * Nf;
+  const int4 xi = __ldg(reinterpret_cast<const int4 *>(tx.r4 + I)), yi = __ldg(reinterpret_cast<const int4 *>(ty.r4 + J));
+  const float4 xw = __ldg(reinterpret_cast<const float4 *>(tx.r4 + I) + 1), yw = __ldg(reinterpret_cast<const float4 *>(ty.r4 + J) + 1);
+  const int ix[4] = {xi.x, xi.y, xi.z, xi.w}, iy[4] = {yi.x, yi.y, yi.z, yi.w};
+  const float wx[4] = {xw.x, xw.y, xw.z, xw.w}, wy[4] = {yw.x, yw.y, yw.z, yw.w};
+  T v[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const T *row = f + (size_t)ix[p] * a.nyf;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[p][q] = ldg(row + iy[q]);
+  }
+  T acc = zero_of<T>();
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    T racc = zero_of<T>();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) racc += wy[q] * v[p][q];
+    acc += wx[p] * racc;
   }
   if ((comp == 0 && a.mask_y && J == 0 && a.nyc > 1) || (comp == 1 && a.mask_x && I == 0 && a.nxc > 1)) acc = zero_of<T>();
   coarse[((size_t)b * 2 + comp) * Nc + (size_t)I * a.nyc + J] = acc;
@@ -872,12 +917,18 @@ __global__ void __launch_bounds__(256) prolong_add4_kernel(TransferArgs a, const
   const int nq = min(4, a.nyf - j0);
   if (nq == 4) {
     const int4 q0 = __ldg(reinterpret_cast<const int4 *>(ty.p_i0 + j0)), q1 = __ldg(reinterpret_cast<const int4 *>(ty.p_i1 + j0));
-    const double2 w0a = __ldg(reinterpret_cast<const double2 *>(ty.p_w0 + j0)), w0b = __ldg(reinterpret_cast<const double2 *>(ty.p_w0 + j0 + 2));
-    const double2 w1a = __ldg(reinterpret_cast<const double2 *>(ty.p_w1 + j0)), w1b = __ldg(reinterpret_cast<const double2 *>(ty.p_w1 + j0 + 2));
     J0[0] = q0.x; J0[1] = q0.y; J0[2] = q0.z; J0[3] = q0.w;
     J1[0] = q1.x; J1[1] = q1.y; J1[2] = q1.z; J1[3] = q1.w;
-    wy0[0] = (R)w0a.x; wy0[1] = (R)w0a.y; wy0[2] = (R)w0b.x; wy0[3] = (R)w0b.y;
-    wy1[0] = (R)w1a.x; wy1[1] = (R)w1a.y; wy1[2] = (R)w1b.x; wy1[3] = (R)w1b.y;
+    if constexpr (VEC && std::is_same<R, float>::value) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4 *>(ty.p_w0f + j0)), w1 = __ldg(reinterpret_cast<const float4 *>(ty.p_w1f + j0));
+      wy0[0] = w0.x; wy0[1] = w0.y; wy0[2] = w0.z; wy0[3] = w0.w;
+      wy1[0] = w1.x; wy1[1] = w1.y; wy1[2] = w1.z; wy1[3] = w1.w;
+    } else {
+      const double2 w0a = __ldg(reinterpret_cast<const double2 *>(ty.p_w0 + j0)), w0b = __ldg(reinterpret_cast<const double2 *>(ty.p_w0 + j0 + 2));
+      const double2 w1a = __ldg(reinterpret_cast<const double2 *>(ty.p_w1 + j0)), w1b = __ldg(reinterpret_cast<const double2 *>(ty.p_w1 + j0 + 2));
+      wy0[0] = (R)w0a.x; wy0[1] = (R)w0a.y; wy0[2] = (R)w0b.x; wy0[3] = (R)w0b.y;
+      wy1[0] = (R)w1a.x; wy1[1] = (R)w1a.y; wy1[2] = (R)w1b.x; wy1[3] = (R)w1b.y;
+    }
   } else {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

@@ -876,7 +876,9 @@ class BatchSolver {
           restrict_tiled_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
         } else {
           dim3 grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, 2 * B);
-          restrict_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+          const bool packed = (opt_.transfer_vec & 2) && std::is_same<typename RealOf<P>::type, float>::value && t.xn.r4 && t.xe.r4 && t.yn.r4 && t.ye.r4;
+          if (packed) restrict4_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
+          else restrict_kernel<P><<<grd, blk, 0, st_>>>(t, v.r, lv[l + 1].b);
         }
       } else {
         dim3 grd((t.nyc + 63) / 64, (t.nxc + 3) / 4, 2 * B);
@@ -1862,6 +1864,7 @@ class BatchSolver {
     for (const Transfer1D *q : {&t.node, &t.edge}) {
       ints += q->p_i0.size() * 2 + q->r_ptr.size() + q->r_idx.size() + 256;
       dbls += q->p_w0.size() * 2 + q->r_w.size() + 256;
+      dbls += q->p_w0.size() + 4 * q->r_ptr.size() + 192;  // fp32 prolongation weights (2 x n floats) and the packed restriction lists (32 B per coarse index)
     }
   }
   template <typename U>
@@ -1874,6 +1877,24 @@ class BatchSolver {
   void upload_transfer(const Transfer1D &h, Transfer1DDev &d) {
     d.p_i0 = up(h.p_i0); d.p_i1 = up(h.p_i1); d.p_w0 = up(h.p_w0); d.p_w1 = up(h.p_w1);
     d.r_ptr = up(h.r_ptr); d.r_idx = up(h.r_idx); d.r_w = up(h.r_w);
+    std::vector<float> w0f(h.p_w0.begin(), h.p_w0.end()), w1f(h.p_w1.begin(), h.p_w1.end());
+    d.p_w0f = up(w0f); d.p_w1f = up(w1f);
+    // packed restriction lists (csrc/kernels.cuh restrict4_kernel): possible when no coarse index gathers more than four fine ones
+    const int nc = (int)h.r_ptr.size() - 1;
+    bool ok = nc > 0;
+    for (int I = 0; I < nc && ok; ++I) ok = h.r_ptr[I + 1] - h.r_ptr[I] <= 4;
+    d.r4 = nullptr;
+    if (ok) {
+      std::vector<RList4> packed(nc);
+      for (int I = 0; I < nc; ++I) {
+        const int k0 = h.r_ptr[I], cnt = h.r_ptr[I + 1] - k0;
+        for (int q = 0; q < 4; ++q) {
+          packed[I].idx[q] = cnt > 0 ? h.r_idx[k0 + std::min(q, cnt - 1)] : 0;
+          packed[I].w[q] = q < cnt ? (float)h.r_w[k0 + q] : 0.0f;
+        }
+      }
+      d.r4 = up(packed);
+    }
   }
   int keep_of(int keep_target) const { return keep_target; }
 
