@@ -244,6 +244,10 @@ int b200ms_debug_setup(const b200ms_problem *prob, double *sigma, int *flags, do
 int b200ms_debug_hierarchy(const b200ms_problem *prob, const b200ms_options *opt, int max_levels,
                            int *shapes);
 
+/* launch geometry of the pair-marching stencil kernels (csrc/march2.cuh) for an nx x ny level of `nbatch` problems on a device
+ * that keeps `resident_ctas` of them resident: threads per CTA (column pairs per strip), strips per row, rows marched per CTA */
+int b200ms_debug_march2_geometry(int nx, int ny, int nbatch, int resident_ctas, int *cta_width, int *nstrips, int *rows);
+
 /* ---- device debug hooks (GPU tests compare these against the numpy model) ------------------- */
 /* y = (A - sigma) x on level `level` of the hierarchy of `prob`; x,y complex128 2*nxl*nyl */
 int b200ms_debug_apply(b200ms_handle *h, const b200ms_problem *prob, int level, int mode,

@@ -14,7 +14,7 @@ def test_abi_exports_every_declared_symbol(built_lib):
     import os
 
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "b200ms.h")).read()
-    declared = sorted(set(re.findall(r"\b(b200ms_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(b200ms_[a-z0-9_]+)\s*\(", hdr)))
     L = built_lib.lib()
     assert set(declared) == set(built_lib.EXPORTS)
     for sym in declared:
@@ -180,3 +180,33 @@ def test_section_rasterisation_host_mirror(built_lib):
     assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0], b[0])
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
     assert np.abs(b[5][0].reshape(23, 30) - eps[0]).max() < 1e-14  # exx of the set-up is the sampled eps_xx (no Jacobian here)
+
+
+def test_pair_kernel_strip_geometry_covers_every_column_pair_once(built_lib):
+    """Launch geometry of the pair-marching stencil kernels (csrc/march2.cuh march2_strips / march2_rows, the rule the kernels
+    apply on the device restated here): every column pair of a row is an output of exactly one strip, CTA widths are whole warps,
+    a row that fits one CTA has no halo pairs, and the march length is 6 m - 3 rows (the row loop is unrolled six-fold)."""
+    import ctypes as C
+
+    L = built_lib.lib()
+    W, S, R = C.c_int(), C.c_int(), C.c_int()
+    for ny in list(range(8, 700, 2)) + [1024, 1100, 2048, 4096, 5000]:
+        assert L.b200ms_debug_march2_geometry(512, ny, 64, 296, C.byref(W), C.byref(S), C.byref(R)) == 0
+        w, s, npairs = W.value, S.value, ny // 2
+        assert w % 32 == 0 and 32 <= w <= 256
+        owners = [0] * npairs
+        for i in range(s):
+            for c in range(w):
+                q = i * (w - 2) + c
+                if q < npairs and (c >= 1 or i == 0) and (c <= w - 2 or q == npairs - 1):
+                    owners[q] += 1
+        assert owners == [1] * npairs, (ny, w, s)
+        if npairs <= w:
+            assert s == 1
+    for nx, nb, res in ((512, 64, 296), (512, 32, 296), (256, 64, 592), (128, 64, 1184), (40, 1, 296), (33, 7, 148)):
+        assert L.b200ms_debug_march2_geometry(nx, 512, nb, res, C.byref(W), C.byref(S), C.byref(R)) == 0
+        assert (R.value + 3) % 6 == 0 and 9 <= R.value <= 69
+    # the headline level: 64 problems of 512 x 512 on 296 resident CTAs -> 9 CTAs of 57 rows per problem = 576 CTAs, two full waves
+    assert L.b200ms_debug_march2_geometry(512, 512, 64, 296, C.byref(W), C.byref(S), C.byref(R)) == 0
+    assert (W.value, S.value, R.value) == (256, 1, 57)
+    assert L.b200ms_debug_march2_geometry(512, 511, 64, 296, C.byref(W), C.byref(S), C.byref(R)) != 0  # odd widths use the one-column kernel

@@ -1060,6 +1060,13 @@ extern "C" int b200ms_debug_hierarchy(const b200ms_problem *prob, const b200ms_o
   return (int)plan.nx.size();
 }
 
+extern "C" int b200ms_debug_march2_geometry(int nx, int ny, int nbatch, int resident_ctas, int *cta_width, int *nstrips, int *rows) {
+  if (nx < 1 || ny < 2 || (ny & 1) || nbatch < 1 || !cta_width || !nstrips || !rows) return B200MS_ERR_ARG;
+  march2_strips(ny, *cta_width, *nstrips);
+  *rows = march2_rows(nx, *nstrips, nbatch, resident_ctas);
+  return B200MS_OK;
+}
+
 // ---- device debug hooks -------------------------------------------------------------------------------
 namespace {
 template <typename T, typename C, typename P, typename PC>

@@ -10,7 +10,7 @@
 // (Little's law: ~40 KB in flight per SM at 7.7 TB/s).  A stage is refilled by the elected thread right after the
 // __syncthreads that ends the step which consumed it (the march needs that barrier anyway), so no "empty" barriers exist.
 // Requirements beyond the register version: ny % 4 == 0 (16-byte aligned row slices).  MODE_JACOBI_D0 stays with the register
-// version.  A wait that does not complete within ~2^21 polls traps instead of hanging the device.
+// version.  A wait that does not complete within ~2^24 polls traps instead of hanging the device.
 #pragma once
 
 namespace b200ms {
@@ -39,7 +39,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 21)) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
