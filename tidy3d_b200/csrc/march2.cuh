@@ -34,12 +34,9 @@ constexpr int kM2MaxW = 256;      // threads per CTA (column pairs per strip)
 constexpr int kM2MaxSteps = 72;   // row steps per CTA (rows per CTA + 3), multiple of 6
 constexpr int kM2Unroll = 6;
 
-// Strip geometry (host and device agree on it): strip i covers the column pairs [i (W-2), i (W-2) + W); a pair is an output
-// of its strip unless it is the strip's first pair (except in strip 0) or its last pair (except when it is the last pair of
-// the row).  One strip of W >= ny/2 threads has no halo pairs at all.
-struct March2Geom {
-  int W, nstrips, rows;  // threads per CTA, strips per row, rows marched per CTA (rows + 3 is a multiple of 6)
-};
+// Strip geometry (host and device agree on it; tests/test_host_logic.py restates the rule): strip i covers the column pairs
+// [i (W-2), i (W-2) + W); a pair is an output of its strip unless it is the strip's first pair (except in strip 0) or its last pair
+// (except when it is the last pair of the row).  One strip of W >= ny/2 threads has no halo pairs at all.
 
 template <typename T, int MODE, int PF>
 __global__ void __launch_bounds__(kM2MaxW, 2) stencil_march2_kernel(StencilArgs<T, T> a, int rows) {
@@ -137,7 +134,6 @@ __global__ void __launch_bounds__(kM2MaxW, 2) stencil_march2_kernel(StencilArgs<
 #pragma unroll
     for (int u = 0; u < kM2Unroll; ++u) {
       const int j = j0 + u, k = k0 + j;
-      constexpr int dummy = 0; (void)dummy;
       const int s = u & 1, sp = s ^ 1;
       const int slot = u % PF;
       // step 0: row k+2 out of the prefetch registers; issue the loads of row k+2+PF and of the rhs of row k+PF

@@ -151,7 +151,6 @@ __global__ void __launch_bounds__(kM2MaxW, 2) stencil_march2_tma_kernel(StencilA
     for (int u = 0; u < kM2Unroll; ++u) {
       const int j = j0 + u, k = k0 + j;
       const int s = u & 1, sp = s ^ 1;
-      constexpr int dummy = 0; (void)dummy;
       const int stage = u % D;
       const unsigned parity = (parity0 + (unsigned)(u / D)) & 1u;
       const int gr = k + 2;
