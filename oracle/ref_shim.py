@@ -2,9 +2,12 @@
 
 Imports ``tidy3d/plugins/mode/{solver,derivatives,transforms}.py`` straight from
 ``/root/reference`` under a stub package (full ``import tidy3d`` needs xarray/shapely/... which
-this image lacks; recipe from SURVEY.md Appendix C).  Only usable in the build container: the GPU
-box has no ``/root/reference``.  Used to (a) pin ``oracle/restatement.py`` and (b) generate the
-golden fixtures under ``tests/golden`` (``tests/golden/make_golden.py``).
+this image lacks; recipe from SURVEY.md Appendix C).  Where ``/root/reference`` does not exist (the
+GPU box) the same four files are loaded from their byte-compiled form under ``oracle/_ref``
+(``oracle/build_ref.py``: sourceless ``.pyc``, nothing of the reference is copied into the repository).
+Used to (a) pin ``oracle/restatement.py``, (b) generate the golden fixtures under ``tests/golden``
+(``tests/golden/make_golden.py``) and (c) as the CPU arm of ``bench.py`` (``cpu_baseline.kind ==
+"reference"``).
 
 Nothing under ``tidy3d_b200/`` may import this module.
 """
@@ -18,10 +21,30 @@ import numpy as np
 
 REF_ROOT = os.environ.get("B200MS_REFERENCE", "/root/reference")
 _REF = os.path.join(REF_ROOT, "tidy3d")
+_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "tidy3d")
+
+
+def source_available() -> bool:
+    return os.path.isfile(os.path.join(_REF, "plugins", "mode", "solver.py"))
+
+
+def built_available() -> bool:
+    """``oracle/_ref`` holds byte code made by THIS interpreter version (oracle/build_ref.py)."""
+    path = os.path.join(_BUILT, "plugins", "mode", "solver.pyc")
+    try:
+        with open(path, "rb") as f:
+            return f.read(4) == importlib.util.MAGIC_NUMBER
+    except OSError:
+        return False
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(_REF, "plugins", "mode", "solver.py"))
+    return source_available() or built_available()
+
+
+def origin() -> str:
+    """Where the reference code comes from: "source" (/root/reference), "built" (oracle/_ref) or "none"."""
+    return "source" if source_available() else "built" if built_available() else "none"
 
 
 def _mod(name, path=None):
@@ -46,12 +69,13 @@ def load():
     if _loaded is not None:
         return _loaded
     if not available():
-        raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+        raise RuntimeError(f"reference tree not found under {REF_ROOT} and oracle/_ref is not built")
+    root, ext = (_REF, ".py") if source_available() else (_BUILT, ".pyc")
     if "tidy3d" in sys.modules and not getattr(sys.modules["tidy3d"], "_b200_shim", False):
         raise RuntimeError("a real 'tidy3d' is already imported; refusing to shadow it")
     for pkg in ("tidy3d", "tidy3d.components", "tidy3d.plugins", "tidy3d.plugins.mode"):
         _mod(pkg)._b200_shim = True
-    _mod("tidy3d.constants", f"{_REF}/constants.py")
+    _mod("tidy3d.constants", f"{root}/constants{ext}")
     base = _mod("tidy3d.components.base")
     base.Tidy3dBaseModel = type("Tidy3dBaseModel", (), {})
     typ = _mod("tidy3d.components.types")
@@ -59,9 +83,9 @@ def load():
     typ.Numpy = np.ndarray
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        _mod("tidy3d.plugins.mode.derivatives", f"{_REF}/plugins/mode/derivatives.py")
-        _mod("tidy3d.plugins.mode.transforms", f"{_REF}/plugins/mode/transforms.py")
-        _loaded = _mod("tidy3d.plugins.mode.solver", f"{_REF}/plugins/mode/solver.py")
+        _mod("tidy3d.plugins.mode.derivatives", f"{root}/plugins/mode/derivatives{ext}")
+        _mod("tidy3d.plugins.mode.transforms", f"{root}/plugins/mode/transforms{ext}")
+        _loaded = _mod("tidy3d.plugins.mode.solver", f"{root}/plugins/mode/solver{ext}")
     return _loaded
 
 

@@ -1,5 +1,7 @@
 """CPU: the oracle restatement is pinned to the reference -- golden fixtures (generated from the unmodified
 reference), the reference's own exact known-answer test, and, in the build container, the reference itself."""
+import os
+
 import numpy as np
 import pytest
 
@@ -7,6 +9,8 @@ from oracle import ref_shim
 from oracle import restatement as R
 from tests.golden.cases import CASES, resolve_kwargs
 from tests.helpers import load_golden, mode_overlaps, signature
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 FAST = ["c1_64", "c1_64_minus", "c1_64_sym_pmc_pec", "lossy_48", "nonuniform_56", "slab1d_x1", "slab1d_y1",
         "angled_48_minus", "angled_phi_48", "offdiag_48", "c3_96", "c4_96", "c4_96_axis0", "strip_128_m4", "pec_block_40", "lossy_angled_40", "lossy_angled_40_minus", "angle_bend_44",
@@ -107,3 +111,39 @@ def test_reference_pml_factors_match():
             a = der.create_sfactor_b(2e15, dls, 30, n_pml, dmin, (0.6, 0.7))
             b = R.sfactor("b", 2e15, dls, 30, n_pml, dmin, (0.6, 0.7))
             assert np.allclose(a, b, rtol=1e-14)
+
+
+def test_built_reference_loads_without_the_source_tree(tmp_path):
+    """oracle/_ref (byte-compiled by oracle/build_ref.py) is the reference itself: loaded with /root/reference hidden, in a
+    clean interpreter, it reproduces the golden made from the source tree to the last bit of the ARPACK run."""
+    import json
+    import subprocess
+    import sys
+
+    from oracle import build_ref
+
+    if not build_ref.build():
+        pytest.skip("no reference tree here and no oracle/_ref shipped")
+    man = json.load(open(build_ref.manifest_path()))
+    assert set(man["sha256"]) == set(build_ref.FILES)
+    if ref_shim.source_available():  # build container: the byte code was made from exactly the files under /root/reference
+        import hashlib
+
+        for f, sha in man["sha256"].items():
+            assert hashlib.sha256(open(os.path.join(ref_shim.REF_ROOT, "tidy3d", f), "rb").read()).hexdigest() == sha
+    code = (
+        "import numpy as np, sys\n"
+        "from oracle import ref_shim\n"
+        "from tests.golden.cases import CASES\n"
+        "assert ref_shim.origin() == 'built', ref_shim.origin()\n"
+        "fac, kw, _ = CASES['c1_64']\n"
+        "wl = fac()\n"
+        "f, n, s = ref_shim.compute_modes(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, **kw)\n"
+        "assert sys.modules['tidy3d.plugins.mode.solver'].__file__.endswith('.pyc')\n"
+        "np.save(sys.argv[1], n)\n"
+    )
+    out = str(tmp_path / "n.npy")
+    env = dict(os.environ, B200MS_REFERENCE=str(tmp_path / "no_reference_here"), PYTHONPATH=ROOT)
+    subprocess.run([sys.executable, "-c", code, out], check=True, cwd=ROOT, env=env, timeout=300)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_64.npz"))
+    assert np.abs(np.load(out) - g["n_ref"]).max() < 1e-12
