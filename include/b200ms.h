@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200MS_VERSION 200
+#define B200MS_VERSION 201
 
 /* return codes */
 enum {
@@ -50,17 +50,40 @@ typedef struct b200ms_handle b200ms_handle;
 
 /* A cross-section described by geometry instead of a sampled permittivity array: what ModeSolver._solver_eps builds on the
  * host with nine Simulation.epsilon_on_grid calls per frequency (mode_solver.py:587-653, simulation.py:1135-1241) is
- * rasterised on the device.  Axis-aligned rectangles in the solver plane (the cut of Box structures), later entries
- * override earlier ones, staircased at the Yee E-sites exactly like epsilon_on_grid (eps_xx, eps_xy, eps_xz at the Ex site
- * (cell centre in x, lower boundary in y), eps_y* at the Ey site, eps_z* at the Ez site). */
+ * rasterised on the device.  epsilon_on_grid starts from the background medium and lets every structure, in order, overwrite
+ * the Yee sites its geometry contains (simulation.py:1191-1226); eps_xx, eps_xy, eps_xz are sampled at the Ex site (cell
+ * centre in x, lower boundary in y), eps_y* at the Ey site, eps_z* at the Ez site (simulation.py:1231-1236).  Two ways to say
+ * where the media are, which may be combined:
+ *   - a list of primitive shapes in the solver plane (the cuts of Box / Cylinder / Sphere / PolySlab structures), later
+ *     entries override earlier ones;
+ *   - `site_medium`, a per-site medium index the CALLER evaluated once per plane with the reference's own
+ *     Geometry.inside_meshgrid (any geometry: the map does not depend on the frequency); the listed shapes then draw on
+ *     top of it.  Either way only 9 numbers per medium change from one frequency to the next. */
+enum {
+  B200MS_SHAPE_RECT = 0,    /* row: center_x, center_y, size_x, size_y; inside when |x - cx| <= sx/2 and |y - cy| <= sy/2
+                               (Box.inside, components/geometry/base.py:2042-2068) */
+  B200MS_SHAPE_DISC = 1,    /* row: center_x, center_y, radius, dz; inside when |x-cx|^2 + |y-cy|^2 + dz^2 <= radius^2: the cut of a
+                               Cylinder whose axis is the plane normal (dz = 0; Cylinder.inside, geometry/primitives.py:600-632) or
+                               of a Sphere whose centre lies dz off the plane (Sphere.inside, primitives.py:44-70) */
+  B200MS_SHAPE_POLYGON = 2  /* row unused; vertices poly_xy[poly_start[i] .. poly_start[i+1]): the cut of a PolySlab whose axis is the
+                               plane normal (vertical side walls), or the trapezoid a slanted-wall slab shows in a plane containing
+                               its axis.  Even-odd crossing rule; like the reference's matplotlib Path.contains_points
+                               (polyslab.py:509-516) the result for a point exactly ON an edge is unspecified */
+};
 typedef struct {
-  int nrect;
-  const double *rects;     /* nrect x 4: center_x, center_y, size_x, size_y; a site is inside when |x - cx| <= sx/2 and
-                              |y - cy| <= sy/2 (Box.inside, components/geometry/base.py:2042-2068) */
-  const int *medium;       /* nrect: row of eps_table used inside each rectangle */
+  int nrect;               /* number of shapes */
+  const double *rects;     /* nrect x 4 doubles, meaning per shape kind above */
+  const int *medium;       /* nrect: row of eps_table used inside each shape */
   int nmedia;              /* rows of eps_table; row 0 is the background medium */
   const double *eps_table; /* nmedia x 9 complex128 (re,im): relative permittivity tensor (xx,xy,...,zz) of each medium AT THIS
                               PROBLEM'S FREQUENCY (dispersive media are evaluated by the caller: 9 numbers per medium) */
+  /* ---- since version 201 (all may be NULL: a list of rectangles, as in version 200) ---- */
+  const int *shape;        /* NULL (every shape is a rectangle) or nrect kinds B200MS_SHAPE_* */
+  const int *poly_start;   /* NULL without polygons, else nrect + 1 offsets (in vertices) into poly_xy */
+  const double *poly_xy;   /* polygon vertices, (x, y) pairs in plane coordinates */
+  const unsigned short *site_medium; /* NULL, or 3*nx*ny medium indices [Ex sites | Ey sites | Ez sites], each C-order with y fastest:
+                              the medium found at every Yee site before the listed shapes are drawn (replaces "background
+                              everywhere").  Indices >= nmedia are a caller error (clamped to nmedia - 1 on the device) */
 } b200ms_section;
 
 /* One eigenproblem == one compute_modes call (one plane, one frequency). */

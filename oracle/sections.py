@@ -1,7 +1,33 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of the permittivity sampling ``ModeSolver._solver_eps`` performs for a
-cross-section made of boxes (mode_solver.py:587-653 -> Simulation.epsilon_on_grid, simulation.py:1135-1241; Box.inside,
-components/geometry/base.py:2042-2068).  PARITY UNPINNED: needs the full tidy3d package to run the reference itself."""
+cross-section (mode_solver.py:587-653 -> Simulation.epsilon_on_grid, simulation.py:1135-1241) whose structures cut the
+plane as boxes (Box.inside, components/geometry/base.py:2042-2068), discs (Cylinder.inside / Sphere.inside,
+geometry/primitives.py:600-632, 44-70) or polygons (PolySlab.inside, geometry/polyslab.py:464-546), or whose inside-masks
+were evaluated beforehand.  PARITY UNPINNED: needs the full tidy3d package (and, for polygons, matplotlib) to run the
+reference itself."""
 import numpy as np
+
+
+def inside(shape, sx, sy):
+    """Boolean (len(sx), len(sy)) array: the sites (sx[i], sy[j]) the structure's cut contains."""
+    kind = type(shape).__name__
+    X, Y = np.meshgrid(np.asarray(sx, float), np.asarray(sy, float), indexing="ij")
+    if kind == "Rect":  # base.py:2062-2068: dist <= size / 2 on every axis
+        return (np.abs(X - shape.center[0]) <= shape.size[0] / 2) & (np.abs(Y - shape.center[1]) <= shape.size[1] / 2)
+    if kind == "Disc":  # primitives.py:66-70 / :624-632
+        dist_x, dist_y, dist_z = np.abs(X - shape.center[0]), np.abs(Y - shape.center[1]), np.abs(shape.dz)
+        return (dist_x**2 + dist_y**2 + dist_z**2) <= (shape.radius**2)
+    if kind == "Polygon":
+        # polyslab.py:509-516 asks matplotlib's Path.contains_points; restated as the winding number of the polygon around the
+        # point being non-zero (equal to the even-odd rule for the simple polygons a PolySlab accepts); sites exactly on an
+        # edge are unspecified there and here
+        v = np.asarray(shape.vertices, float)
+        wn = np.zeros(X.shape, int)
+        for (x0, y0), (x1, y1) in zip(v, np.roll(v, -1, axis=0)):
+            left = (x1 - x0) * (Y - y0) - (X - x0) * (y1 - y0)  # > 0: the point is left of the directed edge
+            wn += ((y0 <= Y) & (y1 > Y) & (left > 0)).astype(int)
+            wn -= ((y0 > Y) & (y1 <= Y) & (left < 0)).astype(int)
+        return wn != 0
+    raise TypeError(kind)
 
 
 def eps_on_grid(section, coords, freq):
@@ -15,8 +41,10 @@ def eps_on_grid(section, coords, freq):
     for row, (sx, sy) in enumerate(sites):
         for col in range(3):
             arr = np.full((sx.size, sy.size), section.background.tensor(freq)[row, col], complex)
-            for rect, med in section.structures:
-                inside = (np.abs(sx - rect.center[0]) <= rect.size[0] / 2)[:, None] & (np.abs(sy - rect.center[1]) <= rect.size[1] / 2)[None, :]
-                arr[inside] = med.tensor(freq)[row, col]
+            if getattr(section, "site_medium", None) is not None:  # inside-masks evaluated beforehand, one medium index per site
+                for k, med in enumerate(section.media):
+                    arr[np.asarray(section.site_medium)[row] == k] = med.tensor(freq)[row, col]
+            for shape, med in section.structures:
+                arr[inside(shape, sx, sy)] = med.tensor(freq)[row, col]
             out[3 * row + col] = arr
     return out

@@ -19,7 +19,7 @@ def test_abi_exports_every_declared_symbol(built_lib):
     assert set(declared) == set(built_lib.EXPORTS)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert L.b200ms_version() == 200
+    assert L.b200ms_version() == 201
 
 
 def test_ctypes_structs_mirror_the_header(built_lib):
@@ -180,6 +180,148 @@ def test_section_rasterisation_host_mirror(built_lib):
     assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0], b[0])
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
     assert np.abs(b[5][0].reshape(23, 30) - eps[0]).max() < 1e-14  # exx of the set-up is the sampled eps_xx (no Jacobian here)
+
+
+def _setup_of(built_lib, pk):
+    nx, ny = pk.nx, pk.ny
+    sigma = np.zeros(2)
+    flags = (C.c_int * 4)()
+    tgt, kn = C.c_double(), C.c_double()
+    cx, cy, f = np.zeros(4 * nx, complex), np.zeros(4 * ny, complex), np.zeros((6, nx * ny), complex)
+    rc = built_lib.lib().b200ms_debug_setup(C.byref(pk.struct), built_lib._ptr(sigma), flags, C.byref(tgt), C.byref(kn),
+                                            built_lib._ptr(cx.view(float)), built_lib._ptr(cy.view(float)), built_lib._ptr(f.view(float)))
+    return rc, (sigma.copy(), list(flags), tgt.value, cx, cy, f)
+
+
+def _yee_sites(x, y):
+    xc, yc = (x[:-1] + x[1:]) / 2, (y[:-1] + y[1:]) / 2
+    return [(xc, y[:-1]), (x[:-1], yc), (x[:-1], y[:-1])]  # Ex, Ey, Ez
+
+
+def test_section_shapes_and_site_map_host_mirror(built_lib):
+    """Discs, polygons and the caller-made site map (b200ms_section since v201) through the host mirror of
+    section_raster_kernel, against the numpy restatement of epsilon_on_grid: a fibre-like disc, a slanted-wall trapezoid, a
+    concave polygon and a sphere cut, on a non-uniform grid, drawn in order over a site map that holds a slab."""
+    from oracle import sections as OS
+    from tidy3d_b200 import workloads as W
+    from tidy3d_b200.sections import Disc, Medium, Polygon, Rect, Section, site_medium_from_masks
+
+    rng = np.random.default_rng(11)
+    x = np.cumsum(np.r_[-1.1, rng.uniform(0.03, 0.07, 44)])
+    y = np.cumsum(np.r_[-0.9, rng.uniform(0.03, 0.06, 40)])
+    nx, ny = x.size - 1, y.size - 1
+    bg, slab, core, clad2 = Medium(1.44**2), Medium([4.0, 4.2, 3.9]), Medium(lambda f: 12.0 + 1e-15 * f), Medium(2.1 + 0.01j)
+    slab_rect = Rect((0.0, -0.5), (5.0, 0.3))
+    masks = np.stack([OS.inside(slab_rect, sx, sy) for sx, sy in _yee_sites(x, y)])
+    site = site_medium_from_masks((nx, ny), [(masks, 1)])
+    assert site.dtype == np.uint16 and 0 < site.sum() < site.size
+    trapezoid = Polygon([(-0.25, -0.35), (0.25, -0.35), (0.17, -0.13), (-0.17, -0.13)])  # 70-degree side walls
+    concave = Polygon([(0.5, 0.0), (0.9, 0.0), (0.9, 0.4), (0.7, 0.15), (0.5, 0.4)][::-1])  # clockwise on purpose
+    sec = Section(background=bg, media=[bg, slab], site_medium=site, structures=[
+        (Disc((-0.55, 0.2), 0.23), core),
+        (trapezoid, core),
+        (concave, clad2),
+        (Disc((0.1, 0.35), 0.2, dz=0.12), clad2),  # sphere of radius 0.2 whose centre is 0.12 off the plane
+        (Rect((-0.55, 0.2), (0.1, 0.1)), bg),      # a later box punches a hole into the disc
+    ])
+    spec = W.ModeSpecLike(num_modes=2, num_pml=(0, 0))
+    freq = W.C_0 / 1.3
+    eps = OS.eps_on_grid(sec, [x, y], freq)
+    # the restatement really drew every shape: each medium is present, and the disc has the area of a disc
+    for m in (bg, slab, core, clad2):
+        assert (eps[8] == m.tensor(freq)[2, 2]).any()
+    only_disc = OS.eps_on_grid(Section(background=bg, structures=[(Disc((-0.55, 0.2), 0.23), core)]), [x, y], freq)[8]
+    cell_area = np.outer(np.diff(x), np.diff(y))
+    assert abs(cell_area[only_disc != bg.tensor(freq)[2, 2]].sum() - np.pi * 0.23**2) < 0.1 * np.pi * 0.23**2
+    rc_a, a = _setup_of(built_lib, built_lib.PackedProblem(None, [x, y], freq, spec, section=sec))
+    rc_b, b = _setup_of(built_lib, built_lib.PackedProblem(eps, [x, y], freq, spec))
+    assert rc_a == 0 and rc_b == 0
+    assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0], b[0])
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+    assert np.abs(b[5][0].reshape(nx, ny) - eps[0]).max() < 1e-14 and np.abs(b[5][2].reshape(nx, ny) - eps[8]).max() < 1e-14
+
+
+def test_section_site_map_alone_reproduces_any_sampled_geometry(built_lib):
+    """A site map made from arbitrary inside-masks (here: random blobs no primitive could describe) gives exactly the array
+    the reference's sampling loop would: background, then every structure's mask in order (simulation.py:1199-1226)."""
+    from tidy3d_b200 import workloads as W
+    from tidy3d_b200.sections import Medium, Section, site_medium_from_masks
+
+    rng = np.random.default_rng(5)
+    nx, ny = 31, 26
+    x, y = np.linspace(-1, 1, nx + 1), np.linspace(-0.8, 0.8, ny + 1)
+    media = [Medium(2.0), Medium(11.7 + 0.1j), Medium(np.array([[4.0, 0.1, 0], [0.1, 4.2, 0], [0, 0, 3.9]]))]
+    masks = [(rng.random((3, nx, ny)) < 0.3, 1), (rng.random((3, nx, ny)) < 0.2, 2), (rng.random((3, nx, ny)) < 0.05, 0)]
+    site = site_medium_from_masks((nx, ny), masks)
+    freq = W.C_0 / 1.55
+    want = np.zeros((9, nx, ny), complex)
+    for row in range(3):
+        for col in range(3):
+            arr = np.full((nx, ny), media[0].tensor(freq)[row, col])
+            for inside, k in masks:
+                arr[inside[row]] = media[k].tensor(freq)[row, col]
+            want[3 * row + col] = arr
+    spec = W.ModeSpecLike(num_modes=1)
+    sec = Section(background=media[0], media=media, site_medium=site)
+    rc_a, a = _setup_of(built_lib, built_lib.PackedProblem(None, [x, y], freq, spec, section=sec))
+    rc_b, b = _setup_of(built_lib, built_lib.PackedProblem(want, [x, y], freq, spec))
+    assert rc_a == 0 and rc_b == 0 and a[1] == b[1] and a[1][1] == 1  # tensorial (off-diagonal medium)
+    assert a[2] == b[2] and np.array_equal(a[0], b[0]) and np.array_equal(a[5], b[5])
+
+
+def test_gpu_section_case_host_mirror_equals_restatement(built_lib):
+    """The cross-section of the GPU test (tests/test_gpu_sections.py shapes_section) through the host mirror: the rasteriser
+    and the restatement agree on every site, so on the GPU box only the device arithmetic is left to check; no site sits
+    within 1e-9 of a shape boundary (where the reference itself is unspecified for polygons)."""
+    from oracle import sections as OS
+    from tests.test_gpu_sections import shapes_section
+    from tidy3d_b200 import workloads as W
+
+    sec, c = shapes_section()
+    spec = W.ModeSpecLike(num_modes=3, precision="double")
+    freq = float(W.sweep_freqs(3)[1])
+    eps = OS.eps_on_grid(sec, [c, c], freq)
+    rc_a, a = _setup_of(built_lib, built_lib.PackedProblem(None, [c, c], freq, spec, section=sec))
+    rc_b, b = _setup_of(built_lib, built_lib.PackedProblem(eps, [c, c], freq, spec))
+    assert rc_a == 0 and rc_b == 0 and a[1] == b[1] and np.array_equal(a[5], b[5]) and a[2] == b[2]
+    import dataclasses
+
+    for shape, _ in sec.structures:  # shrinking / growing every shape by 1e-9 must not move a site across its boundary
+        for sx, sy in _yee_sites(c, c):
+            if type(shape).__name__ == "Polygon":
+                v = np.asarray(shape.vertices)
+                ctr = v.mean(axis=0)
+                lo, hi = (dataclasses.replace(shape, vertices=ctr + (v - ctr) * k) for k in (1 - 1e-8, 1 + 1e-8))
+            elif type(shape).__name__ == "Disc":
+                lo, hi = (dataclasses.replace(shape, radius=shape.radius * k) for k in (1 - 1e-8, 1 + 1e-8))
+            else:
+                lo, hi = (dataclasses.replace(shape, size=(shape.size[0] * k, shape.size[1] * k)) for k in (1 - 1e-8, 1 + 1e-8))
+            assert np.array_equal(OS.inside(lo, sx, sy), OS.inside(hi, sx, sy))
+
+
+def test_section_validation(built_lib):
+    from tidy3d_b200 import workloads as W
+    from tidy3d_b200.sections import Medium, Polygon, Rect, Section
+
+    x = np.linspace(-1, 1, 17)
+    spec = W.ModeSpecLike(num_modes=1)
+    bg = Medium(2.0)
+    with pytest.raises(ValueError, match="site_medium refers to medium"):
+        built_lib.PackedProblem(None, [x, x], 2e14, spec, section=Section(bg, site_medium=np.ones((3, 16, 16), int)))
+    with pytest.raises(ValueError, match="Mismatch between 'coords' and 'site_medium'"):
+        built_lib.PackedProblem(None, [x, x], 2e14, spec, section=Section(bg, site_medium=np.zeros((3, 15, 16), int)))
+    with pytest.raises(ValueError, match="Polygon.vertices"):
+        built_lib.PackedProblem(None, [x, x], 2e14, spec, section=Section(bg, structures=[(Polygon([(0, 0), (1, 1)]), bg)]))
+    # the library itself rejects descriptions whose indices it could not follow (B200MS_ERR_ARG), whatever the Python layer checked
+    pk = built_lib.PackedProblem(None, [x, x], 2e14, spec, section=Section(bg, structures=[(Rect((0, 0), (1, 1)), Medium(3.0))]))
+    pk._section_arrays[1][0] = 7  # medium index out of range
+    rc, _ = _setup_of(built_lib, pk)
+    assert rc == built_lib.ERR_ARG
+    pk._section_arrays[1][0] = 1
+    kinds = np.array([2], dtype=np.int32)  # a polygon without vertices
+    pk.section.shape = kinds.ctypes.data_as(built_lib._ip)
+    rc, _ = _setup_of(built_lib, pk)
+    assert rc == built_lib.ERR_ARG
 
 
 def test_pair_kernel_strip_geometry_covers_every_column_pair_once(built_lib):

@@ -110,3 +110,150 @@ def test_group_index_formula():
     assert np.allclose(ng[:, 0], a + 2 * b * f0 + 3 * c * f0**2, rtol=1e-12)
     d2 = 2 * c
     assert np.allclose(disp[:, 0], -(f0 / 2.99792458e14) ** 2 * (2 * (b + 2 * c * f0) + f0 * d2) * 1e18, rtol=1e-6)
+
+
+class _Coords:
+    def __init__(self, x, y, z):
+        self.x, self.y, self.z = x, y, z
+
+
+class _BoxGeom:
+    """Stand-in geometry with the reference's Geometry.inside_meshgrid contract (geometry/base.py:172-201)."""
+
+    def __init__(self, center, size):
+        self.center, self.size = np.array(center, float), np.array(size, float)
+
+    def inside_meshgrid(self, x, y, z):
+        X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+        return ((np.abs(X - self.center[0]) <= self.size[0] / 2) & (np.abs(Y - self.center[1]) <= self.size[1] / 2)
+                & (np.abs(Z - self.center[2]) <= self.size[2] / 2))
+
+
+class _BallGeom:
+    def __init__(self, center, radius):
+        self.center, self.radius = np.array(center, float), radius
+
+    def inside_meshgrid(self, x, y, z):
+        X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+        return (X - self.center[0]) ** 2 + (Y - self.center[1]) ** 2 + (Z - self.center[2]) ** 2 <= self.radius**2
+
+
+class _TensorMedium:
+    def __init__(self, t, slope=0.0):
+        self.t, self.slope = np.asarray(t, complex), slope
+
+    def eps_comp(self, row, col, frequency):
+        return self.t[row, col] * (1 + self.slope * (frequency / 2e14 - 1))
+
+    def __eq__(self, other):
+        return isinstance(other, _TensorMedium) and np.array_equal(self.t, other.t) and self.slope == other.slope
+
+
+class _Structure:
+    def __init__(self, geometry, medium):
+        self.geometry, self.medium = geometry, medium
+
+    def eps_comp(self, row, col, frequency, coords):  # structure.py:279-300
+        return self.medium.eps_comp(row, col, frequency)
+
+
+class _PlaneSolver:
+    """The part of ModeSolver that feeds the solver its permittivity, written out literally from the reference:
+    _get_epsilon (mode_solver.py:587-593) -> Simulation.epsilon_on_grid (simulation.py:1179-1236) for the nine keys, then
+    _tensorial_material_profile_modal_plane_tranform (:594-624)."""
+
+    def __init__(self, normal_axis, bounds, n, structures, background):
+        self.normal_axis = normal_axis
+        edges = [np.linspace(lo, hi, k + 1) for (lo, hi), k in zip(bounds, n)]
+        edges[normal_axis] = np.array([-0.01, 0.01])  # one cell along the normal
+        centers = [(e[:-1] + e[1:]) / 2 for e in edges]
+        lower = [e[:-1] for e in edges]
+        self._grid = {}
+        for a, key in enumerate(("Ex", "Ey", "Ez")):  # Yee E_a site: centre along a, lower cell boundary along the others
+            self._grid[key] = _Coords(*[centers[d] if d == a else lower[d] for d in range(3)])
+        self.edges = edges
+        self.simulation = types.SimpleNamespace(scene=types.SimpleNamespace(background_structure=_Structure(None, background)),
+                                                volumetric_structures=structures)
+        self.freqs = [1.9e14, 2.1e14]
+        self.mode_spec = types.SimpleNamespace(num_modes=1)
+        self.direction = "+"
+
+    @property
+    def _solver_grid(self):
+        return self._grid
+
+    def _epsilon_on_grid(self, coord_key, freq):
+        row = "xyz".index(coord_key[1])
+        col = row if len(coord_key) == 2 else "xyz".index(coord_key[2])
+        c = self._grid[coord_key[0:2]]
+        arrays = (np.array(c.x), np.array(c.y), np.array(c.z))
+        sim = self.simulation
+        eps_array = sim.scene.background_structure.eps_comp(row, col, freq, None) * np.ones(tuple(len(a) for a in arrays), dtype=complex)
+        for structure in sim.volumetric_structures:
+            is_inside = structure.geometry.inside_meshgrid(*arrays)
+            eps_array[is_inside] = structure.eps_comp(row, col, freq, None)
+        return eps_array
+
+    def _solver_eps(self, freq):
+        keys = ["Ex", "Exy", "Exz", "Eyx", "Ey", "Eyz", "Ezx", "Ezy", "Ez"]
+        mat_data = np.stack([self._epsilon_on_grid(k, freq) for k in keys], axis=0)
+        mat_tensor = np.take(mat_data, indices=[0], axis=1 + self.normal_axis)
+        mat_tensor = np.squeeze(mat_tensor, axis=1 + self.normal_axis)
+        flat_shape = np.shape(mat_tensor)
+        mat_tensor = mat_tensor.reshape([3, 3] + list(flat_shape[1:]))
+        if self.normal_axis == 0:
+            mat_tensor[[0, 1], :, ...] = mat_tensor[[1, 0], :, ...]
+            mat_tensor[:, [0, 1], ...] = mat_tensor[:, [1, 0], ...]
+        if self.normal_axis <= 1:
+            mat_tensor[[1, 2], :, ...] = mat_tensor[[2, 1], :, ...]
+            mat_tensor[:, [1, 2], ...] = mat_tensor[:, [2, 1], ...]
+        return mat_tensor.reshape(flat_shape)
+
+    def plane_coords(self):
+        return [self.edges[a] for a in range(3) if a != self.normal_axis]
+
+
+def test_section_of_reproduces_solver_eps_for_every_plane_orientation(built_lib):
+    """Seam 2b: the per-plane description built by plugin.section_of + the rasteriser give exactly the array
+    ModeSolver._solver_eps samples per frequency -- for the three plane normals (tensor rows / columns and Yee sites rotate
+    together), fully anisotropic dispersive media, overlapping structures, media shared between structures."""
+    import ctypes as C
+
+    import tidy3d_b200.plugin as plugin
+    from oracle import sections as OS
+
+    full = np.array([[4.0, 0.3, 0.1], [0.3, 4.4, 0.2j], [0.1, -0.2j, 3.7]])
+    si = _TensorMedium(np.diag([12.0, 12.1, 12.2]), slope=0.05)
+    for normal in (0, 1, 2):
+        structures = [
+            _Structure(_BoxGeom((0.05, -0.1, 0.0), (0.9, 0.5, 0.7)), _TensorMedium(full, slope=-0.02)),
+            _Structure(_BallGeom((0.2, 0.1, 0.05), 0.33), si),
+            _Structure(_BoxGeom((-0.3, 0.2, -0.2), (0.2, 0.3, 0.25)), _TensorMedium(np.diag([12.0, 12.1, 12.2]), slope=0.05)),  # equal medium, new object
+        ]
+        ms = _PlaneSolver(normal, [(-0.8, 0.9), (-0.7, 0.7), (-0.6, 0.75)], (17, 14, 15), structures, _TensorMedium(2.1 * np.eye(3)))
+        sec = plugin.section_of(ms)
+        assert len(sec.media) == 3  # background + two distinct media (the third structure re-uses silicon)
+        coords = ms.plane_coords()
+        for freq in ms.freqs:
+            want = ms._solver_eps(freq)
+            got = OS.eps_on_grid(sec, coords, freq)
+            assert got.shape == want.shape and np.array_equal(got, want)
+            # ... and the library's own rasteriser (host mirror of section_raster_kernel) sets the same problem up
+            outs = []
+            for pk in (built_lib.PackedProblem(None, coords, freq, ms.mode_spec, section=sec), built_lib.PackedProblem(want, coords, freq, ms.mode_spec)):
+                f = np.zeros((6, pk.nx * pk.ny), complex)
+                flags, sigma = (C.c_int * 4)(), np.zeros(2)
+                rc = built_lib.lib().b200ms_debug_setup(C.byref(pk.struct), built_lib._ptr(sigma), flags, None, None, None, None, built_lib._ptr(f.view(float)))
+                assert rc == 0
+                outs.append((list(flags), sigma.copy(), f))
+            assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    # the batched seam hands the section to the device call instead of nine arrays per frequency
+    plugin.DEVICE_EPS = True
+    try:
+        probs = plugin._problems(ms, coords, (0, 0))
+    finally:
+        plugin.DEVICE_EPS = False
+    assert all("eps_cross" not in p and p["section"] is probs[0]["section"] for p in probs) and len(probs) == 2
+    # custom (space-dependent) media keep the sampled-array path
+    structures[0].medium.eps_comp_on_grid = lambda *a, **k: None
+    assert plugin.section_of(ms) is None

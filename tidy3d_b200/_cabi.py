@@ -25,7 +25,8 @@ _ip = C.POINTER(C.c_int)
 
 
 class SectionStruct(C.Structure):
-    _fields_ = [("nrect", C.c_int), ("rects", _dp), ("medium", _ip), ("nmedia", C.c_int), ("eps_table", _dp)]
+    _fields_ = [("nrect", C.c_int), ("rects", _dp), ("medium", _ip), ("nmedia", C.c_int), ("eps_table", _dp),
+                ("shape", _ip), ("poly_start", _ip), ("poly_xy", _dp), ("site_medium", C.POINTER(C.c_ushort))]
 
 
 class Problem(C.Structure):
@@ -122,7 +123,7 @@ class PackedProblem:
                  mu_cross=None, target_override=None, incidence=False, post=0, section=None):
         self.section = None
         if section is not None:  # geometric cross-section rasterised on the device (tidy3d_b200/sections.py); no eps array
-            self.section, self._section_arrays = section.pack(float(freq))
+            self.section, self._section_arrays = section.pack(float(freq), (len(coords[0]) - 1, len(coords[1]) - 1))
             eps = None
         elif eps_packed is not None:
             eps = eps_packed

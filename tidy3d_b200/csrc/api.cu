@@ -212,6 +212,17 @@ struct Window {
   size_t h2d_bytes = 0;
 };
 
+// bytes of the raw buffer one geometric cross-section takes on the device (every array in its own 256-byte aligned sub-buffer)
+size_t section_device_bytes(const b200ms_section &sec, int nx, int ny) {
+  const int nv = (sec.poly_start && sec.nrect > 0) ? sec.poly_start[sec.nrect] : 0;
+  size_t b = align256((size_t)sec.nrect * 4 * sizeof(double)) + align256((size_t)sec.nrect * sizeof(int)) + align256((size_t)sec.nmedia * 9 * sizeof(cplx)) +
+             align256((size_t)(nx + 1) * sizeof(double)) + align256((size_t)(ny + 1) * sizeof(double));
+  if (sec.shape) b += align256((size_t)sec.nrect * sizeof(int));
+  if (nv > 0) b += align256((size_t)(sec.nrect + 1) * sizeof(int)) + align256((size_t)nv * 2 * sizeof(double));
+  if (sec.site_medium) b += align256((size_t)3 * nx * ny * sizeof(unsigned short));
+  return b;
+}
+
 void prepare_window(b200ms_handle *h, const b200ms_problem *prob, int i0, int i1, DevBuf &raw, cudaStream_t st, Window &W) {
   const int n = i1 - i0;
   W.i0 = i0;
@@ -248,11 +259,9 @@ void prepare_window(b200ms_handle *h, const b200ms_problem *prob, int i0, int i1
       off_d[q] = total;
       total += align256(2 * s.jz_e.size() * sizeof(double));
     }
-    if (!p.eps) {  // geometric cross-section: rectangles, medium ids, eps table, cell boundaries
-      const b200ms_section &sec = *p.section;
+    if (!p.eps) {  // geometric cross-section: shapes, medium ids, eps table, cell boundaries (+ shape kinds, polygon vertices, site map)
       off_sec[q] = total;
-      total += align256((size_t)sec.nrect * 4 * sizeof(double)) + align256((size_t)sec.nrect * sizeof(int)) +
-               align256((size_t)sec.nmedia * 9 * sizeof(cplx)) + align256((size_t)(p.nx + p.ny + 2) * sizeof(double));
+      total += section_device_bytes(*p.section, p.nx, p.ny);
     }
   }
   const int nslot = (int)seen.size();
@@ -275,20 +284,25 @@ void prepare_window(b200ms_handle *h, const b200ms_problem *prob, int i0, int i1
       W.h2d_bytes += 9 * N * sizeof(cplx);
     } else {  // rasterise the geometric cross-section on the device (f-2: replaces nine epsilon_on_grid calls + a 9N upload)
       const b200ms_section &sec = *p.section;
-      unsigned char *b0 = raw.p + off_sec[q];
-      double *d_rects = reinterpret_cast<double *>(b0);
-      int *d_med = reinterpret_cast<int *>(b0 + align256((size_t)sec.nrect * 4 * sizeof(double)));
-      cplx *d_tab = reinterpret_cast<cplx *>(reinterpret_cast<unsigned char *>(d_med) + align256((size_t)sec.nrect * sizeof(int)));
-      double *d_xy = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(d_tab) + align256((size_t)sec.nmedia * 9 * sizeof(cplx)));
-      if (sec.nrect > 0) {
-        CUDA_CHECK(cudaMemcpyAsync(d_rects, sec.rects, (size_t)sec.nrect * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaMemcpyAsync(d_med, sec.medium, (size_t)sec.nrect * sizeof(int), cudaMemcpyHostToDevice, st));
-      }
-      CUDA_CHECK(cudaMemcpyAsync(d_tab, sec.eps_table, (size_t)sec.nmedia * 9 * sizeof(cplx), cudaMemcpyHostToDevice, st));
-      CUDA_CHECK(cudaMemcpyAsync(d_xy, p.coords_x, (size_t)(p.nx + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
-      CUDA_CHECK(cudaMemcpyAsync(d_xy + p.nx + 1, p.coords_y, (size_t)(p.ny + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
-      W.h2d_bytes += (size_t)sec.nrect * 36 + (size_t)sec.nmedia * 144 + (size_t)(p.nx + p.ny + 2) * 8;
-      SectionDev sd{sec.nrect, d_rects, d_med, d_tab, d_xy, d_xy + p.nx + 1};
+      unsigned char *cur = raw.p + off_sec[q];
+      auto put = [&](const void *src, size_t bytes) -> unsigned char * {  // 256-byte aligned sub-buffer, filled from host memory
+        unsigned char *dst = cur;
+        if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        cur += align256(bytes);
+        W.h2d_bytes += bytes;
+        return dst;
+      };
+      const int nv = (sec.poly_start && sec.nrect > 0) ? sec.poly_start[sec.nrect] : 0;
+      double *d_rects = reinterpret_cast<double *>(put(sec.rects, (size_t)sec.nrect * 4 * sizeof(double)));
+      int *d_med = reinterpret_cast<int *>(put(sec.medium, (size_t)sec.nrect * sizeof(int)));
+      cplx *d_tab = reinterpret_cast<cplx *>(put(sec.eps_table, (size_t)sec.nmedia * 9 * sizeof(cplx)));
+      double *d_x = reinterpret_cast<double *>(put(p.coords_x, (size_t)(p.nx + 1) * sizeof(double)));
+      double *d_y = reinterpret_cast<double *>(put(p.coords_y, (size_t)(p.ny + 1) * sizeof(double)));
+      const int *d_shape = sec.shape ? reinterpret_cast<const int *>(put(sec.shape, (size_t)sec.nrect * sizeof(int))) : nullptr;
+      const int *d_pstart = nv > 0 ? reinterpret_cast<const int *>(put(sec.poly_start, (size_t)(sec.nrect + 1) * sizeof(int))) : nullptr;
+      const double *d_pxy = nv > 0 ? reinterpret_cast<const double *>(put(sec.poly_xy, (size_t)nv * 2 * sizeof(double))) : nullptr;
+      const unsigned short *d_site = sec.site_medium ? reinterpret_cast<const unsigned short *>(put(sec.site_medium, 3 * N * sizeof(unsigned short))) : nullptr;
+      SectionDev sd{sec.nrect, d_rects, d_med, d_tab, d_x, d_y, sec.nmedia, d_shape, d_pstart, d_pxy, d_site};
       section_raster_kernel<<<(unsigned)std::min<size_t>((N + 255) / 256, 2048), 256, 0, st>>>(sd, p.nx, p.ny, const_cast<cplx *>(r.eps));
     }
     r.mu = nullptr;

@@ -168,6 +168,22 @@ inline void setup_geometry(const b200ms_problem &p, ProblemSetup &s) {
     s.error = "bad problem description";
     return;
   }
+  if (!p.eps) {  // geometric cross-section (include/b200ms.h b200ms_section): every index the rasteriser follows must be in range
+    const b200ms_section &q = *p.section;
+    bool ok = q.nrect >= 0 && q.nmedia >= 1 && q.eps_table && (q.nrect == 0 || (q.rects && q.medium));
+    for (int r = 0; ok && r < q.nrect; ++r) {
+      const int kind = q.shape ? q.shape[r] : B200MS_SHAPE_RECT;
+      ok = q.medium[r] >= 0 && q.medium[r] < q.nmedia && kind >= B200MS_SHAPE_RECT && kind <= B200MS_SHAPE_POLYGON;
+      if (ok && kind == B200MS_SHAPE_POLYGON)
+        ok = q.poly_start && q.poly_xy && q.poly_start[r] >= 0 && q.poly_start[r + 1] - q.poly_start[r] >= 3;
+      if (ok && q.poly_start) ok = q.poly_start[r + 1] >= q.poly_start[r];
+    }
+    if (!ok) {
+      s.status = B200MS_ERR_ARG;
+      s.error = "bad cross-section description (medium index, shape kind or polygon range)";
+      return;
+    }
+  }
   if (p.mu) s.has_mu = true;
   s.k0 = 2.0 * M_PI * p.freq / kC0;
   const bool bend = !std::isnan(p.bend_radius);
@@ -321,7 +337,7 @@ inline void setup_problem(const b200ms_problem &pin, ProblemSetup &s) {
   if (!p.eps && p.section) {  // host mirror of section_raster_kernel
     const b200ms_section &q = *p.section;
     raster.resize((size_t)9 * p.nx * p.ny);
-    SectionDev sd{q.nrect, q.rects, q.medium, reinterpret_cast<const cplx *>(q.eps_table), p.coords_x, p.coords_y};
+    SectionDev sd{q.nrect, q.rects, q.medium, reinterpret_cast<const cplx *>(q.eps_table), p.coords_x, p.coords_y, q.nmedia, q.shape, q.poly_start, q.poly_xy, q.site_medium};
     for (int ix = 0; ix < p.nx; ++ix)
       for (int iy = 0; iy < p.ny; ++iy) section_cell(sd, p.nx, p.ny, ix, iy, raster.data());
     p.eps = reinterpret_cast<const double *>(raster.data());

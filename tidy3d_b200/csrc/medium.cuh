@@ -260,23 +260,70 @@ __global__ void __launch_bounds__(256) tensor_fields_kernel(const MediumRef *med
 // ---- rasterisation of a geometric cross-section (b200ms_section) into the raw eps layout [9][nx][ny] ------------------------
 struct SectionDev {
   int nrect;
-  const double *rects;  // nrect x 4: cx, cy, sx, sy
+  const double *rects;  // nrect x 4, meaning per shape kind (include/b200ms.h)
   const int *medium;    // nrect
   const cplx *table;    // nmedia x 9
   const double *xs, *ys;  // cell boundaries, nx+1 / ny+1
+  int nmedia;
+  const int *shape;                  // nullptr: all rectangles
+  const int *poly_start;             // nrect + 1 vertex offsets (polygons only)
+  const double *poly_xy;             // (x, y) pairs
+  const unsigned short *site_medium; // nullptr, or [3][nx][ny] medium found at the Ex / Ey / Ez sites before the shapes are drawn
 };
-HD int section_medium_at(const SectionDev &s, double x, double y) {
-  int med = 0;
+// products / sums that must round like numpy's (no fused multiply-add): a site exactly on a circle must fall on the same side
+// on the device, in the host mirror and in the reference
+HD double section_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+HD double section_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+// even-odd crossing rule: a horizontal ray from (x, y) towards +x toggles at every edge it crosses
+HD bool section_in_polygon(const double *v, int nv, double x, double y) {
+  bool in = false;
+  for (int i = 0, j = nv - 1; i < nv; j = i++) {
+    const double xi = v[2 * i], yi = v[2 * i + 1], xj = v[2 * j], yj = v[2 * j + 1];
+    if (((yi > y) != (yj > y)) && (x < section_add(section_mul(xj - xi, y - yi) / (yj - yi), xi))) in = !in;
+  }
+  return in;
+}
+HD int section_medium_at(const SectionDev &s, double x, double y, int base) {
+  int med = base;
   for (int r = 0; r < s.nrect; ++r) {
     const double *q = s.rects + 4 * r;
-    if (fabs(x - q[0]) <= q[2] / 2 && fabs(y - q[1]) <= q[3] / 2) med = s.medium[r];  // later structures override (simulation.py:1199-1226)
+    const int kind = s.shape ? s.shape[r] : 0;
+    bool in;
+    if (kind == 1) {  // disc: Cylinder.inside / Sphere.inside (geometry/primitives.py:600-632, 44-70)
+      const double dx = fabs(x - q[0]), dy = fabs(y - q[1]);
+      in = section_add(section_add(section_mul(dx, dx), section_mul(dy, dy)), section_mul(q[3], q[3])) <= section_mul(q[2], q[2]);
+    } else if (kind == 2) {
+      const int v0 = s.poly_start[r];
+      in = section_in_polygon(s.poly_xy + 2 * (size_t)v0, s.poly_start[r + 1] - v0, x, y);
+    } else {  // Box.inside (geometry/base.py:2042-2068): inclusive bounds
+      in = fabs(x - q[0]) <= q[2] / 2 && fabs(y - q[1]) <= q[3] / 2;
+    }
+    if (in) med = s.medium[r];  // later structures override (simulation.py:1199-1226)
   }
   return med;
 }
 HD void section_cell(const SectionDev &s, int nx, int ny, int ix, int iy, cplx *eps) {
   const size_t n = (size_t)nx * ny, c = (size_t)ix * ny + iy;
   const double xb = s.xs[ix], yb = s.ys[iy], xc = (s.xs[ix] + s.xs[ix + 1]) / 2, yc = (s.ys[iy] + s.ys[iy + 1]) / 2;
-  const int med[3] = {section_medium_at(s, xc, yb), section_medium_at(s, xb, yc), section_medium_at(s, xb, yb)};  // Ex, Ey, Ez sites
+  int base[3] = {0, 0, 0};
+  if (s.site_medium)
+    for (int k = 0; k < 3; ++k) {
+      const int m = s.site_medium[(size_t)k * n + c];
+      base[k] = m < s.nmedia ? m : s.nmedia - 1;
+    }
+  const int med[3] = {section_medium_at(s, xc, yb, base[0]), section_medium_at(s, xb, yc, base[1]), section_medium_at(s, xb, yb, base[2])};  // Ex, Ey, Ez sites
   for (int row = 0; row < 3; ++row)
     for (int col = 0; col < 3; ++col) eps[(size_t)(3 * row + col) * n + c] = s.table[(size_t)med[row] * 9 + 3 * row + col];
 }

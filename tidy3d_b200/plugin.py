@@ -8,6 +8,12 @@ and ``ModeSolver._solve_all_freqs_relative(self, coords, symmetry, basis_fields)
 solve over ``self.freqs``; the replacements gather ``self._solver_eps(f)`` for every frequency, run ONE device call and
 reuse the reference's own ``_postprocess_solver_fields`` (:695).
 
+Seam 2b (opt-in ``install(device_eps=True)``): instead of calling ``self._solver_eps(freq)`` -- nine
+``Simulation.epsilon_on_grid`` passes over all structures and a fresh (9,Nx,Ny) complex array PER FREQUENCY
+(mode_solver.py:587-653, simulation.py:1135-1241) -- ``section_of(mode_solver)`` evaluates every structure's
+``geometry.inside_meshgrid`` ONCE per plane into a per-site medium map; per frequency only the 3x3 tensor of every medium is
+evaluated (``Structure.eps_comp``) and the array is rasterised on the device.
+
 Seam 3 (many mode planes): ``run_batch(mode_solvers)`` mirrors ``tidy3d.web.api.mode.run_batch``
 (web/api/mode.py:147-158) locally: the problems of ALL solvers -- including the 3x frequency copies the reference makes
 for the group index (mode_solver.py:267-299) and EME cell planes (components/eme/simulation.py:521-540 build one
@@ -23,10 +29,71 @@ import numpy as np
 from .solver import compute_modes, compute_modes_batch
 
 
+DEVICE_EPS = False  # set by install(device_eps=True)
+
+# plane coordinates (x', y', z' = normal) in terms of the simulation axes: what
+# ModeSolver._tensorial_material_profile_modal_plane_tranform does to the rows / columns of the tensor (mode_solver.py:594-624:
+# normal 0 -> swap x,y then y,z = (y, z, x); normal 1 -> swap y,z = (x, z, y))
+_PLANE_AXES = {0: (1, 2, 0), 1: (0, 2, 1), 2: (0, 1, 2)}
+
+
+def section_of(ms):
+    """Frequency-independent description of the cross-section ``ms._solver_eps(freq)`` samples, as a
+    ``tidy3d_b200.sections.Section``; ``None`` when a medium varies in space (custom media: the sampled array is needed).
+
+    Restates the loop of ``Simulation.epsilon_on_grid`` (simulation.py:1191-1226) with the geometry part hoisted out of
+    the frequency loop: background first, then ``structure.geometry.inside_meshgrid`` of every volumetric structure, in
+    order, at the Ex / Ey / Ez sites of ``ms._solver_grid`` (the off-diagonal components are sampled at the site of their
+    row, simulation.py:1231-1236), reduced to the plane (index 0 along the normal axis, mode_solver.py:600-601) with the
+    tensor rows / columns rotated so that the normal becomes z (mode_solver.py:608-616)."""
+    from .sections import Medium, Section, site_medium_from_masks
+
+    sim, grid, normal = ms.simulation, ms._solver_grid, ms.normal_axis
+    perm = _PLANE_AXES[normal]
+    structures = [sim.scene.background_structure] + list(sim.volumetric_structures)
+    if any(hasattr(st.medium, "eps_comp_on_grid") for st in structures):  # AbstractCustomMedium (structure.py:296-299)
+        return None
+
+    def medium_of(st):
+        def tensor(freq, st=st):
+            return np.array([[st.eps_comp(perm[r], perm[c], freq, None) for c in range(3)] for r in range(3)], dtype=complex)
+
+        return Medium(tensor)
+
+    known, media, masks = [], [], []
+    site_arrays = []
+    for key in ("Ex", "Ey", "Ez"):
+        c = grid[key]
+        site_arrays.append((np.array(c.x), np.array(c.y), np.array(c.z)))
+    for k, st in enumerate(structures):
+        for j, m in enumerate(known):
+            if m is st.medium or m == st.medium:
+                idx = j
+                break
+        else:
+            known.append(st.medium)
+            media.append(medium_of(st))
+            idx = len(known) - 1
+        if k == 0:
+            continue  # the background fills the plane
+        rows = []
+        for arrays in site_arrays:
+            inside = st.geometry.inside_meshgrid(*arrays)
+            rows.append(np.squeeze(np.take(inside, indices=[0], axis=normal), axis=normal))
+        masks.append((np.stack([rows[a] for a in perm]), idx))
+    shape = masks[0][0].shape[1:] if masks else tuple(n for a, n in enumerate(len(x) for x in site_arrays[0]) if a != normal)
+    return Section(background=media[0], media=media, site_medium=site_medium_from_masks(shape, masks))
+
+
 def _problems(ms, coords, symmetry, basis_fields=None):
     out = []
+    sec = section_of(ms) if DEVICE_EPS else None
     for k, freq in enumerate(ms.freqs):
-        p = dict(eps_cross=ms._solver_eps(freq), coords=coords, freq=freq, mode_spec=ms.mode_spec, symmetry=symmetry, direction=ms.direction)
+        p = dict(coords=coords, freq=freq, mode_spec=ms.mode_spec, symmetry=symmetry, direction=ms.direction)
+        if sec is not None:
+            p["section"] = sec  # rasterised on the device: 9 numbers per medium instead of a (9,Nx,Ny) array per frequency
+        else:
+            p["eps_cross"] = ms._solver_eps(freq)
         if basis_fields is not None:
             p["solver_basis_fields"] = ms._postprocess_solver_fields_inverse(basis_fields[k])  # mode_solver.py:774
         out.append(p)
@@ -52,9 +119,15 @@ def solve_all_freqs_relative_batched(self, coords, symmetry, basis_fields):
     return _assemble(self, compute_modes_batch(_problems(self, coords, symmetry, basis_fields)))
 
 
-def install(batched: bool = True):
-    """Route ``tidy3d.plugins.mode.ModeSolver`` through the B200 library.  Raises ImportError without tidy3d."""
+def install(batched: bool = True, device_eps: bool = None):
+    """Route ``tidy3d.plugins.mode.ModeSolver`` through the B200 library.  Raises ImportError without tidy3d.
+    ``device_eps=True``: the batched seams describe each plane once by ``section_of`` and let the device rasterise the
+    permittivity of every frequency (falls back to ``_solver_eps`` arrays for custom media); ``None`` keeps the setting."""
     import tidy3d.plugins.mode.mode_solver as ms  # noqa: PLC0415
+
+    global DEVICE_EPS
+    if device_eps is not None:
+        DEVICE_EPS = bool(device_eps)
 
     ms.compute_modes = compute_modes
     ms.LOCAL_SOLVER_IMPORTED = True
