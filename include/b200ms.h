@@ -34,8 +34,13 @@ extern "C" {
 /* return codes */
 enum {
   B200MS_OK = 0,
-  B200MS_ERR_SHAPE = 1,       /* ValueError: "Mismatch between 'coords' and 'esp_cross' shapes." (solver.py:107) */
-  B200MS_ERR_NO_MODES = 2,    /* RuntimeError: "Could not find any eigenmodes for this waveguide." (solver.py:876) */
+  B200MS_ERR_SHAPE = 1,       /* ValueError: "Mismatch between 'coords' and 'esp_cross' shapes." (solver.py:107).  Reserved for the
+                                 language binding: the C arrays carry no lengths (nx, ny are stated once and every array is
+                                 sized from them), so only the binding that still holds the caller's arrays can see a mismatch
+                                 (tidy3d_b200/_cabi.py PackedProblem raises it before the call) */
+  B200MS_ERR_NO_MODES = 2,    /* RuntimeError: "Could not find any eigenmodes for this waveguide." (solver.py:876: an EMPTY result of
+                                 scipy's eigs).  Reserved: a shift-invert run that finds fewer than num_modes pairs reports
+                                 B200MS_ERR_NOCONV, as scipy raises ArpackNoConvergence before the reference reaches :876 */
   B200MS_ERR_UNSUPPORTED = 3, /* combination the reference itself rejects (tensorial eps + basis fields, solver.py:357-361) or that is
                                  outside the built scope (basis fields together with removed PEC unknowns) */
   B200MS_ERR_CUDA = 4,        /* CUDA runtime failure or no device -- never falls back to the CPU */
