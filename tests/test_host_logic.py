@@ -19,7 +19,7 @@ def test_abi_exports_every_declared_symbol(built_lib):
     assert set(declared) == set(built_lib.EXPORTS)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert L.b200ms_version() == 201
+    assert L.b200ms_version() == built_lib.ABI_VERSION == int(re.search(r"#define B200MS_VERSION (\d+)", hdr).group(1))
 
 
 def test_ctypes_structs_mirror_the_header(built_lib):
@@ -35,14 +35,14 @@ def test_ctypes_structs_mirror_the_header(built_lib):
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
         for decl in body.split(";"):
-            m = re.search(r"(?:const\s+)?(?:double|int|long long|b200ms_section)\s*\*?\s*([a-z_0-9,\s\*\[\]]+)$", decl.strip())
+            m = re.search(r"(?:const\s+)?(?:double|int|long long|unsigned short|b200ms_section)\s*\*?\s*([a-z_0-9,\s\*\[\]]+)$", decl.strip())
             if m:
                 for part in m.group(1).split(","):
                     names.append(re.sub(r"[\*\s]|\[\d+\]", "", part))
         return names
 
     for name, cls in (("b200ms_problem", built_lib.Problem), ("b200ms_result", built_lib.Result), ("b200ms_options", built_lib.Options),
-                      ("b200ms_stats", built_lib.Stats)):
+                      ("b200ms_stats", built_lib.Stats), ("b200ms_section", built_lib.SectionStruct)):
         assert fields(name) == [f[0] for f in cls._fields_], name
 
 

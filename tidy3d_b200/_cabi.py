@@ -17,6 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200MS_LIB") or os.path.join(_HERE, "libb200ms.so")  # B200MS_LIB: developer override (A/B of builds)
 
+ABI_VERSION = 201  # B200MS_VERSION of include/b200ms.h
 OK, ERR_SHAPE, ERR_NO_MODES, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOCONV, ERR_ARG = range(7)
 SPEC_NAMES = {0: "diagonal", 1: "tensorial_real", 2: "tensorial_complex"}
 
@@ -87,6 +88,11 @@ def lib():
                 )
             L = C.CDLL(LIB_PATH)
             L.b200ms_version.restype = C.c_int
+            if L.b200ms_version() != ABI_VERSION:  # the ctypes structs below mirror include/b200ms.h of exactly this version
+                raise OSError(
+                    f"{LIB_PATH} implements ABI version {L.b200ms_version()}, this package expects {ABI_VERSION}: rebuild it "
+                    '(`python -c "import __graft_entry__ as g; g.build()"` at the repo root)'
+                )
             L.b200ms_default_options.argtypes = [C.POINTER(Options)]
             L.b200ms_default_options.restype = None
             L.b200ms_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
