@@ -276,6 +276,13 @@ int b200ms_debug_hierarchy(const b200ms_problem *prob, const b200ms_options *opt
  * that keeps `resident_ctas` of them resident: threads per CTA (column pairs per strip), strips per row, rows marched per CTA */
 int b200ms_debug_march2_geometry(int nx, int ny, int nbatch, int resident_ctas, int *cta_width, int *nstrips, int *rows);
 
+/* the 1-D tables of the on-device post-processing for one axis of n cells (coords: n + 1 boundaries; sym: the problem's
+ * symmetry value for that axis): colocation points (interior boundaries, plus the symmetry plane), and for each of them the
+ * two source indices / weights of the linear interpolation from the centre sites and from the boundary sites of the
+ * symmetry-expanded data, and its trapezoid weight.  idx / wgt: 4 per point {centre i0, centre i1, boundary i0, boundary i1};
+ * returns the number of points, -1 on bad arguments or when max_points is too small */
+int b200ms_debug_post_tables(const double *coords, int n, int sym, int max_points, int *idx, double *wgt, double *area);
+
 /* ---- device debug hooks (GPU tests compare these against the numpy model) ------------------- */
 /* y = (A - sigma) x on level `level` of the hierarchy of `prob`; x,y complex128 2*nxl*nyl */
 int b200ms_debug_apply(b200ms_handle *h, const b200ms_problem *prob, int level, int mode,

@@ -51,8 +51,9 @@ def _site_coords(coords, kind):
 
 
 def interp_weights(src, dst):
-    """Linear interpolation src -> dst as (i0, w0, i1, w1) per destination point; points outside [src[0], src[-1]] get
-    zero weights (xarray/scipy return NaN there and the reference's ``.sum`` skips NaN, monitor_data.py:532-539, 611)."""
+    """Linear interpolation src -> dst as (i0, w0, i1, w1) per destination point (what ``DataArray.interp`` does along one
+    axis); points outside [src[0], src[-1]] get zero weights (NaN in xarray / scipy; does not happen on this path: with a
+    symmetry plane the data is mirrored first, ``expand_symmetry``, and covers the plane)."""
     src, dst = np.asarray(src, float), np.asarray(dst, float)
     i1 = np.searchsorted(src, dst, side="left")
     i0 = np.clip(i1 - 1, 0, src.size - 1)
@@ -65,9 +66,29 @@ def interp_weights(src, dst):
     return i0, np.where(outside, 0.0, w0), i1, np.where(outside, 0.0, w1)
 
 
+def symmetry_eigenvalue(name, axis):
+    """components/data/dataset.py:210-220: E is a vector (the component along the mirrored axis flips), H a pseudovector."""
+    k = "xyz".index(name[1])
+    return (-1 if k == axis else +1) if name[0] == "E" else (+1 if k == axis else -1)
+
+
+def expand_symmetry(f, sites, axis, name, sym_val, center):
+    """monitor_data.py:237-282 (``_symmetry_update_dict``) along one axis: the half-domain data (sites >= center) is mirrored
+    to the sites ``2 center - site`` on the other side of the symmetry plane and multiplied there by
+    ``sym_val * symmetry_eigenvalue``.  A site exactly on the plane is not duplicated.  Returns (values, sites) of the
+    full domain."""
+    sites = np.asarray(sites, float)
+    left = sites > center  # these have a mirror image strictly left of the plane
+    mirrored = 2 * center - sites[left][::-1]
+    vals = np.flip(np.compress(left, f, axis=axis), axis=axis) * (sym_val * symmetry_eigenvalue(name, axis))
+    return np.concatenate([vals, f], axis=axis), np.concatenate([mirrored, sites])
+
+
 def colocate(fields, coords, symmetry=(0, 0)):
-    """mode_solver.py:504-507 / monitor_data.py:523-539: every component linearly interpolated from its Yee sites to the
-    colocation points.  Returns dict name -> (Px, Py, M) arrays."""
+    """mode_solver.py:490-507 (``_colocate_data``): every component of the SYMMETRY-EXPANDED data linearly interpolated from
+    its Yee sites to the colocation points (with a symmetry plane the first of them is the plane itself, where a
+    centre-site component is the mean of its first value and that value's mirror image: the value for an even component,
+    zero for an odd one).  Returns dict name -> (Px, Py, M) arrays."""
     pts = colocation_points(coords, symmetry)
     out = {}
     for name, (kx, ky) in SITES.items():
@@ -75,7 +96,10 @@ def colocate(fields, coords, symmetry=(0, 0)):
         for ax, (kind, p) in enumerate(zip((kx, ky), pts)):
             if p is None:
                 continue
-            i0, w0, i1, w1 = interp_weights(_site_coords(coords[ax], kind), p)
+            src = _site_coords(coords[ax], kind)
+            if symmetry[ax] != 0:
+                f, src = expand_symmetry(f, src, ax, name, symmetry[ax], float(np.asarray(coords[ax])[0]))
+            i0, w0, i1, w1 = interp_weights(src, p)
             shape = [1, 1, 1]
             shape[ax] = -1
             f = np.take(f, i0, axis=ax) * w0.reshape(shape) + np.take(f, i1, axis=ax) * w1.reshape(shape)

@@ -1,6 +1,7 @@
 """CPU: the post-processing restatement (oracle/postprocess.py) against the third-party ground truths that exist here, and
 the product's host-side mode tracking (tidy3d_b200/postprocess.py) against the restatement."""
 import numpy as np
+import pytest
 from scipy.interpolate import interp1d
 
 from oracle import postprocess as OP
@@ -80,3 +81,87 @@ def test_filter_polarization_order():
     te = np.array([0.9, 0.2, np.nan, 0.5, 0.7])
     assert list(PP.filter_polarization(te, "te")) == [0, 3, 4, 1, 2]
     assert list(PP.filter_polarization(te, "tm")) == [1, 3, 0, 4, 2]
+
+
+def _mirror_full(fields, coords, symmetry):
+    """Half-domain Yee data -> the full-domain Yee data the reference's ``symmetry_expanded`` represents (monitor_data.py:237-282),
+    laid out on the full grid's own Yee sites (the lower-boundary site on the far mirrored wall is never read: 0)."""
+    f = np.asarray(fields)
+    coords = [np.asarray(c, float) for c in coords]
+    for ax in (0, 1):
+        s0 = symmetry[ax]
+        if s0 == 0:
+            continue
+        c = coords[ax]
+        n = c.size - 1
+        out = np.zeros(f.shape[:2 + ax] + (2 * n,) + f.shape[3 + ax:], dtype=complex)
+        for name, (fi, ci) in OP.COMP.items():
+            kind = OP.SITES[name][ax]
+            sign = s0 * OP.symmetry_eigenvalue(name, ax)
+            half = f[fi, ci]
+            if kind == "c":
+                full = np.concatenate([sign * np.flip(half, axis=ax), half], axis=ax)
+            else:
+                inner = np.flip(np.take(half, range(1, n), axis=ax), axis=ax)
+                full = np.concatenate([np.zeros_like(np.take(half, [0], axis=ax)), sign * inner, half], axis=ax)
+            out[fi, ci] = full
+        f = out
+        coords[ax] = np.concatenate([2 * c[0] - c[:0:-1], c])
+    return f, coords
+
+
+@pytest.mark.parametrize("symmetry", [(-1, 0), (1, 0), (0, -1), (0, 1), (-1, 1), (1, -1), (-1, -1)])
+def test_symmetry_plane_equals_the_mirrored_full_domain(symmetry):
+    """The reference colocates and integrates the SYMMETRY-EXPANDED data (mode_solver.py:504-507, monitor_data.py:517, 237-282):
+    flux, TE fraction and modal overlaps of a half domain with symmetry planes must equal those of the mirrored full
+    domain without.  At a PEC plane (-1) Ex, Hy, Hz are even across the plane and keep their value there; dropping that
+    point (an earlier reading of the code) loses half a cell of an even mode's power."""
+    rng = np.random.default_rng(4)
+    nx, ny, m = 9, 7, 3
+    x = np.cumsum(np.r_[0.3, rng.uniform(0.05, 0.12, nx)])
+    y = np.cumsum(np.r_[-0.2, rng.uniform(0.05, 0.12, ny)])
+    fa = rng.standard_normal((2, 3, nx, ny, 1, m)) + 1j * rng.standard_normal((2, 3, nx, ny, 1, m))
+    fb = rng.standard_normal((2, 3, nx, ny, 1, m)) + 1j * rng.standard_normal((2, 3, nx, ny, 1, m))
+    full_a, full_coords = _mirror_full(fa, [x, y], symmetry)
+    full_b, _ = _mirror_full(fb, [x, y], symmetry)
+    assert np.allclose(OP.flux(fa, [x, y], symmetry), OP.flux(full_a, full_coords), rtol=1e-12, atol=1e-14)
+    assert np.allclose(OP.pol_fraction(fa, [x, y], symmetry), OP.pol_fraction(full_a, full_coords), rtol=1e-12)
+    assert np.allclose(OP.dot(fa, fb, [x, y], symmetry), OP.dot(full_a, full_b, full_coords), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("symmetry", [(0, 0), (-1, 0), (1, 0), (0, -1), (-1, 1), (1, -1)])
+def test_library_post_tables_equal_the_symmetry_expanded_restatement(built_lib, symmetry):
+    """The 1-D interpolation / integration tables the library uploads for its post-processing kernels (host code of
+    csrc/api.cu, b200ms_debug_post_tables) applied in numpy: colocated fields, flux and overlaps equal the restatement of
+    the reference's symmetry-expanded colocation, including the point on a PEC / PMC symmetry plane."""
+    import ctypes as C
+
+    rng = np.random.default_rng(9)
+    nx, ny, m = 11, 8, 2
+    x = np.cumsum(np.r_[0.0, rng.uniform(0.05, 0.12, nx)])
+    y = np.cumsum(np.r_[-0.4, rng.uniform(0.05, 0.12, ny)])
+    f = _fields(nx, ny, m, seed=2)
+    tabs = []
+    for c, n, s in ((x, nx, symmetry[0]), (y, ny, symmetry[1])):
+        idx, wgt, area = np.zeros(4 * (n + 1), np.int32), np.zeros(4 * (n + 1)), np.zeros(n + 1)
+        P = built_lib.lib().b200ms_debug_post_tables(built_lib._ptr(np.ascontiguousarray(c)), n, s, n + 1, idx.ctypes.data_as(built_lib._ip),
+                                                     built_lib._ptr(wgt), built_lib._ptr(area))
+        assert P == (n - 1 if s == 0 else n)
+        tabs.append((idx[: 4 * P].reshape(P, 4), wgt[: 4 * P].reshape(P, 4), area[:P]))
+    want = OP.colocate(f, [x, y], symmetry)
+    got = {}
+    for name, kinds in OP.SITES.items():
+        g = f[OP.COMP[name][0], OP.COMP[name][1], :, :, 0, :]
+        for ax, kind in enumerate(kinds):
+            idx, wgt, _ = tabs[ax]
+            o = 0 if kind == "c" else 2
+            shape = [1, 1, 1]
+            shape[ax] = -1
+            g = np.take(g, idx[:, o], axis=ax) * wgt[:, o].reshape(shape) + np.take(g, idx[:, o + 1], axis=ax) * wgt[:, o + 1].reshape(shape)
+        got[name] = g
+        assert np.abs(g - want[name]).max() < 1e-13, name
+    da = np.outer(tabs[0][2], tabs[1][2])
+    assert np.abs(da - OP.diff_area([x, y], symmetry)).max() < 1e-15
+    mult = 2 ** sum(1 for q in symmetry if q != 0)
+    fl = mult * np.einsum("xym,xy->m", 0.5 * np.real(got["Ex"] * np.conj(got["Hy"]) - got["Ey"] * np.conj(got["Hx"])), da)
+    assert np.allclose(fl, OP.flux(f, [x, y], symmetry), rtol=1e-12)

@@ -69,7 +69,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "b200ms_version", "b200ms_get_stats", "b200ms_default_options", "b200ms_create", "b200ms_destroy", "b200ms_set_options",
     "b200ms_last_error", "b200ms_host_alloc", "b200ms_host_free", "b200ms_solve_batch", "b200ms_bench_stencil", "b200ms_debug_schur", "b200ms_debug_setup",
-    "b200ms_debug_hierarchy", "b200ms_debug_apply", "b200ms_debug_vcycle", "b200ms_debug_solve", "b200ms_debug_march2_geometry",
+    "b200ms_debug_hierarchy", "b200ms_debug_apply", "b200ms_debug_vcycle", "b200ms_debug_solve", "b200ms_debug_march2_geometry", "b200ms_debug_post_tables",
 ]  # fmt: skip
 
 _lib = None
@@ -114,6 +114,7 @@ def lib():
             L.b200ms_debug_vcycle.argtypes = [C.c_void_p, C.POINTER(Problem), _dp, _dp]
             L.b200ms_debug_solve.argtypes = [C.c_void_p, C.POINTER(Problem), _dp, _dp, _ip, _dp]
             L.b200ms_debug_march2_geometry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip]
+            L.b200ms_debug_post_tables.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp]
             _lib = L
     return _lib
 

@@ -348,8 +348,10 @@ const MediumRef *upload_refs(b200ms_handle *h, const std::vector<MediumRef> &ref
 
 
 // ---- on-device post-processing (csrc/post.cuh) ----------------------------------------------------------------------
-// 1-D tables of one axis: colocation points = interior cell boundaries (mode_solver.py:494-502), linear interpolation from
-// the centre / boundary Yee sites (monitor_data.py:523-539), trapezoid weights (monitor_data.py:425-467).
+// 1-D tables of one axis: colocation points = interior cell boundaries, plus the symmetry plane itself when the min wall is one
+// (mode_solver.py:494-502), linear interpolation from the centre / boundary Yee sites of the SYMMETRY-EXPANDED data
+// (mode_solver.py:504-507 interpolates mode_solver_data.symmetry_expanded; monitor_data.py:237-282 mirrors the half domain
+// with the factor sym_val * symmetry_eigenvalue), trapezoid weights (monitor_data.py:425-467).
 struct HostAxisTables {
   std::vector<int> ci0, ci1, bi0, bi1;
   std::vector<double> cw0, cw1, bw0, bw1, area;
@@ -367,7 +369,7 @@ void interp_row(const std::vector<double> &src, double d, int &i0, double &w0, i
   } else {
     w0 = 1.0 - w1;
   }
-  if (d < src.front() || d > src.back()) w0 = w1 = 0.0;  // NaN in the reference, skipped by its sums
+  if (d < src.front() || d > src.back()) w0 = w1 = 0.0;  // only the symmetry-plane point of the centre sites; axis_tables sets it
 }
 void axis_tables(const double *coords, int n, int sym, HostAxisTables &t) {
   std::vector<double> pts;
@@ -386,6 +388,15 @@ void axis_tables(const double *coords, int n, int sym, HostAxisTables &t) {
   for (int p = 0; p < t.P; ++p) {
     interp_row(cen, pts[p], t.ci0[p], t.cw0[p], t.ci1[p], t.cw1[p]);
     interp_row(bnd, pts[p], t.bi0[p], t.bw0[p], t.bi1[p], t.bw1[p]);
+  }
+  if (sym != 0) {
+    // the first point is the symmetry plane: a centre-site component there is the mean of its first value v and the mirror
+    // image s v, s = sym_val * symmetry_eigenvalue (components/data/dataset.py:210-220).  The components that sit on centre
+    // sites along an axis (x: Ex, Hy, Hz; y: Ey, Hx, Hz) all have eigenvalue -1 along it, so s = -sym: the value itself at a
+    // PEC plane (sym = -1, even components), zero at a PMC plane (sym = +1, odd components)
+    t.ci0[0] = t.ci1[0] = 0;
+    t.cw0[0] = sym < 0 ? 1.0 : 0.0;
+    t.cw1[0] = 0.0;
   }
   if (t.P == 1) return;
   for (int p = 0; p < t.P; ++p) {
@@ -1079,6 +1090,19 @@ extern "C" int b200ms_debug_march2_geometry(int nx, int ny, int nbatch, int resi
   march2_strips(ny, *cta_width, *nstrips);
   *rows = march2_rows(nx, *nstrips, nbatch, resident_ctas);
   return B200MS_OK;
+}
+
+extern "C" int b200ms_debug_post_tables(const double *coords, int n, int sym, int max_points, int *idx, double *wgt, double *area) {
+  if (!coords || n < 1 || !idx || !wgt || !area) return -1;
+  HostAxisTables t;
+  axis_tables(coords, n, sym, t);
+  if (t.P > max_points) return -1;
+  for (int p = 0; p < t.P; ++p) {
+    idx[4 * p] = t.ci0[p]; idx[4 * p + 1] = t.ci1[p]; idx[4 * p + 2] = t.bi0[p]; idx[4 * p + 3] = t.bi1[p];
+    wgt[4 * p] = t.cw0[p]; wgt[4 * p + 1] = t.cw1[p]; wgt[4 * p + 2] = t.bw0[p]; wgt[4 * p + 3] = t.bw1[p];
+    area[p] = t.area[p];
+  }
+  return t.P;
 }
 
 // ---- device debug hooks -------------------------------------------------------------------------------
