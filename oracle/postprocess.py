@@ -107,6 +107,28 @@ def colocate(fields, coords, symmetry=(0, 0)):
     return out
 
 
+C_0 = 2.99792458e14  # um / s (tidy3d/constants.py:16)
+
+
+def grid_correction(n_complex, freq, normal_primal, normal_dual, normal_pos, angle_theta=0.0, direction="+"):
+    """mode_solver.py:847-904 (``ModeSolver._grid_correction``): the factors (primal[M], dual[M]) by which the tangential E /
+    H fields of every mode are multiplied in flux and dot products (monitor_data.py:492-503): the mode is taken to propagate
+    as exp(i k r) on the simulation grid along the normal and is linearly interpolated from the primal (cell boundaries:
+    tangential E) and dual (cell centres: tangential H) grid points to the exact position of the mode plane."""
+    n_complex = np.asarray(n_complex, complex)
+    k_vec = 2 * np.pi * n_complex * freq / C_0 / np.cos(angle_theta)
+    if direction == "-":
+        k_vec = -k_vec
+    out = []
+    for pts in (np.atleast_1d(np.asarray(normal_primal, float)), np.atleast_1d(np.asarray(normal_dual, float))):
+        phase = np.exp(1j * k_vec[:, None] * (pts[None, :] - normal_pos))  # (M, points)
+        if pts.size > 1:  # DataArray.interp(normal_dim=normal_pos): linear
+            out.append(np.array([np.interp(normal_pos, pts, ph.real) + 1j * np.interp(normal_pos, pts, ph.imag) for ph in phase]))
+        else:  # .squeeze(dim=normal_dim)
+            out.append(phase[:, 0])
+    return out[0], out[1]
+
+
 def diff_area(coords, symmetry=(0, 0)):
     """monitor_data.py:425-467 for data colocated at the points of ``colocation_points``: cell sizes from the mid-points
     between neighbouring points, closed with the first and last point (trapezoid weights); a one-cell axis has size 1."""
@@ -121,10 +143,25 @@ def diff_area(coords, symmetry=(0, 0)):
     return np.outer(sizes[0], sizes[1])
 
 
-def flux(fields, coords, symmetry=(0, 0)):
-    """monitor_data.py:582-618: 0.5 Re(E1 H2* - E2 H1*) of the colocated tangential fields integrated with ``diff_area``;
-    a symmetry plane doubles the integral (symmetry_expanded mirrors the half domain)."""
-    c = colocate(fields, coords, symmetry)
+def _corrected(c, correction):
+    """monitor_data.py:488-503 (``_tangential_corrected``) in plane coordinates: tangential E (eigenvalue +1 under a
+    reflection of the normal axis) times the primal factor, tangential H (eigenvalue -1) times the dual factor."""
+    if correction is None:
+        return c
+    primal, dual = (np.asarray(q, complex) for q in correction)
+    out = dict(c)
+    for k in ("Ex", "Ey"):
+        out[k] = c[k] * primal
+    for k in ("Hx", "Hy"):
+        out[k] = c[k] * dual
+    return out
+
+
+def flux(fields, coords, symmetry=(0, 0), correction=None):
+    """monitor_data.py:582-618: 0.5 Re(E1 H2* - E2 H1*) of the colocated tangential fields (times their grid-correction
+    factors ``correction = (primal[M], dual[M])``, if any) integrated with ``diff_area``; a symmetry plane doubles the
+    integral (symmetry_expanded mirrors the half domain)."""
+    c = _corrected(colocate(fields, coords, symmetry), correction)
     s = 0.5 * np.real(c["Ex"] * np.conj(c["Hy"]) - c["Ey"] * np.conj(c["Hx"]))
     mult = 2 ** sum(1 for q in symmetry if q != 0)
     return mult * np.einsum("xym,xy->m", s, diff_area(coords, symmetry))
@@ -139,16 +176,17 @@ def pol_fraction(fields, coords, symmetry=(0, 0)):
     return te / (te + tm)
 
 
-def normalize(fields, coords, symmetry=(0, 0)):
+def normalize(fields, coords, symmetry=(0, 0), correction=None):
     """mode_solver.py:517-521: all six components divided by sqrt(|flux|)."""
-    fl = flux(fields, coords, symmetry)
+    fl = flux(fields, coords, symmetry, correction)
     return np.asarray(fields) / np.sqrt(np.abs(fl)), fl
 
 
-def dot(fields_a, fields_b, coords, symmetry=(0, 0), conjugate=True):
+def dot(fields_a, fields_b, coords, symmetry=(0, 0), conjugate=True, correction_a=None, correction_b=None):
     """monitor_data.py:640-697: M_a x M_b matrix  1/4 sum (E_a* x H_b + H_a* ... ) dS  of the colocated tangential fields
-    (``outer_dot`` for all pairs)."""
-    a, b = colocate(fields_a, coords, symmetry), colocate(fields_b, coords, symmetry)
+    (``outer_dot`` for all pairs), each data set with its own grid-correction factors."""
+    a = _corrected(colocate(fields_a, coords, symmetry), correction_a)
+    b = _corrected(colocate(fields_b, coords, symmetry), correction_b)
     if conjugate:
         a = {k: np.conj(v) for k, v in a.items()}
     da = diff_area(coords, symmetry)
