@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200MS_VERSION 201
+#define B200MS_VERSION 202
 
 /* return codes */
 enum {
@@ -121,6 +121,14 @@ typedef struct {
   const double *basis_e; /* NULL, or the in-plane E part of `solver_basis_fields` (solver.py:219-236, 750-776):
                             2*nx*ny*num_modes complex128 (re,im) laid out [Ex|Ey][ix][iy][mode]; the modes are then
                             computed as linear combinations of this basis (relative mode solver) */
+  const double *grid_correction; /* since version 202.  NULL (factors 1), or 8 doubles {dp0, wp0, dp1, wp1, dd0, wd0, dd1, wd1} from which the
+                            finite-grid correction factors of ModeSolver._grid_correction (mode_solver.py:847-904) are formed for every
+                            mode once its n_complex is known: with k = 2 pi n_complex freq / C_0 / cos(angle_theta) (negated for
+                            direction "-"), primal = wp0 exp(i k dp0) + wp1 exp(i k dp1) multiplies the tangential E, dual (dd*, wd*)
+                            the tangential H in the flux and in the modal overlaps (monitor_data.py:488-503).  dp* / dd*: offsets
+                            along the plane normal (um) from the mode plane to the two simulation-grid boundaries / centres that
+                            bracket it, w*: the linear interpolation weights (one grid point only: {d, 1, 0, 0}).  Only the
+                            post-processing results (post bit 1, flux, overlap_prev) depend on it; the fields themselves do not */
 } b200ms_problem;
 
 typedef struct {
@@ -276,6 +284,10 @@ int b200ms_debug_hierarchy(const b200ms_problem *prob, const b200ms_options *opt
 /* launch geometry of the pair-marching stencil kernels (csrc/march2.cuh) for an nx x ny level of `nbatch` problems on a device
  * that keeps `resident_ctas` of them resident: threads per CTA (column pairs per strip), strips per row, rows marched per CTA */
 int b200ms_debug_march2_geometry(int nx, int ny, int nbatch, int resident_ctas, int *cta_width, int *nstrips, int *rows);
+
+/* the finite-grid correction factors (b200ms_problem.grid_correction) the post-processing applies to the modes of `prob` given
+ * their n_complex (num_modes complex (re,im)): primal / dual, num_modes complex (re,im) each */
+int b200ms_debug_grid_factors(const b200ms_problem *prob, const double *n_complex, double *primal, double *dual);
 
 /* the 1-D tables of the on-device post-processing for one axis of n cells (coords: n + 1 boundaries; sym: the problem's
  * symmetry value for that axis): colocation points (interior boundaries, plus the symmetry plane), and for each of them the

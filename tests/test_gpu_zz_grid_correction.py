@@ -1,0 +1,56 @@
+"""GPU: flux normalisation and modal overlaps with the finite-grid correction factors of ModeSolver._grid_correction
+(mode_solver.py:847-904; b200ms_problem.grid_correction, csrc/post.cuh GC kernel variants) against the numpy restatement
+(oracle/postprocess.py) applied to the raw device fields.  (The file name sorts last on purpose: the newest device code of
+the round is exercised after everything else.)"""
+import numpy as np
+import pytest
+
+from oracle import postprocess as OP
+from tidy3d_b200 import compute_modes_batch
+from tidy3d_b200 import postprocess as PP
+from tidy3d_b200 import workloads as W
+from tidy3d_b200.solver import get_handle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["lossless", "bend_single_minus"])
+def test_flux_normalisation_and_overlaps_with_grid_correction(case):
+    """A mode plane a third of the way between two grid boundaries of a coarse normal grid: primal and dual factors differ
+    from 1 by a few per cent, per mode.  The bent case has complex n_eff (factors of modulus != 1, different for every mode),
+    complex64 fields and backward propagation (k -> -k)."""
+    nf = 3
+    if case == "lossless":
+        wl = W.c2(nf=nf, n=96)
+        kw = {}
+    else:
+        wl = W.c4(n=96)
+        wl.mode_spec.precision = "single"
+        wl.freqs = [wl.freqs[0] * s for s in (0.99, 1.0, 1.01)]
+        kw = dict(direction="-")
+    bounds = np.array([-0.12, -0.04, 0.05, 0.13])
+    centers = (bounds[:-1] + bounds[1:]) / 2
+    pos = bounds[1] + (bounds[2] - bounds[1]) / 3
+    table = PP.grid_correction_table(bounds, centers, pos)
+    probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=f, mode_spec=wl.mode_spec, **kw) for f in wl.freqs]
+    h = get_handle(tolerance="tight")
+    raw = compute_modes_batch(probs, handle=h)
+    out, info = compute_modes_batch([dict(p, grid_correction=table) for p in probs], handle=h, post=("gauge", "normalize", "flux", "overlaps"),
+                                    return_info=True)
+    plain, info_plain = compute_modes_batch(probs, handle=h, post=("normalize", "flux"), return_info=True)
+    tol = 2e-5 if case != "lossless" else 1e-9
+    prev = None
+    for i, ((f_raw, n_raw, _), (f_post, n_post, _)) in enumerate(zip(raw, out)):
+        assert np.array_equal(n_raw, n_post)
+        corr = OP.grid_correction(n_raw, wl.freqs[i], bounds, centers, pos, 0.0, kw.get("direction", "+"))
+        assert np.abs(np.abs(corr[1]) - 1).max() > 1e-3  # the correction is not a no-op
+        g, _ = OP.gauge(f_raw.astype(complex))
+        fn, fl = OP.normalize(g, wl.coords, correction=corr)
+        assert np.abs(info[i]["flux"] - fl).max() < max(tol, 1e-10) * np.abs(fl).max()
+        assert np.abs(info[i]["flux"] - info_plain[i]["flux"]).max() > 1e-4 * np.abs(fl).max()  # and it reaches the flux
+        assert np.abs(f_post - fn).max() < max(tol, 1e-9) * np.abs(fn).max()
+        assert np.allclose(np.abs(OP.flux(f_post.astype(complex), wl.coords, correction=corr)), 1.0, atol=max(tol, 1e-9))
+        if prev is not None:
+            ref = OP.dot(prev[0], fn, wl.coords, correction_a=prev[1], correction_b=corr)
+            assert np.abs(info[i]["overlap_prev"] - ref).max() < max(10 * tol, 1e-9)
+        prev = (fn, corr)

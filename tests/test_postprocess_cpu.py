@@ -165,3 +165,43 @@ def test_library_post_tables_equal_the_symmetry_expanded_restatement(built_lib, 
     mult = 2 ** sum(1 for q in symmetry if q != 0)
     fl = mult * np.einsum("xym,xy->m", 0.5 * np.real(got["Ex"] * np.conj(got["Hy"]) - got["Ey"] * np.conj(got["Hx"])), da)
     assert np.allclose(fl, OP.flux(f, [x, y], symmetry), rtol=1e-12)
+
+
+def test_grid_correction_factors_host_helper_and_library_equal_the_restatement(built_lib):
+    """ModeSolver._grid_correction (mode_solver.py:847-904) three ways: the restatement (exp(i k r) sampled on the whole normal
+    grid, then np.interp like DataArray.interp), the Python helper (bracketing points + weights) and the library's host
+    routine behind b200ms_problem.grid_correction -- lossy and backward modes, an angled plane, a plane exactly on a grid
+    boundary (primal factor exactly 1) and a one-point grid (squeeze instead of interp)."""
+    import ctypes as C
+
+    from tidy3d_b200 import workloads as W
+
+    rng = np.random.default_rng(2)
+    bounds = np.cumsum(np.r_[-0.3, rng.uniform(0.02, 0.05, 12)])
+    centers = (bounds[:-1] + bounds[1:]) / 2
+    n = np.array([2.45 + 0.0j, 1.86 + 3.3e-3j, 1.43 + 0.12j])
+    freq = W.C_0 / 1.55
+    wl = W.c1()
+    for pos, theta, direction, primal_pts, dual_pts in (
+        (0.5 * (bounds[4] + centers[4]), 0.0, "+", bounds, centers),
+        (bounds[6], 0.0, "-", bounds, centers),
+        (0.3 * bounds[7] + 0.7 * bounds[8], 0.2, "+", bounds, centers),
+        (0.013, 0.0, "+", np.array([0.0]), np.array([0.025])),
+    ):
+        want_p, want_d = OP.grid_correction(n, freq, primal_pts, dual_pts, pos, theta, direction)
+        table = PP.grid_correction_table(primal_pts, dual_pts, pos)
+        got_p, got_d = PP.grid_correction_factors(n, freq, table, theta, direction)
+        assert np.abs(got_p - want_p).max() < 1e-14 and np.abs(got_d - want_d).max() < 1e-14
+        if pos == bounds[6]:
+            assert np.abs(want_p - 1).max() < 1e-15 and np.abs(want_d).max() < 1 - 1e-4  # dual ~ cos(k dl / 2)
+        spec = W.ModeSpecLike(num_modes=3, angle_theta=theta)
+        pk = built_lib.PackedProblem(wl.eps_cross, wl.coords, freq, spec, direction=direction, grid_correction=table)
+        lp, ld = np.zeros(3, complex), np.zeros(3, complex)
+        rc = built_lib.lib().b200ms_debug_grid_factors(C.byref(pk.struct), built_lib._ptr(n.view(float)), built_lib._ptr(lp.view(float)),
+                                                       built_lib._ptr(ld.view(float)))
+        assert rc == 0 and np.abs(lp - want_p).max() < 1e-14 and np.abs(ld - want_d).max() < 1e-14
+    # without a table the factors are 1
+    pk = built_lib.PackedProblem(wl.eps_cross, wl.coords, freq, W.ModeSpecLike(num_modes=3))
+    assert built_lib.lib().b200ms_debug_grid_factors(C.byref(pk.struct), built_lib._ptr(n.view(float)), built_lib._ptr(lp.view(float)),
+                                                     built_lib._ptr(ld.view(float))) == 0
+    assert np.array_equal(lp, np.ones(3)) and np.array_equal(ld, np.ones(3))

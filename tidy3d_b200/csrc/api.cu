@@ -406,6 +406,23 @@ void axis_tables(const double *coords, int n, int sym, HostAxisTables &t) {
   }
 }
 
+// Finite-grid correction factors of the modes of one problem (mode_solver.py:847-904, see b200ms_problem.grid_correction):
+// primal multiplies the tangential E, dual the tangential H.  n_complex: num_modes complex (re,im).
+using zc = std::complex<double>;  // (post_batch / post_overlaps have locals called cd)
+void grid_factors(const b200ms_problem &p, const double *n_complex, std::vector<zc> &primal, std::vector<zc> &dual) {
+  const int M = p.num_modes;
+  primal.assign(M, zc(1.0, 0.0));
+  dual.assign(M, zc(1.0, 0.0));
+  if (!p.grid_correction || !n_complex) return;
+  const double *g = p.grid_correction;
+  const double scale = 2.0 * M_PI * p.freq / kC0 / std::cos(p.angle_theta) * (p.direction < 0 ? -1.0 : 1.0);
+  for (int m = 0; m < M; ++m) {
+    const zc ik = zc(0.0, 1.0) * (scale * zc(n_complex[2 * m], n_complex[2 * m + 1]));
+    primal[m] = g[1] * std::exp(ik * g[0]) + g[3] * std::exp(ik * g[2]);
+    dual[m] = g[5] * std::exp(ik * g[4]) + g[7] * std::exp(ik * g[6]);
+  }
+}
+
 struct PostBatch {  // device-side description of the problems of one device batch (kept until the window's overlaps are done)
   std::vector<PostProblem> pp;
 };
@@ -435,8 +452,24 @@ void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, 
   const size_t off_part = off_pp + align256((size_t)B * sizeof(PostProblem));
   const size_t off_flux = off_part + align256((size_t)B * kPostChunks * M * kPostSlots * sizeof(double));
   const size_t off_scal = off_flux + align256((size_t)2 * B * M * sizeof(double));
-  const size_t total = off_scal + align256((size_t)B * M * sizeof(cplx));
+  const size_t off_gc = off_scal + align256((size_t)B * M * sizeof(cplx));
+  const size_t total = off_gc + align256((size_t)B * M * sizeof(cplx));
   h->post.reserve(total + 4096);
+  // grid-correction factors: flux = 0.5 Re(primal conj(dual) int (E1 H2* - E2 H1*) dS); problems without them get 1
+  bool any_gc = false;
+  for (int b = 0; b < B; ++b) any_gc = any_gc || prob[W.i0 + ids[b]].grid_correction != nullptr;
+  std::vector<cplx> hgc;
+  if (any_gc) {
+    hgc.resize((size_t)B * M);
+    std::vector<zc> gp, gd;
+    for (int b = 0; b < B; ++b) {
+      grid_factors(prob[W.i0 + ids[b]], res[W.i0 + ids[b]].n_complex, gp, gd);
+      for (int m = 0; m < M; ++m) {
+        const zc g = gp[m] * std::conj(gd[m]);
+        hgc[(size_t)b * M + m] = mk(g.real(), g.imag());
+      }
+    }
+  }
   std::vector<int> hi(ints);
   std::vector<double> hd(dbls);
   std::vector<PostProblem> pp(B);
@@ -468,12 +501,22 @@ void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, 
   CUDA_CHECK(cudaMemcpyAsync(dpp, pp.data(), (size_t)B * sizeof(PostProblem), cudaMemcpyHostToDevice, st));
   double *dpart = reinterpret_cast<double *>(h->post.p + off_part), *dflux = reinterpret_cast<double *>(h->post.p + off_flux);
   cplx *dscal = reinterpret_cast<cplx *>(h->post.p + off_scal);
+  cplx *dgc = nullptr;
+  if (any_gc) {
+    dgc = reinterpret_cast<cplx *>(h->post.p + off_gc);
+    CUDA_CHECK(cudaMemcpyAsync(dgc, hgc.data(), hgc.size() * sizeof(cplx), cudaMemcpyHostToDevice, st));
+  }
   const bool single = p0.precision == 1;
   const int nch = (int)std::min<size_t>(kPostChunks, ((size_t)2 * nx * ny + 255) / 256);
   dim3 g1(nch, B);
-  if (single) post_scan_kernel<cplxf><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
-  else post_scan_kernel<cplx><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
-  post_final_kernel<<<B, std::max(32, ((M + 31) / 32) * 32), 0, st>>>(dpp, dpart, nch, M, dflux, dscal, dflux + (size_t)B * M);
+  if (any_gc) {
+    if (single) post_scan_kernel<cplxf, true><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
+    else post_scan_kernel<cplx, true><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
+  } else {
+    if (single) post_scan_kernel<cplxf, false><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
+    else post_scan_kernel<cplx, false><<<g1, 256, 0, st>>>(dpp, nx, ny, M, dpart);
+  }
+  post_final_kernel<<<B, std::max(32, ((M + 31) / 32) * 32), 0, st>>>(dpp, dpart, nch, M, dflux, dscal, dflux + (size_t)B * M, dgc);
   if (do_gauge || do_norm) {
     dim3 g2((unsigned)std::min<size_t>(((size_t)6 * nx * ny * M + 255) / 256, 2048), B);
     if (single) post_apply_kernel<cplxf><<<g2, 256, 0, st>>>(dpp, (size_t)6 * nx * ny, M, dscal);
@@ -526,9 +569,12 @@ void post_overlaps(b200ms_handle *h, const b200ms_problem *prob, b200ms_result *
     }
     const size_t off_d = align256(ints * sizeof(int)), off_pp = off_d + align256(dbls * sizeof(double));
     const size_t off_pairs = off_pp + align256((size_t)np * sizeof(PostProblem));
+    bool any_gc = false;  // grid-correction factors on either side of a pair: keep the two cross products apart
+    for (int q = 0; q < np; ++q) any_gc = any_gc || prob[todo[k + q]].grid_correction || prob[todo[k + q] - 1].grid_correction;
+    const int E = (any_gc ? 2 : 1) * M * M;
     const size_t off_part = off_pairs + align256((size_t)np * sizeof(PostPair));
-    const size_t off_out = off_part + align256((size_t)np * kPostChunks * M * M * sizeof(cplx));
-    h->post.reserve(off_out + align256((size_t)np * M * M * sizeof(cplx)) + 4096);
+    const size_t off_out = off_part + align256((size_t)np * kPostChunks * E * sizeof(cplx));
+    h->post.reserve(off_out + align256((size_t)np * E * sizeof(cplx)) + 4096);
     std::vector<int> hi(ints);
     std::vector<double> hd(dbls);
     std::vector<PostProblem> pp(np);
@@ -564,15 +610,37 @@ void post_overlaps(b200ms_handle *h, const b200ms_problem *prob, b200ms_result *
     cplx *dpart = reinterpret_cast<cplx *>(h->post.p + off_part), *dout = reinterpret_cast<cplx *>(h->post.p + off_out);
     const int nch = (int)std::min<size_t>(kPostChunks, ((size_t)nx * ny + 255) / 256);
     dim3 g(nch, np, M * M);
-    if (p0.precision == 1) post_dot_kernel<cplxf><<<g, 256, 0, st>>>(dpp, dpairs, nx, ny, M, dpart);
-    else post_dot_kernel<cplx><<<g, 256, 0, st>>>(dpp, dpairs, nx, ny, M, dpart);
-    post_dot_final_kernel<<<np, std::max(32, ((M * M + 31) / 32) * 32), 0, st>>>(dpart, nch, M, dout);
-    std::vector<cplx> hout((size_t)np * M * M);
+    if (any_gc) {
+      if (p0.precision == 1) post_dot_kernel<cplxf, true><<<g, 256, 0, st>>>(dpp, dpairs, nx, ny, M, dpart);
+      else post_dot_kernel<cplx, true><<<g, 256, 0, st>>>(dpp, dpairs, nx, ny, M, dpart);
+    } else {
+      if (p0.precision == 1) post_dot_kernel<cplxf, false><<<g, 256, 0, st>>>(dpp, dpairs, nx, ny, M, dpart);
+      else post_dot_kernel<cplx, false><<<g, 256, 0, st>>>(dpp, dpairs, nx, ny, M, dpart);
+    }
+    post_dot_final_kernel<<<np, std::min(1024, std::max(32, ((M * M + 31) / 32) * 32)), 0, st>>>(dpart, nch, E, dout);
+    std::vector<cplx> hout((size_t)np * E);
     CUDA_CHECK(cudaMemcpyAsync(hout.data(), dout, hout.size() * sizeof(cplx), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     CUDA_CHECK(cudaGetLastError());
     h->stats.launches += 2;
-    for (int q = 0; q < np; ++q) std::memcpy(res[todo[k + q]].overlap_prev, hout.data() + (size_t)q * M * M, (size_t)M * M * sizeof(cplx));
+    if (!any_gc) {
+      for (int q = 0; q < np; ++q) std::memcpy(res[todo[k + q]].overlap_prev, hout.data() + (size_t)q * M * M, (size_t)M * M * sizeof(cplx));
+    } else {  // dot = conj(primal_a) dual_b (1/4 int Ea* x Hb) - conj(dual_a) primal_b (1/4 int Ha* x Eb)   (monitor_data.py:488-503, 680-697)
+      std::vector<zc> pa, da, pb, db;
+      for (int q = 0; q < np; ++q) {
+        const int i = todo[k + q];
+        grid_factors(prob[i - 1], res[i - 1].n_complex, pa, da);
+        grid_factors(prob[i], res[i].n_complex, pb, db);
+        const cplx *i1 = hout.data() + (size_t)q * E, *i2 = i1 + (size_t)M * M;
+        for (int ma = 0; ma < M; ++ma)
+          for (int mb = 0; mb < M; ++mb) {
+            const size_t e = (size_t)ma * M + mb;
+            const zc v = std::conj(pa[ma]) * db[mb] * zc(i1[e].re, i1[e].im) - std::conj(da[ma]) * pb[mb] * zc(i2[e].re, i2[e].im);
+            res[i].overlap_prev[2 * e] = v.real();
+            res[i].overlap_prev[2 * e + 1] = v.imag();
+          }
+      }
+    }
     k = e;
   }
 }
@@ -1089,6 +1157,17 @@ extern "C" int b200ms_debug_march2_geometry(int nx, int ny, int nbatch, int resi
   if (nx < 1 || ny < 2 || (ny & 1) || nbatch < 1 || !cta_width || !nstrips || !rows) return B200MS_ERR_ARG;
   march2_strips(ny, *cta_width, *nstrips);
   *rows = march2_rows(nx, *nstrips, nbatch, resident_ctas);
+  return B200MS_OK;
+}
+
+extern "C" int b200ms_debug_grid_factors(const b200ms_problem *prob, const double *n_complex, double *primal, double *dual) {
+  if (!prob || !n_complex || !primal || !dual || prob->num_modes < 1) return B200MS_ERR_ARG;
+  std::vector<zc> gp, gd;
+  grid_factors(*prob, n_complex, gp, gd);
+  for (int m = 0; m < prob->num_modes; ++m) {
+    primal[2 * m] = gp[m].real(); primal[2 * m + 1] = gp[m].imag();
+    dual[2 * m] = gd[m].real(); dual[2 * m + 1] = gd[m].imag();
+  }
   return B200MS_OK;
 }
 

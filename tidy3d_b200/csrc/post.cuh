@@ -52,8 +52,10 @@ __device__ __forceinline__ cplx colocated(const F *f, int comp, bool xc, bool yc
 
 // partial[b][chunk][m] = {flux partial, max |E_inplane|^2, its raveled index (as double), re, im of that entry,
 //                        int |E1|^2 dS, int |E2|^2 dS of the colocated field (pol_fraction, monitor_data.py:1625-1652)}
-constexpr int kPostSlots = 7;
-template <typename F>
+// GC (grid-correction factors present, mode_solver.py:847-904): slot 7 = the imaginary part of the integrated complex Poynting
+// product, which the factor primal * conj(dual) mixes into the flux (post_final_kernel)
+constexpr int kPostSlots = 8;
+template <typename F, bool GC>
 __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, int nx, int ny, int M, double *partial) {
   const PostProblem P = pp[blockIdx.y];
   const F *f = reinterpret_cast<const F *>(P.fields);
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, i
   const size_t N = (size_t)nx * ny;
   __shared__ double red[8][kPostSlots];
   for (int m = 0; m < M; ++m) {
-    double fl = 0.0, best = -1.0, bidx = 0.0, bre = 0.0, bim = 0.0, te = 0.0, tm = 0.0;
+    double fl = 0.0, best = -1.0, bidx = 0.0, bre = 0.0, bim = 0.0, te = 0.0, tm = 0.0, fli = 0.0;
     const size_t npts = (size_t)P.ax.P * P.ay.P;
     for (size_t t = (size_t)chunk * 256 + threadIdx.x; t < npts; t += (size_t)nchunk * 256) {
       const int p = (int)(t / P.ay.P), q = (int)(t % P.ay.P);
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, i
       const cplx s = ex * cj(hy) - ey * cj(hx);
       const double da = P.ax.area[p] * P.ay.area[q];
       fl += 0.5 * s.re * da;
+      if constexpr (GC) fli += 0.5 * s.im * da;
       te += abs2(ex) * da;
       tm += abs2(ey) * da;
     }
@@ -85,13 +88,14 @@ __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, i
       fl += __shfl_down_sync(0xffffffffu, fl, o);
       te += __shfl_down_sync(0xffffffffu, te, o);
       tm += __shfl_down_sync(0xffffffffu, tm, o);
+      if constexpr (GC) fli += __shfl_down_sync(0xffffffffu, fli, o);
       const double ob = __shfl_down_sync(0xffffffffu, best, o), oi = __shfl_down_sync(0xffffffffu, bidx, o);
       const double orr = __shfl_down_sync(0xffffffffu, bre, o), oim = __shfl_down_sync(0xffffffffu, bim, o);
       if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bre = orr; bim = oim; }
     }
     if ((threadIdx.x & 31) == 0) {
       double *r = red[threadIdx.x >> 5];
-      r[0] = fl; r[1] = best; r[2] = bidx; r[3] = bre; r[4] = bim; r[5] = te; r[6] = tm;
+      r[0] = fl; r[1] = best; r[2] = bidx; r[3] = bre; r[4] = bim; r[5] = te; r[6] = tm; r[7] = fli;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -99,27 +103,35 @@ __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, i
         fl += red[w][0];
         te += red[w][5];
         tm += red[w][6];
+        if constexpr (GC) fli += red[w][7];
         if (red[w][1] > best || (red[w][1] == best && red[w][2] < bidx)) { best = red[w][1]; bidx = red[w][2]; bre = red[w][3]; bim = red[w][4]; }
       }
       double *o = partial + (((size_t)blockIdx.y * nchunk + chunk) * M + m) * kPostSlots;
-      o[0] = fl; o[1] = best; o[2] = bidx; o[3] = bre; o[4] = bim; o[5] = te; o[6] = tm;
+      o[0] = fl; o[1] = best; o[2] = bidx; o[3] = bre; o[4] = bim; o[5] = te; o[6] = tm; o[7] = fli;
     }
     __syncthreads();
   }
 }
 
-// flux[b][m], scal[b][m] = exp(-i phi) / sqrt(|flux|)  (either factor optional)
-__global__ void post_final_kernel(const PostProblem *pp, const double *partial, int nchunk, int M, double *flux, cplx *scal, double *te_frac) {
+// flux[b][m], scal[b][m] = exp(-i phi) / sqrt(|flux|)  (either factor optional).  gc: nullptr, or [b][m] = primal * conj(dual) of the
+// grid-correction factors: flux = 0.5 Re(gc * int (E1 H2* - E2 H1*) dS)  (monitor_data.py:488-503, 582-618)
+__global__ void post_final_kernel(const PostProblem *pp, const double *partial, int nchunk, int M, double *flux, cplx *scal, double *te_frac,
+                                  const cplx *gc) {
   const int b = blockIdx.x, m = threadIdx.x;
   if (m >= M) return;
   const int do_gauge = pp[b].flags & 1, do_norm = pp[b].flags & 2;
-  double fl = 0.0, best = -1.0, bidx = 0.0, bre = 1.0, bim = 0.0, te = 0.0, tm = 0.0;
+  double fl = 0.0, best = -1.0, bidx = 0.0, bre = 1.0, bim = 0.0, te = 0.0, tm = 0.0, fli = 0.0;
   for (int c = 0; c < nchunk; ++c) {
     const double *o = partial + (((size_t)b * nchunk + c) * M + m) * kPostSlots;
     fl += o[0];
+    if (gc) fli += o[7];
     te += o[5];
     tm += o[6];
     if (o[1] > best || (o[1] == best && o[2] < bidx)) { best = o[1]; bidx = o[2]; bre = o[3]; bim = o[4]; }
+  }
+  if (gc) {
+    const cplx g = gc[(size_t)b * M + m];
+    fl = g.re * fl - g.im * fli;
   }
   fl *= pp[b].mult;
   flux[(size_t)b * M + m] = fl;
@@ -149,14 +161,16 @@ struct PostPair {
   const void *a, *b;  // fields of the two problems
   int prob;           // index of problem B in the PostProblem array (its tables are used; both share the grid)
 };
-template <typename F>
+// GC: the two cross products are kept apart, partial[pair][chunk][2][m][m'] = {1/4 sum Ea* x Hb dS, 1/4 sum Ha* x Eb dS}: the host
+// combines them with the grid-correction factors of the two data sets, conj(primal_a) dual_b and conj(dual_a) primal_b
+template <typename F, bool GC>
 __global__ void __launch_bounds__(256) post_dot_kernel(const PostProblem *pp, const PostPair *pairs, int nx, int ny, int M, cplx *partial) {
   const PostPair pr = pairs[blockIdx.y];
   const PostProblem P = pp[pr.prob];
   const F *fa = reinterpret_cast<const F *>(pr.a), *fb = reinterpret_cast<const F *>(pr.b);
   const int ma = blockIdx.z / M, mb = blockIdx.z % M;
   const int chunk = blockIdx.x, nchunk = gridDim.x;
-  cplx acc = mk(0.0, 0.0);
+  cplx acc = mk(0.0, 0.0), acc2 = mk(0.0, 0.0);
   const size_t npts = (size_t)P.ax.P * P.ay.P;
   for (size_t t = (size_t)chunk * 256 + threadIdx.x; t < npts; t += (size_t)nchunk * 256) {
     const int p = (int)(t / P.ay.P), q = (int)(t % P.ay.P);
@@ -164,25 +178,44 @@ __global__ void __launch_bounds__(256) post_dot_kernel(const PostProblem *pp, co
     const cplx ha1 = cj(colocated(fa, 3, false, true, P.ax, P.ay, nx, ny, M, p, q, ma)), ha2 = cj(colocated(fa, 4, true, false, P.ax, P.ay, nx, ny, M, p, q, ma));
     const cplx eb1 = colocated(fb, 0, true, false, P.ax, P.ay, nx, ny, M, p, q, mb), eb2 = colocated(fb, 1, false, true, P.ax, P.ay, nx, ny, M, p, q, mb);
     const cplx hb1 = colocated(fb, 3, false, true, P.ax, P.ay, nx, ny, M, p, q, mb), hb2 = colocated(fb, 4, true, false, P.ax, P.ay, nx, ny, M, p, q, mb);
-    const cplx v = (ea1 * hb2 - ea2 * hb1) - (ha1 * eb2 - ha2 * eb1);
-    acc += (P.ax.area[p] * P.ay.area[q]) * v;
+    if constexpr (GC) {
+      acc += (P.ax.area[p] * P.ay.area[q]) * (ea1 * hb2 - ea2 * hb1);
+      acc2 += (P.ax.area[p] * P.ay.area[q]) * (ha1 * eb2 - ha2 * eb1);
+    } else {
+      const cplx v = (ea1 * hb2 - ea2 * hb1) - (ha1 * eb2 - ha2 * eb1);
+      acc += (P.ax.area[p] * P.ay.area[q]) * v;
+    }
   }
   acc = warp_sum(acc);
-  __shared__ cplx red[8];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  if constexpr (GC) acc2 = warp_sum(acc2);
+  __shared__ cplx red[8], red2[8];
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = acc;
+    if constexpr (GC) red2[threadIdx.x >> 5] = acc2;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     cplx s = red[0];
     for (int w = 1; w < 8; ++w) s += red[w];
-    partial[(((size_t)blockIdx.y * nchunk + chunk) * M + ma) * M + mb] = (0.25 * P.mult) * s;
+    if constexpr (GC) {
+      cplx s2 = red2[0];
+      for (int w = 1; w < 8; ++w) s2 += red2[w];
+      cplx *o = partial + ((size_t)blockIdx.y * nchunk + chunk) * 2 * M * M;
+      o[(size_t)ma * M + mb] = (0.25 * P.mult) * s;
+      o[(size_t)M * M + (size_t)ma * M + mb] = (0.25 * P.mult) * s2;
+    } else {
+      partial[(((size_t)blockIdx.y * nchunk + chunk) * M + ma) * M + mb] = (0.25 * P.mult) * s;
+    }
   }
 }
-__global__ void post_dot_final_kernel(const cplx *partial, int nchunk, int M, cplx *out) {
-  const int pair = blockIdx.x, e = threadIdx.x;
-  if (e >= M * M) return;
-  cplx s = mk(0.0, 0.0);
-  for (int c = 0; c < nchunk; ++c) s += partial[((size_t)pair * nchunk + c) * M * M + e];
-  out[(size_t)pair * M * M + e] = s;
+// out[pair][e] = sum over chunks of partial[pair][chunk][e], e < E (E = M^2, or 2 M^2 with grid-correction factors)
+__global__ void post_dot_final_kernel(const cplx *partial, int nchunk, int E, cplx *out) {
+  const int pair = blockIdx.x;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    cplx s = mk(0.0, 0.0);
+    for (int c = 0; c < nchunk; ++c) s += partial[((size_t)pair * nchunk + c) * E + e];
+    out[(size_t)pair * E + e] = s;
+  }
 }
 
 }  // namespace b200ms

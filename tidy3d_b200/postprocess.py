@@ -96,3 +96,37 @@ def filter_polarization(te_fraction: np.ndarray, filter_pol: str) -> np.ndarray:
     else:
         raise ValueError("filter_pol must be 'te' or 'tm'")
     return np.concatenate(parts)
+
+
+def grid_correction_table(normal_primal, normal_dual, normal_pos: float) -> np.ndarray:
+    """The 8 numbers of ``b200ms_problem.grid_correction`` for a mode plane at ``normal_pos`` in a simulation whose grid
+    along the plane normal has the boundaries ``normal_primal`` and the centres ``normal_dual``
+    (``simulation.grid.boundaries / centers`` along ``normal_axis``, mode_solver.py:879-883): for each of the two grids the
+    offsets from the plane to the two grid points that bracket it and the weights of the linear interpolation the reference
+    does with ``DataArray.interp`` (:893-900); a grid of one point contributes that point with weight 1 (``squeeze``).
+    The library forms ``primal = w0 exp(i k d0) + w1 exp(i k d1)`` (and ``dual``) per mode once ``n_complex`` is known, and uses
+    them in the flux normalisation and the modal overlaps (monitor_data.py:488-503) -- what ``ModeSolverData`` stores as
+    ``grid_primal_correction`` / ``grid_dual_correction``."""
+    out = []
+    for pts in (normal_primal, normal_dual):
+        pts = np.atleast_1d(np.asarray(pts, dtype=float))
+        if pts.size == 1:
+            out += [pts[0] - normal_pos, 1.0, 0.0, 0.0]
+            continue
+        if not (pts[0] <= normal_pos <= pts[-1]):
+            raise ValueError("the mode plane lies outside the simulation grid along its normal")
+        i = int(np.clip(np.searchsorted(pts, normal_pos, side="right") - 1, 0, pts.size - 2))
+        w1 = (normal_pos - pts[i]) / (pts[i + 1] - pts[i])
+        out += [pts[i] - normal_pos, 1.0 - w1, pts[i + 1] - normal_pos, w1]
+    return np.array(out, dtype=float)
+
+
+def grid_correction_factors(n_complex, freq: float, table, angle_theta: float = 0.0, direction: str = "+"):
+    """``(primal[M], dual[M])`` for given ``n_complex`` (what the reference stores in ``ModeSolverData.grid_primal_correction`` /
+    ``grid_dual_correction``, mode_solver.py:884-904), from the table of ``grid_correction_table``: cheap host arithmetic on
+    M numbers for callers that assemble ``ModeSolverData`` themselves."""
+    t = np.asarray(table, float)
+    k = 2 * np.pi * np.asarray(n_complex, complex) * freq / 2.99792458e14 / np.cos(angle_theta) * (-1.0 if direction == "-" else 1.0)
+    primal = t[1] * np.exp(1j * k * t[0]) + t[3] * np.exp(1j * k * t[2])
+    dual = t[5] * np.exp(1j * k * t[4]) + t[7] * np.exp(1j * k * t[6])
+    return primal, dual

@@ -93,7 +93,9 @@ def compute_modes_batch(
     any of ``"gauge"`` (mode_solver.py:802-810), ``"normalize"`` (flux normalisation, mode_solver.py:517-521), ``"flux"``
     (report each mode's flux and TE polarisation fraction in the info dict; the fraction is None for angled mode planes) and ``"overlaps"`` (M x M modal overlap matrix with the previous problem of
     the call, monitor_data.py:640-697, in the info dict as ``overlap_prev``; the input of ``postprocess.overlap_sort``).
-    With ``want_fields=False`` only ``n_complex`` and these small results leave the GPU.
+    With ``want_fields=False`` only ``n_complex`` and these small results leave the GPU.  A problem may carry
+    ``grid_correction=postprocess.grid_correction_table(...)``: flux, normalisation and overlaps then include the
+    finite-grid correction factors of ``ModeSolver._grid_correction`` (mode_solver.py:847-904), like the reference's.
     """
     post = tuple(post or ())
     unknown = set(post) - {"gauge", "normalize", "flux", "overlaps"}
@@ -122,7 +124,7 @@ def compute_modes_batch(
             section=section,
             mu_cross=p.get("mu_cross"), target_override=target_override,
             incidence=(split is not None or p.get("mu_cross") is not None),  # solver.py:93
-            post=post_flags,
+            post=post_flags, grid_correction=p.get("grid_correction"),
         )  # fmt: skip
         if split is None and section is None:
             cache[key] = pk.eps
