@@ -257,3 +257,21 @@ def test_section_of_reproduces_solver_eps_for_every_plane_orientation(built_lib)
     # custom (space-dependent) media keep the sampled-array path
     structures[0].medium.eps_comp_on_grid = lambda *a, **k: None
     assert plugin.section_of(ms) is None
+
+
+def test_grid_correction_of_reads_the_normal_grid_of_the_simulation():
+    import tidy3d_b200.plugin as plugin
+    from oracle import postprocess as OP
+    from tidy3d_b200 import postprocess as PP
+
+    bounds = [np.linspace(-1, 1, 21), np.array([-0.3, -0.1, 0.05, 0.2, 0.4]), np.linspace(-1, 1, 11)]
+    centers = [(b[:-1] + b[1:]) / 2 for b in bounds]
+    ms = types.SimpleNamespace(
+        normal_axis=1, plane=types.SimpleNamespace(center=(0.0, 0.08, 0.0)),
+        simulation=types.SimpleNamespace(grid=types.SimpleNamespace(boundaries=types.SimpleNamespace(to_list=bounds),
+                                                                    centers=types.SimpleNamespace(to_list=centers))))
+    table = plugin.grid_correction_of(ms)
+    n = np.array([2.4 + 0.01j, 1.7])
+    got = PP.grid_correction_factors(n, 1.9e14, table)
+    want = OP.grid_correction(n, 1.9e14, bounds[1], centers[1], 0.08)
+    assert np.allclose(got[0], want[0], rtol=1e-14) and np.allclose(got[1], want[1], rtol=1e-14)

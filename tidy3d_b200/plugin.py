@@ -85,6 +85,17 @@ def section_of(ms):
     return Section(background=media[0], media=media, site_medium=site_medium_from_masks(shape, masks))
 
 
+def grid_correction_of(ms) -> np.ndarray:
+    """``b200ms_problem.grid_correction`` table of a ``ModeSolver``: where its plane sits between the boundaries (tangential E)
+    and the centres (tangential H) of the simulation grid along the plane normal -- the inputs of
+    ``ModeSolver._grid_correction`` (mode_solver.py:873-883); pass it as ``grid_correction=`` with ``post=("normalize", ...)``
+    so that flux normalisation and overlaps on the device include the factors the reference applies (monitor_data.py:488-503)."""
+    from .postprocess import grid_correction_table
+
+    axis, grid = ms.normal_axis, ms.simulation.grid
+    return grid_correction_table(grid.boundaries.to_list[axis], grid.centers.to_list[axis], ms.plane.center[axis])
+
+
 def _problems(ms, coords, symmetry, basis_fields=None):
     out = []
     sec = section_of(ms) if DEVICE_EPS else None
