@@ -167,12 +167,32 @@ def flux(fields, coords, symmetry=(0, 0), correction=None):
     return mult * np.einsum("xym,xy->m", s, diff_area(coords, symmetry))
 
 
-def pol_fraction(fields, coords, symmetry=(0, 0)):
-    """monitor_data.py:1625-1652: TE fraction = int |E1|^2 dS / int (|E1|^2 + |E2|^2) dS of the colocated field."""
+def rotation_matrix(axis, angle):
+    """components/transformation.py:112-131 (``RotationAroundAxis.matrix``), counter-clockwise by ``angle`` around ``axis``."""
+    n = np.asarray(axis, float) / np.linalg.norm(axis)
+    c, s = np.cos(angle), np.sin(angle)
+    rot = np.zeros((3, 3))
+    tan_dim = [[1, 2], [2, 0], [0, 1]]
+    for dim in range(3):
+        rot[dim, dim] = c + n[dim] ** 2 * (1 - c)
+        rot[dim, tan_dim[dim][0]] = n[dim] * n[tan_dim[dim][0]] * (1 - c) - n[tan_dim[dim][1]] * s
+        rot[dim, tan_dim[dim][1]] = n[dim] * n[tan_dim[dim][1]] * (1 - c) + n[tan_dim[dim][0]] * s
+    return rot
+
+
+def pol_fraction(fields, coords, symmetry=(0, 0), angle_theta=0.0, angle_phi=0.0):
+    """monitor_data.py:1625-1652: TE fraction = int |E1|^2 dS / int (|E1|^2 + |E2|^2) dS of the colocated field, E1 / E2 its
+    first two components in the propagation axes (:1584-1614: [tangential 1, tangential 2, normal] rotated by -phi around
+    the normal and then by -theta around the second axis)."""
     c = colocate(fields, coords, symmetry)
     da = diff_area(coords, symmetry)
-    te = np.einsum("xym,xy->m", np.abs(c["Ex"]) ** 2, da)
-    tm = np.einsum("xym,xy->m", np.abs(c["Ey"]) ** 2, da)
+    field = np.array([c["Ex"], c["Ey"], c["Ez"]])
+    if angle_phi != 0:
+        field = np.tensordot(rotation_matrix([0, 0, 1], -angle_phi), field, axes=1)
+    if angle_theta != 0:
+        field = np.tensordot(rotation_matrix([0, 1, 0], -angle_theta), field, axes=1)
+    te = np.einsum("xym,xy->m", np.abs(field[0]) ** 2, da)
+    tm = np.einsum("xym,xy->m", np.abs(field[1]) ** 2, da)
     return te / (te + tm)
 
 

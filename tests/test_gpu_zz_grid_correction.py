@@ -54,3 +54,21 @@ def test_flux_normalisation_and_overlaps_with_grid_correction(case):
             ref = OP.dot(prev[0], fn, wl.coords, correction_a=prev[1], correction_b=corr)
             assert np.abs(info[i]["overlap_prev"] - ref).max() < max(10 * tol, 1e-9)
         prev = (fn, corr)
+
+
+@pytest.mark.parametrize("name", ["angled_48_minus", "angled_phi_48"])
+def test_te_fraction_of_an_angled_plane_is_taken_in_the_propagation_axes(name):
+    """ModeData.pol_fraction rotates the colocated field by -phi and -theta first (monitor_data.py:1603-1607, 1625-1652)."""
+    from tests.golden.cases import CASES
+
+    fac, kw, _ = CASES[name]
+    wl = fac()
+    theta, phi = wl.mode_spec.angle_theta, getattr(wl.mode_spec, "angle_phi", 0.0)
+    assert theta != 0.0
+    probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=wl.freqs[0], mode_spec=wl.mode_spec, **kw)]
+    raw = compute_modes_batch(probs)[0][0]
+    _, info = compute_modes_batch(probs, post=("flux",), return_info=True)
+    want = OP.pol_fraction(raw.astype(complex), wl.coords, angle_theta=theta, angle_phi=phi)
+    tol = 1e-5 if raw.dtype == np.complex64 else 1e-10
+    assert np.abs(info[0]["te_fraction"] - want).max() < tol
+    assert np.abs(want - OP.pol_fraction(raw.astype(complex), wl.coords)).max() > 1e-4  # the rotation matters

@@ -205,3 +205,18 @@ def test_grid_correction_factors_host_helper_and_library_equal_the_restatement(b
     assert built_lib.lib().b200ms_debug_grid_factors(C.byref(pk.struct), built_lib._ptr(n.view(float)), built_lib._ptr(lp.view(float)),
                                                      built_lib._ptr(ld.view(float))) == 0
     assert np.array_equal(lp, np.ones(3)) and np.array_equal(ld, np.ones(3))
+
+
+def test_pol_fraction_in_propagation_axes_closed_form():
+    """The two rotations of monitor_data.py:1603-1607 written out (what csrc/post.cuh post_scan_kernel evaluates per point):
+    E1 = cos(theta) (cos(phi) Ex + sin(phi) Ey) - sin(theta) Ez,  E2 = cos(phi) Ey - sin(phi) Ex."""
+    f = _fields(9, 8, 3, seed=5)
+    x, y = np.linspace(0, 1, 10), np.linspace(-0.4, 0.4, 9)
+    for theta, phi in ((0.2, 0.0), (0.0, 0.7), (-0.3, 1.1)):
+        c = OP.colocate(f, [x, y])
+        da = OP.diff_area([x, y])
+        e1 = np.cos(theta) * (np.cos(phi) * c["Ex"] + np.sin(phi) * c["Ey"]) - np.sin(theta) * c["Ez"]
+        e2 = np.cos(phi) * c["Ey"] - np.sin(phi) * c["Ex"]
+        te, tm = np.einsum("xym,xy->m", np.abs(e1) ** 2, da), np.einsum("xym,xy->m", np.abs(e2) ** 2, da)
+        assert np.allclose(OP.pol_fraction(f, [x, y], angle_theta=theta, angle_phi=phi), te / (te + tm), rtol=1e-13)
+    assert np.allclose(OP.pol_fraction(f, [x, y]), OP.pol_fraction(f, [x, y], angle_theta=0.0, angle_phi=0.0))

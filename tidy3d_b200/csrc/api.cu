@@ -491,6 +491,8 @@ void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, 
     pp[b].fields = region + (size_t)b * per;
     pp[b].mult = (p.symmetry[0] != 0 ? 2.0 : 1.0) * (p.symmetry[1] != 0 ? 2.0 : 1.0);
     pp[b].flags = p.post;
+    pp[b].ct = std::cos(p.angle_theta); pp[b].st = std::sin(p.angle_theta);
+    pp[b].cp = std::cos(p.angle_phi); pp[b].sp = std::sin(p.angle_phi);
     do_gauge |= p.post & 1;
     do_norm |= p.post & 2;
   }
@@ -596,6 +598,8 @@ void post_overlaps(b200ms_handle *h, const b200ms_problem *prob, b200ms_result *
       pp[q].fields = const_cast<void *>(dev_fields[i]);
       pp[q].mult = (prob[i].symmetry[0] != 0 ? 2.0 : 1.0) * (prob[i].symmetry[1] != 0 ? 2.0 : 1.0);
       pp[q].flags = 0;
+      pp[q].ct = pp[q].cp = 1.0;
+      pp[q].st = pp[q].sp = 0.0;
       pairs[q].a = dev_fields[i - 1];
       pairs[q].b = dev_fields[i];
       pairs[q].prob = q;

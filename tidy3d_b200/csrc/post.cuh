@@ -7,7 +7,7 @@
 //   overlaps       monitor_data.py:640-697 (dot / outer_dot)   M x M modal overlap matrix between the modes of one problem
 //                  and the next (adjacent frequencies), the input of overlap_sort (monitor_data.py:1295-1375)
 // Fields layout: [2][3][nx][ny][M] (mode fastest), complex128 or complex64.
-// Yee sites (c = cell centre, b = lower boundary):  Ex (c,b)  Ey (b,c)  Hx (b,c)  Hy (c,b).
+// Yee sites (c = cell centre, b = lower boundary):  Ex (c,b)  Ey (b,c)  Ez (b,b)  Hx (b,c)  Hy (c,b).
 #pragma once
 #include "kernels.cuh"
 
@@ -28,6 +28,7 @@ struct PostProblem {
   PostAxis ax, ay;
   double mult;   // 2^(number of symmetry planes)
   int flags;     // b200ms_problem.post: bit 0 gauge, bit 1 flux normalisation
+  double ct, st, cp, sp;  // cos / sin of mode_spec.angle_theta, angle_phi: the TE fraction is taken in the propagation axes
 };
 
 template <typename F> __device__ __forceinline__ cplx ldf(const F *p);
@@ -75,8 +76,18 @@ __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, i
       const double da = P.ax.area[p] * P.ay.area[q];
       fl += 0.5 * s.re * da;
       if constexpr (GC) fli += 0.5 * s.im * da;
-      te += abs2(ex) * da;
-      tm += abs2(ey) * da;
+      if (P.st != 0.0 || P.sp != 0.0) {
+        // angled plane: the colocated E field is rotated by -phi around the normal, then by -theta around the second tangential
+        // axis (monitor_data.py:1603-1607, rotation matrices components/transformation.py:112-131) before |E1|^2, |E2|^2
+        const cplx ez = colocated(f, 2, false, false, P.ax, P.ay, nx, ny, M, p, q, m);
+        const cplx e1 = P.ct * (P.cp * ex + P.sp * ey) - P.st * ez;
+        const cplx e2 = P.cp * ey - P.sp * ex;
+        te += abs2(e1) * da;
+        tm += abs2(e2) * da;
+      } else {
+        te += abs2(ex) * da;
+        tm += abs2(ey) * da;
+      }
     }
     for (size_t c = (size_t)chunk * 256 + threadIdx.x; c < 2 * N; c += (size_t)nchunk * 256) {  // E[:2] raveled: comp, ix, iy
       const cplx v = ldf(f + c * M + m);

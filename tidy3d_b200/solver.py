@@ -91,7 +91,7 @@ def compute_modes_batch(
 
     ``post``: on-device post-processing applied to the fields before they are delivered (``tidy3d_b200.postprocess``):
     any of ``"gauge"`` (mode_solver.py:802-810), ``"normalize"`` (flux normalisation, mode_solver.py:517-521), ``"flux"``
-    (report each mode's flux and TE polarisation fraction in the info dict; the fraction is None for angled mode planes) and ``"overlaps"`` (M x M modal overlap matrix with the previous problem of
+    (report each mode's flux and TE polarisation fraction in the info dict) and ``"overlaps"`` (M x M modal overlap matrix with the previous problem of
     the call, monitor_data.py:640-697, in the info dict as ``overlap_prev``; the input of ``postprocess.overlap_sort``).
     With ``want_fields=False`` only ``n_complex`` and these small results leave the GPU.  A problem may carry
     ``grid_correction=postprocess.grid_correction_table(...)``: flux, normalisation and overlaps then include the
@@ -158,11 +158,7 @@ def compute_modes_batch(
         )  # fmt: skip
         if flux_out:
             infos[-1]["flux"] = flux_out[i]
-            ms = problems[i]["mode_spec"]
-            # for an angled mode plane the reference rotates the colocated field to the propagation axes before it takes
-            # the fraction (monitor_data.py:1603-1607); the device kernel works in plane axes, so no value is reported
-            angled = getattr(ms, "angle_theta", 0.0) != 0.0 or getattr(ms, "angle_phi", 0.0) != 0.0
-            infos[-1]["te_fraction"] = None if angled else te_out[i]
+            infos[-1]["te_fraction"] = te_out[i]
         if ov_out:
             infos[-1]["overlap_prev"] = ov_out[i]
     return (out, infos) if return_info else out
