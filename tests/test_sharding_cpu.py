@@ -80,3 +80,16 @@ def test_gloo_world2_gather():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_field_meta_of_a_section_problem():
+    """Problems described by a geometric cross-section have no eps_cross array: the field block size comes from coords."""
+    import types
+
+    from tidy3d_b200.sharding import _field_meta
+
+    spec = types.SimpleNamespace(num_modes=3, precision="single")
+    shape, dt, nbytes = _field_meta(dict(section=object(), coords=[np.zeros(11), np.zeros(8)], mode_spec=spec))
+    assert shape == (2, 3, 10, 7, 1, 3) and dt == np.complex64 and nbytes == 2 * 3 * 10 * 7 * 3 * 8
+    spec.precision = "double"
+    assert _field_meta(dict(eps_cross=np.zeros((9, 10, 7)), coords=[np.zeros(11), np.zeros(8)], mode_spec=spec))[1] == np.complex128

@@ -27,8 +27,7 @@ def partition(n_items: int, world: int, rank: int) -> range:
 
 def _field_meta(p):
     """(shape, dtype, nbytes) of the packed fields of one problem (solver.py:257-267)."""
-    e0 = p["eps_cross"][0]
-    nx, ny = e0.shape
+    nx, ny = len(p["coords"][0]) - 1, len(p["coords"][1]) - 1  # (a problem may carry a `section` instead of `eps_cross`)
     m = int(p["mode_spec"].num_modes)
     dt = np.complex64 if getattr(p["mode_spec"], "precision", "single") == "single" else np.complex128
     shape = (2, 3, nx, ny, 1, m)
