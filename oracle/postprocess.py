@@ -2,11 +2,17 @@
 ``compute_modes``, in solver-plane coordinates (propagation along z; the rotation to the simulation's
 axes, mode_solver.py:788-792, is a relabelling of arrays and is not restated).
 
-PARITY UNPINNED for this file as a whole: ``ModeSolverData`` needs xarray / shapely / the full tidy3d package, which this
-image lacks, so no fixture could be generated from the unmodified reference.  Each function cites the
-reference lines it follows; the pieces that have an available third-party ground truth are pinned in
-tests/test_postprocess_cpu.py: the colocation against ``scipy.interpolate.interp1d`` (what ``xarray.DataArray.interp``
-calls for 1-D linear interpolation) and the integration weights against ``numpy.trapz``.
+PARITY PINNED (since round 2, last session): ``ModeSolverData`` cannot be imported here (xarray / shapely / h5py are not in
+the image), but the reference's own METHOD BODIES can be executed: oracle/ref_post.py cuts them out of the
+reference's files at run time and runs them over a small labelled-array stand-in for xarray (oracle/mini_xarray.py).  What
+they produce for the seeded cases of tests/post_cases.py -- the whole of ``ModeSolver.data_raw`` (gauge, colocation, flux
+normalisation with finite-grid correction, polarisation filter, ``overlap_sort``), ``flux``, ``pol_fraction``, ``dot``,
+``outer_dot``, with symmetry planes, a one-cell axis, an angled plane, direction "-" and a finite plane cutting through
+cells -- is committed as tests/golden/post_*.npz (generator tests/golden/make_post_golden.py) and reproduced by this file to
+1e-12 (measured 4e-14) in tests/test_postprocess_pinning.py; the ``reference``-marked tests there repeat it live.  The
+stand-in's own semantics (broadcast by name, inner join, NaN-skipping sums, interp = scipy ``interp1d``) are tested in the
+same file; the older third-party pins (tests/test_postprocess_cpu.py: colocation against ``scipy.interpolate.interp1d``,
+integration weights against ``numpy.trapz``) stay.
 
 Yee sites of the six components in the solver plane (tidy3d/components/grid/grid.py ``Grid.yee``; c = cell centre,
 b = lower cell boundary):  Ex (c,b)  Ey (b,c)  Ez (b,b)  Hx (b,c)  Hy (c,b)  Hz (c,c).
@@ -129,16 +135,21 @@ def grid_correction(n_complex, freq, normal_primal, normal_dual, normal_pos, ang
     return out[0], out[1]
 
 
-def diff_area(coords, symmetry=(0, 0)):
+def diff_area(coords, symmetry=(0, 0), plane_bounds=None):
     """monitor_data.py:425-467 for data colocated at the points of ``colocation_points``: cell sizes from the mid-points
-    between neighbouring points, closed with the first and last point (trapezoid weights); a one-cell axis has size 1."""
+    between neighbouring points, closed with the first and last point (trapezoid weights); a one-cell axis has size 1.
+    ``plane_bounds = (xmin, xmax, ymin, ymax)`` of a finite mode plane: the mid-points / end points are clipped to it
+    (:450-455: "for pixels intersected by the monitor edge, the size is truncated to the part covered by the monitor");
+    with a symmetry plane the bounds are those of the full, mirrored plane and only the max side can cut the half domain."""
     sizes = []
-    for p in colocation_points(coords, symmetry):
+    for ax, p in enumerate(colocation_points(coords, symmetry)):
         if p is None or p.size == 1:
             sizes.append(np.array([1.0]))
             continue
         ctr = 0.5 * (p[1:] + p[:-1])
         ext = np.concatenate(([p[0]], ctr, [p[-1]]))
+        if plane_bounds is not None:
+            ext = np.clip(ext, plane_bounds[2 * ax], plane_bounds[2 * ax + 1])
         sizes.append(ext[1:] - ext[:-1])
     return np.outer(sizes[0], sizes[1])
 
@@ -157,14 +168,14 @@ def _corrected(c, correction):
     return out
 
 
-def flux(fields, coords, symmetry=(0, 0), correction=None):
+def flux(fields, coords, symmetry=(0, 0), correction=None, plane_bounds=None):
     """monitor_data.py:582-618: 0.5 Re(E1 H2* - E2 H1*) of the colocated tangential fields (times their grid-correction
     factors ``correction = (primal[M], dual[M])``, if any) integrated with ``diff_area``; a symmetry plane doubles the
     integral (symmetry_expanded mirrors the half domain)."""
     c = _corrected(colocate(fields, coords, symmetry), correction)
     s = 0.5 * np.real(c["Ex"] * np.conj(c["Hy"]) - c["Ey"] * np.conj(c["Hx"]))
     mult = 2 ** sum(1 for q in symmetry if q != 0)
-    return mult * np.einsum("xym,xy->m", s, diff_area(coords, symmetry))
+    return mult * np.einsum("xym,xy->m", s, diff_area(coords, symmetry, plane_bounds))
 
 
 def rotation_matrix(axis, angle):
@@ -180,12 +191,12 @@ def rotation_matrix(axis, angle):
     return rot
 
 
-def pol_fraction(fields, coords, symmetry=(0, 0), angle_theta=0.0, angle_phi=0.0):
+def pol_fraction(fields, coords, symmetry=(0, 0), angle_theta=0.0, angle_phi=0.0, plane_bounds=None):
     """monitor_data.py:1625-1652: TE fraction = int |E1|^2 dS / int (|E1|^2 + |E2|^2) dS of the colocated field, E1 / E2 its
     first two components in the propagation axes (:1584-1614: [tangential 1, tangential 2, normal] rotated by -phi around
     the normal and then by -theta around the second axis)."""
     c = colocate(fields, coords, symmetry)
-    da = diff_area(coords, symmetry)
+    da = diff_area(coords, symmetry, plane_bounds)
     field = np.array([c["Ex"], c["Ey"], c["Ez"]])
     if angle_phi != 0:
         field = np.tensordot(rotation_matrix([0, 0, 1], -angle_phi), field, axes=1)
@@ -196,20 +207,20 @@ def pol_fraction(fields, coords, symmetry=(0, 0), angle_theta=0.0, angle_phi=0.0
     return te / (te + tm)
 
 
-def normalize(fields, coords, symmetry=(0, 0), correction=None):
+def normalize(fields, coords, symmetry=(0, 0), correction=None, plane_bounds=None):
     """mode_solver.py:517-521: all six components divided by sqrt(|flux|)."""
-    fl = flux(fields, coords, symmetry, correction)
+    fl = flux(fields, coords, symmetry, correction, plane_bounds)
     return np.asarray(fields) / np.sqrt(np.abs(fl)), fl
 
 
-def dot(fields_a, fields_b, coords, symmetry=(0, 0), conjugate=True, correction_a=None, correction_b=None):
+def dot(fields_a, fields_b, coords, symmetry=(0, 0), conjugate=True, correction_a=None, correction_b=None, plane_bounds=None):
     """monitor_data.py:640-697: M_a x M_b matrix  1/4 sum (E_a* x H_b + H_a* ... ) dS  of the colocated tangential fields
     (``outer_dot`` for all pairs), each data set with its own grid-correction factors."""
     a = _corrected(colocate(fields_a, coords, symmetry), correction_a)
     b = _corrected(colocate(fields_b, coords, symmetry), correction_b)
     if conjugate:
         a = {k: np.conj(v) for k, v in a.items()}
-    da = diff_area(coords, symmetry)
+    da = diff_area(coords, symmetry, plane_bounds)
     mult = 2 ** sum(1 for q in symmetry if q != 0)
 
     def integ(x, y):
