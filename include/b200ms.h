@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200MS_VERSION 202
+#define B200MS_VERSION 203
 
 /* return codes */
 enum {
@@ -129,6 +129,11 @@ typedef struct {
                             along the plane normal (um) from the mode plane to the two simulation-grid boundaries / centres that
                             bracket it, w*: the linear interpolation weights (one grid point only: {d, 1, 0, 0}).  Only the
                             post-processing results (post bit 1, flux, overlap_prev) depend on it; the fields themselves do not */
+  const double *plane_bounds; /* since version 203.  NULL (nothing is truncated), or 4 doubles {xmin, xmax, ymin, ymax}: the extent of a
+                            finite mode plane in plane coordinates (of the full, mirrored plane when a symmetry wall is present).
+                            The trapezoid weights of flux, TE fraction and modal overlaps are then truncated to the part of each
+                            cell the plane covers, like the reference's _diff_area (monitor_data.py:437-455: mid-points and end
+                            points clipped to monitor.bounds).  Only the post-processing results depend on it */
 } b200ms_problem;
 
 typedef struct {
@@ -295,6 +300,9 @@ int b200ms_debug_grid_factors(const b200ms_problem *prob, const double *n_comple
  * symmetry-expanded data, and its trapezoid weight.  idx / wgt: 4 per point {centre i0, centre i1, boundary i0, boundary i1};
  * returns the number of points, -1 on bad arguments or when max_points is too small */
 int b200ms_debug_post_tables(const double *coords, int n, int sym, int max_points, int *idx, double *wgt, double *area);
+/* the same with the extent [lo, hi] of a finite mode plane along this axis (b200ms_problem.plane_bounds) */
+int b200ms_debug_post_tables_bounded(const double *coords, int n, int sym, double lo, double hi, int max_points, int *idx, double *wgt,
+                                     double *area);
 
 /* ---- device debug hooks (GPU tests compare these against the numpy model) ------------------- */
 /* y = (A - sigma) x on level `level` of the hierarchy of `prob`; x,y complex128 2*nxl*nyl */

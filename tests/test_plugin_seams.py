@@ -1,9 +1,11 @@
 """CPU: the two seams into tidy3d (tidy3d_b200/plugin.py) against a stand-in for tidy3d.plugins.mode.mode_solver
 (the real package is not importable in this image).  The device call is replaced by a recorder."""
+import os
 import sys
 import types
 
 import numpy as np
+import pytest
 
 
 def _fake_tidy3d(monkeypatch):
@@ -138,6 +140,23 @@ class _BallGeom:
         return (X - self.center[0]) ** 2 + (Y - self.center[1]) ** 2 + (Z - self.center[2]) ** 2 <= self.radius**2
 
 
+class _CylGeom:
+    """Cylinder with vertical side walls (geometry/primitives.py:600-633)."""
+
+    def __init__(self, center, radius, length, axis):
+        self.center, self.radius, self.length, self.axis = np.array(center, float), radius, length, axis
+
+    def inside_meshgrid(self, x, y, z):
+        g = list(np.meshgrid(x, y, z, indexing="ij"))
+        d = [np.abs(g[a] - self.center[a]) for a in range(3)]
+        t = [a for a in range(3) if a != self.axis]
+        return (d[t[0]] ** 2 + d[t[1]] ** 2 <= self.radius**2) & (d[self.axis] <= self.length / 2)
+
+
+def _literal_geometry(kind, kw):
+    return {"Box": _BoxGeom, "Sphere": _BallGeom, "Cylinder": _CylGeom}[kind](**kw)
+
+
 class _TensorMedium:
     def __init__(self, t, slope=0.0):
         self.t, self.slope = np.asarray(t, complex), slope
@@ -222,20 +241,21 @@ def test_section_of_reproduces_solver_eps_for_every_plane_orientation(built_lib)
     import tidy3d_b200.plugin as plugin
     from oracle import sections as OS
 
-    full = np.array([[4.0, 0.3, 0.1], [0.3, 4.4, 0.2j], [0.1, -0.2j, 3.7]])
-    si = _TensorMedium(np.diag([12.0, 12.1, 12.2]), slope=0.05)
+    from tests import section_cases as SC
+
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sections_ref.npz"))
     for normal in (0, 1, 2):
-        structures = [
-            _Structure(_BoxGeom((0.05, -0.1, 0.0), (0.9, 0.5, 0.7)), _TensorMedium(full, slope=-0.02)),
-            _Structure(_BallGeom((0.2, 0.1, 0.05), 0.33), si),
-            _Structure(_BoxGeom((-0.3, 0.2, -0.2), (0.2, 0.3, 0.25)), _TensorMedium(np.diag([12.0, 12.1, 12.2]), slope=0.05)),  # equal medium, new object
-        ]
-        ms = _PlaneSolver(normal, [(-0.8, 0.9), (-0.7, 0.7), (-0.6, 0.75)], (17, 14, 15), structures, _TensorMedium(2.1 * np.eye(3)))
+        structures = [_Structure(_literal_geometry(kind, kw), _TensorMedium(t, slope=slope)) for kind, kw, t, slope in SC.STRUCTURES]
+        ms = _PlaneSolver(normal, SC.BOUNDS, SC.CELLS, structures, _TensorMedium(*SC.BACKGROUND))
+        ms.freqs = list(SC.FREQS)
         sec = plugin.section_of(ms)
-        assert len(sec.media) == 3  # background + two distinct media (the third structure re-uses silicon)
+        assert len(sec.media) == 5  # background + four distinct media (the third structure re-uses silicon)
         coords = ms.plane_coords()
-        for freq in ms.freqs:
+        for k, freq in enumerate(ms.freqs):
             want = ms._solver_eps(freq)
+            # the literal stand-in above IS what the unmodified reference samples (fixture made by oracle/ref_sections.py from
+            # the reference's own epsilon_on_grid / inside_meshgrid / Box, Sphere, Cylinder.inside / plane transform)
+            assert np.array_equal(want, ref[f"eps_n{normal}_f{k}"])
             got = OS.eps_on_grid(sec, coords, freq)
             assert got.shape == want.shape and np.array_equal(got, want)
             # ... and the library's own rasteriser (host mirror of section_raster_kernel) sets the same problem up
@@ -257,6 +277,76 @@ def test_section_of_reproduces_solver_eps_for_every_plane_orientation(built_lib)
     # custom (space-dependent) media keep the sampled-array path
     structures[0].medium.eps_comp_on_grid = lambda *a, **k: None
     assert plugin.section_of(ms) is None
+
+
+@pytest.mark.reference
+def test_section_of_on_a_solver_made_of_the_reference_code():
+    """Live: ``plugin.section_of`` handed a ModeSolver whose sampling path IS the reference's code (oracle/ref_sections.py);
+    section + restated rasteriser == the reference's ``_solver_eps`` for every plane normal, and the committed fixture is
+    what the reference tree here produces."""
+    from oracle import ref_sections as RS
+
+    if not RS.available():
+        pytest.skip("no reference tree here")
+    import tidy3d_b200.plugin as plugin
+    from oracle import sections as OS
+    from tests import section_cases as SC
+
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sections_ref.npz"))
+    for normal in (0, 1, 2):
+        structures = [(RS.geometry(kind, **kw), RS.TensorMedium(t, slope)) for kind, kw, t, slope in SC.STRUCTURES]
+        ms = RS.solver(normal, SC.edges(normal), structures, RS.TensorMedium(*SC.BACKGROUND))
+        sec = plugin.section_of(ms)
+        coords = [e for a, e in enumerate(SC.edges(normal)) if a != normal]
+        for k, freq in enumerate(SC.FREQS):
+            want = np.array(ms._solver_eps(freq))
+            assert np.array_equal(want, ref[f"eps_n{normal}_f{k}"])
+            assert np.array_equal(OS.eps_on_grid(sec, coords, freq), want)
+
+
+def test_primitive_cuts_equal_the_reference_geometry(built_lib):
+    """Rect / Disc of the restatement (oracle/sections.py) and of the library's rasteriser (host mirror of the device code,
+    csrc/medium.cuh section_cell) mark exactly the sites the reference's Box / Sphere / Cylinder.inside_meshgrid mark
+    (fixture made by the reference's own methods, oracle/ref_sections.py) -- sites on an edge or on the circle included."""
+    import tidy3d_b200.sections as S
+    from oracle import sections as OS
+    from tests import section_cases as SC
+
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sections_ref.npz"))
+    for name, (_, _, (kind, kw)) in SC.PRIMITIVES.items():
+        shape = getattr(S, kind)(**kw)
+        want = ref[f"mask_{name}"]
+        assert want.any() and not want.all()
+        assert np.array_equal(OS.inside(shape, SC.SX, SC.SY), want), name
+        # the library: boundaries chosen so that the Ez sites (lower cell boundaries) are the fixture's sites, and the Ex / Ey
+        # sites (cell centres along one axis) the same sites shifted by half a cell
+        import ctypes as C
+
+        coords = [np.r_[SC.SX, SC.SX[-1] + 0.05], np.r_[SC.SY, SC.SY[-1] + 0.05]]
+        sec = S.Section(background=S.Medium(2.0), structures=[(shape, S.Medium((11.0, 12.0, 13.0)))])
+        eps = OS.eps_on_grid(sec, coords, 2e14)
+        assert np.array_equal(eps[8] == 13.0, want)
+        spec = types.SimpleNamespace(num_modes=1)
+        outs = []
+        for pk in (built_lib.PackedProblem(None, coords, 2e14, spec, section=sec), built_lib.PackedProblem(eps, coords, 2e14, spec)):
+            f = np.zeros((6, pk.nx * pk.ny), complex)
+            flags, sigma = (C.c_int * 4)(), np.zeros(2)
+            assert built_lib.lib().b200ms_debug_setup(C.byref(pk.struct), built_lib._ptr(sigma), flags, None, None, None, None, built_lib._ptr(f.view(float))) == 0
+            outs.append((list(flags), sigma.copy(), f))
+        assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2]), name
+
+
+@pytest.mark.reference
+def test_primitive_cut_fixture_is_current():
+    from oracle import ref_sections as RS
+
+    if not RS.available():
+        pytest.skip("no reference tree here")
+    from tests import section_cases as SC
+
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sections_ref.npz"))
+    for name, (kind, kw, _) in SC.PRIMITIVES.items():
+        assert np.array_equal(RS.geometry(kind, **kw).inside_meshgrid(SC.SX, SC.SY, np.array([0.0]))[:, :, 0], ref[f"mask_{name}"])
 
 
 def test_grid_correction_of_reads_the_normal_grid_of_the_simulation():

@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 from scipy.interpolate import interp1d
 
+_trapz = getattr(np, "trapezoid", None) or np.trapz  # numpy >= 2.0 renamed it
+
 from oracle import postprocess as OP
 from tidy3d_b200 import postprocess as PP
 
@@ -37,7 +39,7 @@ def test_diff_area_is_the_trapezoid_rule():
     da = OP.diff_area([x, y])
     px, py = OP.colocation_points([x, y])
     g = np.outer(np.sin(px), np.cos(py))
-    assert abs((g * da).sum() - np.trapz(np.trapz(g, py, axis=1), px)) < 1e-14
+    assert abs((g * da).sum() - _trapz(_trapz(g, py, axis=1), px)) < 1e-14
     assert OP.diff_area([np.array([0.0, 1.0]), y]).shape == (1, 2)  # one-cell axis: size 1
 
 

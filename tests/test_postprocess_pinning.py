@@ -150,3 +150,52 @@ def test_product_polarisation_filter_on_the_reference_fractions(name):
     for i in range(c["nf"]):
         order = PP.filter_polarization(z["ref_te_fraction"][i], c["filter_pol"])
         assert np.allclose(z["in_n_complex"][i][order], z["ref_final_n_complex"][i])
+
+
+def test_library_tables_with_a_finite_plane_reproduce_the_reference_flux(built_lib):
+    """b200ms_problem.plane_bounds (ABI v203): the integration weights the library uploads for a finite mode plane whose
+    edges cut through cells (host code of csrc/api.cu, b200ms_debug_post_tables_bounded), applied in numpy to the gauge-fixed
+    fields of the ``finite_plane`` fixture, give the flux the reference's ``_diff_area`` truncation gives
+    (monitor_data.py:437-455) -- and differ from the untruncated weights."""
+    from oracle import postprocess as OP
+
+    z = np.load(os.path.join(GOLDEN, "post_finite_plane.npz"))
+    c = PC.from_arrays("finite_plane", {k: z[f"in_{k}"] for k in PC.ARRAYS})
+    pb = c["plane_bounds"]
+    areas = []
+    for ax, (co, n) in enumerate(zip(c["coords"], (c["nx"], c["ny"]))):
+        idx, wgt, area = np.zeros(4 * (n + 1), np.int32), np.zeros(4 * (n + 1)), np.zeros(n + 1)
+        P = built_lib.lib().b200ms_debug_post_tables_bounded(built_lib._ptr(np.ascontiguousarray(co)), n, 0, pb[2 * ax], pb[2 * ax + 1], n + 1,
+                                                             idx.ctypes.data_as(built_lib._ip), built_lib._ptr(wgt), built_lib._ptr(area))
+        assert P == n - 1
+        areas.append(area[:P].copy())
+    da = np.outer(*areas)
+    assert np.abs(da - OP.diff_area(c["coords"], (0, 0), pb)).max() < 1e-15
+    assert np.abs(da - OP.diff_area(c["coords"], (0, 0))).max() > 1e-3  # the truncation matters in this case
+    for i in range(c["nf"]):
+        col = OP.colocate(OP.gauge(c["fields"][i])[0], c["coords"])
+        fl = np.einsum("xym,xy->m", 0.5 * np.real(col["Ex"] * np.conj(col["Hy"]) - col["Ey"] * np.conj(col["Hx"])), da)
+        assert np.allclose(fl, z["ref_flux_yee"][i], rtol=1e-12)
+    # the ctypes mirror carries the bounds to the struct
+    from tidy3d_b200 import workloads as W
+
+    wl = W.c1()
+    pk = built_lib.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, plane_bounds=(-1.0, 1.2, -0.5, 0.7))
+    assert [pk.struct.plane_bounds[k] for k in range(4)] == [-1.0, 1.2, -0.5, 0.7]
+    assert not built_lib.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec).struct.plane_bounds
+    with pytest.raises(ValueError):
+        built_lib.PackedProblem(wl.eps_cross, wl.coords, wl.freqs[0], wl.mode_spec, plane_bounds=(1.0, -1.0, 0.0, 1.0))
+
+
+def test_plane_bounds_of_reads_the_plane_of_the_mode_solver():
+    import types
+
+    import tidy3d_b200.plugin as plugin
+
+    for normal, want in ((0, [-2.0, 4.0, -0.5, 2.5]), (1, [0.5, 1.5, -0.5, 2.5]), (2, [0.5, 1.5, -2.0, 4.0])):
+        size = [1.0, 6.0, 3.0]
+        size[normal] = 0.0
+        center = np.array([1.0, 1.0, 1.0])
+        bounds = (tuple(center - np.array(size) / 2), tuple(center + np.array(size) / 2))
+        ms = types.SimpleNamespace(normal_axis=normal, plane=types.SimpleNamespace(bounds=bounds))
+        assert np.allclose(plugin.plane_bounds_of(ms), want)

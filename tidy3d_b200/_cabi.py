@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200MS_LIB") or os.path.join(_HERE, "libb200ms.so")  # B200MS_LIB: developer override (A/B of builds)
 
-ABI_VERSION = 202  # B200MS_VERSION of include/b200ms.h
+ABI_VERSION = 203  # B200MS_VERSION of include/b200ms.h
 OK, ERR_SHAPE, ERR_NO_MODES, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOCONV, ERR_ARG = range(7)
 SPEC_NAMES = {0: "diagonal", 1: "tensorial_real", 2: "tensorial_complex"}
 
@@ -37,7 +37,7 @@ class Problem(C.Structure):
         ("freq", C.c_double), ("target_neff", C.c_double), ("bend_radius", C.c_double),
         ("angle_theta", C.c_double), ("angle_phi", C.c_double),
         ("eps", _dp), ("coords_x", _dp), ("coords_y", _dp), ("mu", _dp), ("section", C.POINTER(SectionStruct)), ("basis_e", _dp),
-        ("grid_correction", _dp),
+        ("grid_correction", _dp), ("plane_bounds", _dp),
     ]  # fmt: skip
 
 
@@ -70,7 +70,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "b200ms_version", "b200ms_get_stats", "b200ms_default_options", "b200ms_create", "b200ms_destroy", "b200ms_set_options",
     "b200ms_last_error", "b200ms_host_alloc", "b200ms_host_free", "b200ms_solve_batch", "b200ms_bench_stencil", "b200ms_debug_schur", "b200ms_debug_setup",
-    "b200ms_debug_hierarchy", "b200ms_debug_apply", "b200ms_debug_vcycle", "b200ms_debug_solve", "b200ms_debug_march2_geometry", "b200ms_debug_post_tables", "b200ms_debug_grid_factors",
+    "b200ms_debug_hierarchy", "b200ms_debug_apply", "b200ms_debug_vcycle", "b200ms_debug_solve", "b200ms_debug_march2_geometry", "b200ms_debug_post_tables", "b200ms_debug_post_tables_bounded", "b200ms_debug_grid_factors",
 ]  # fmt: skip
 
 _lib = None
@@ -116,6 +116,7 @@ def lib():
             L.b200ms_debug_solve.argtypes = [C.c_void_p, C.POINTER(Problem), _dp, _dp, _ip, _dp]
             L.b200ms_debug_march2_geometry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip]
             L.b200ms_debug_post_tables.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp]
+            L.b200ms_debug_post_tables_bounded.argtypes = [_dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _dp]
             L.b200ms_debug_grid_factors.argtypes = [C.POINTER(Problem), _dp, _dp, _dp]
             _lib = L
     return _lib
@@ -129,7 +130,7 @@ class PackedProblem:
     """Owns the contiguous arrays a ``Problem`` struct points to."""
 
     def __init__(self, eps_cross, coords, freq, mode_spec, symmetry=(0, 0), direction="+", eps_packed=None, basis_fields=None,
-                 mu_cross=None, target_override=None, incidence=False, post=0, section=None, grid_correction=None):
+                 mu_cross=None, target_override=None, incidence=False, post=0, section=None, grid_correction=None, plane_bounds=None):
         self.section = None
         if section is not None:  # geometric cross-section rasterised on the device (tidy3d_b200/sections.py); no eps array
             self.section, self._section_arrays = section.pack(float(freq), (len(coords[0]) - 1, len(coords[1]) - 1))
@@ -216,6 +217,12 @@ class PackedProblem:
             if self.grid_correction.size != 8:
                 raise ValueError("grid_correction must hold 8 numbers (postprocess.grid_correction_table)")
             p.grid_correction = _ptr(self.grid_correction)
+        self.plane_bounds = None
+        if plane_bounds is not None:  # (xmin, xmax, ymin, ymax) of a finite mode plane, see b200ms_problem.plane_bounds
+            self.plane_bounds = np.ascontiguousarray(plane_bounds, dtype=np.float64).ravel()
+            if self.plane_bounds.size != 4 or not (self.plane_bounds[0] <= self.plane_bounds[1] and self.plane_bounds[2] <= self.plane_bounds[3]):
+                raise ValueError("plane_bounds must be (xmin, xmax, ymin, ymax)")
+            p.plane_bounds = _ptr(self.plane_bounds)
         self.struct = p
         self.num_modes = p.num_modes
 

@@ -371,7 +371,7 @@ void interp_row(const std::vector<double> &src, double d, int &i0, double &w0, i
   }
   if (d < src.front() || d > src.back()) w0 = w1 = 0.0;  // only the symmetry-plane point of the centre sites; axis_tables sets it
 }
-void axis_tables(const double *coords, int n, int sym, HostAxisTables &t) {
+void axis_tables(const double *coords, int n, int sym, HostAxisTables &t, const double *bounds = nullptr) {
   std::vector<double> pts;
   if (n + 1 > 2) {
     for (int i = (sym == 0 ? 1 : 0); i < n; ++i) pts.push_back(coords[i]);
@@ -400,8 +400,12 @@ void axis_tables(const double *coords, int n, int sym, HostAxisTables &t) {
   }
   if (t.P == 1) return;
   for (int p = 0; p < t.P; ++p) {
-    const double lo = p == 0 ? pts[0] : 0.5 * (pts[p - 1] + pts[p]);
-    const double hi = p == t.P - 1 ? pts[t.P - 1] : 0.5 * (pts[p] + pts[p + 1]);
+    double lo = p == 0 ? pts[0] : 0.5 * (pts[p - 1] + pts[p]);
+    double hi = p == t.P - 1 ? pts[t.P - 1] : 0.5 * (pts[p] + pts[p + 1]);
+    if (bounds) {  // finite plane: cell sizes truncated to the part the plane covers (monitor_data.py:450-455)
+      lo = std::min(std::max(lo, bounds[0]), bounds[1]);
+      hi = std::min(std::max(hi, bounds[0]), bounds[1]);
+    }
     t.area[p] = hi - lo;
   }
 }
@@ -443,8 +447,8 @@ void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, 
   size_t ints = 0, dbls = 0;
   for (int b = 0; b < B; ++b) {
     const b200ms_problem &p = prob[W.i0 + ids[b]];
-    axis_tables(p.coords_x, nx, p.symmetry[0], tx[b]);
-    axis_tables(p.coords_y, ny, p.symmetry[1], ty[b]);
+    axis_tables(p.coords_x, nx, p.symmetry[0], tx[b], p.plane_bounds);
+    axis_tables(p.coords_y, ny, p.symmetry[1], ty[b], p.plane_bounds ? p.plane_bounds + 2 : nullptr);
     ints += 4 * (size_t)(tx[b].P + ty[b].P);
     dbls += 5 * (size_t)(tx[b].P + ty[b].P);
   }
@@ -564,8 +568,8 @@ void post_overlaps(b200ms_handle *h, const b200ms_problem *prob, b200ms_result *
     size_t ints = 0, dbls = 0;
     for (int q = 0; q < np; ++q) {
       const b200ms_problem &p = prob[todo[k + q]];
-      axis_tables(p.coords_x, nx, p.symmetry[0], tx[q]);
-      axis_tables(p.coords_y, ny, p.symmetry[1], ty[q]);
+      axis_tables(p.coords_x, nx, p.symmetry[0], tx[q], p.plane_bounds);
+      axis_tables(p.coords_y, ny, p.symmetry[1], ty[q], p.plane_bounds ? p.plane_bounds + 2 : nullptr);
       ints += 4 * (size_t)(tx[q].P + ty[q].P);
       dbls += 5 * (size_t)(tx[q].P + ty[q].P);
     }
@@ -1175,10 +1179,17 @@ extern "C" int b200ms_debug_grid_factors(const b200ms_problem *prob, const doubl
   return B200MS_OK;
 }
 
+extern "C" int b200ms_debug_post_tables_bounded(const double *coords, int n, int sym, double lo, double hi, int max_points, int *idx,
+                                                double *wgt, double *area);
 extern "C" int b200ms_debug_post_tables(const double *coords, int n, int sym, int max_points, int *idx, double *wgt, double *area) {
+  return b200ms_debug_post_tables_bounded(coords, n, sym, -HUGE_VAL, HUGE_VAL, max_points, idx, wgt, area);
+}
+extern "C" int b200ms_debug_post_tables_bounded(const double *coords, int n, int sym, double lo, double hi, int max_points, int *idx,
+                                                double *wgt, double *area) {
   if (!coords || n < 1 || !idx || !wgt || !area) return -1;
   HostAxisTables t;
-  axis_tables(coords, n, sym, t);
+  const double bounds[2] = {lo, hi};
+  axis_tables(coords, n, sym, t, bounds);
   if (t.P > max_points) return -1;
   for (int p = 0; p < t.P; ++p) {
     idx[4 * p] = t.ci0[p]; idx[4 * p + 1] = t.ci1[p]; idx[4 * p + 2] = t.bi0[p]; idx[4 * p + 3] = t.bi1[p];

@@ -301,14 +301,19 @@ HD int section_medium_at(const SectionDev &s, double x, double y, int base) {
     const double *q = s.rects + 4 * r;
     const int kind = s.shape ? s.shape[r] : 0;
     bool in;
+    // Geometry.inside_meshgrid (geometry/base.py:195-204) evaluates `inside` only at the sites within the bounding box
+    // (_inds_inside_bounds, :164-170: bounds[0] <= site <= bounds[1], bounds = centre -/+ radius or half size as computed in
+    // floating point): a site on the rim can fall out by one rounding, here as there
     if (kind == 1) {  // disc: Cylinder.inside / Sphere.inside (geometry/primitives.py:600-632, 44-70)
       const double dx = fabs(x - q[0]), dy = fabs(y - q[1]);
-      in = section_add(section_add(section_mul(dx, dx), section_mul(dy, dy)), section_mul(q[3], q[3])) <= section_mul(q[2], q[2]);
+      const bool box = q[0] - q[2] <= x && x <= q[0] + q[2] && q[1] - q[2] <= y && y <= q[1] + q[2];
+      in = box && section_add(section_add(section_mul(dx, dx), section_mul(dy, dy)), section_mul(q[3], q[3])) <= section_mul(q[2], q[2]);
     } else if (kind == 2) {
       const int v0 = s.poly_start[r];
       in = section_in_polygon(s.poly_xy + 2 * (size_t)v0, s.poly_start[r + 1] - v0, x, y);
     } else {  // Box.inside (geometry/base.py:2042-2068): inclusive bounds
-      in = fabs(x - q[0]) <= q[2] / 2 && fabs(y - q[1]) <= q[3] / 2;
+      const double hx = q[2] / 2, hy = q[3] / 2;
+      in = q[0] - hx <= x && x <= q[0] + hx && q[1] - hy <= y && y <= q[1] + hy && fabs(x - q[0]) <= hx && fabs(y - q[1]) <= hy;
     }
     if (in) med = s.medium[r];  // later structures override (simulation.py:1199-1226)
   }

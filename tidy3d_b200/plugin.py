@@ -96,6 +96,16 @@ def grid_correction_of(ms) -> np.ndarray:
     return grid_correction_table(grid.boundaries.to_list[axis], grid.centers.to_list[axis], ms.plane.center[axis])
 
 
+def plane_bounds_of(ms) -> np.ndarray:
+    """``b200ms_problem.plane_bounds`` of a ``ModeSolver``: the extent of its plane along the two plane axes, to which the
+    reference truncates the integration cells of flux and overlaps (``_diff_area`` clips to ``monitor.bounds``,
+    monitor_data.py:450-455; the mode-solver monitor has the plane's centre and size, mode_solver.py to_mode_solver_monitor).
+    Infinite extents stay infinite (nothing is truncated along that axis)."""
+    lo, hi = (np.asarray(b, float) for b in ms.plane.bounds)
+    axes = [a for a in range(3) if a != ms.normal_axis]
+    return np.array([lo[axes[0]], hi[axes[0]], lo[axes[1]], hi[axes[1]]])
+
+
 def _problems(ms, coords, symmetry, basis_fields=None):
     out = []
     sec = section_of(ms) if DEVICE_EPS else None

@@ -95,7 +95,9 @@ def compute_modes_batch(
     the call, monitor_data.py:640-697, in the info dict as ``overlap_prev``; the input of ``postprocess.overlap_sort``).
     With ``want_fields=False`` only ``n_complex`` and these small results leave the GPU.  A problem may carry
     ``grid_correction=postprocess.grid_correction_table(...)``: flux, normalisation and overlaps then include the
-    finite-grid correction factors of ``ModeSolver._grid_correction`` (mode_solver.py:847-904), like the reference's.
+    finite-grid correction factors of ``ModeSolver._grid_correction`` (mode_solver.py:847-904), like the reference's; and
+    ``plane_bounds=(xmin, xmax, ymin, ymax)`` (``plugin.plane_bounds_of``): the extent of a finite mode plane, to which the
+    integration weights are truncated like the reference's ``_diff_area`` (monitor_data.py:437-455).
     """
     post = tuple(post or ())
     unknown = set(post) - {"gauge", "normalize", "flux", "overlaps"}
@@ -124,7 +126,7 @@ def compute_modes_batch(
             section=section,
             mu_cross=p.get("mu_cross"), target_override=target_override,
             incidence=(split is not None or p.get("mu_cross") is not None),  # solver.py:93
-            post=post_flags, grid_correction=p.get("grid_correction"),
+            post=post_flags, grid_correction=p.get("grid_correction"), plane_bounds=p.get("plane_bounds"),
         )  # fmt: skip
         if split is None and section is None:
             cache[key] = pk.eps
