@@ -913,13 +913,24 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
           const std::vector<int> &all = kv.second;
           const size_t per = bytes_per_problem(W.setups[all[0]], h->opt);
           int bmax = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, h->opt.max_batch), (size_t)(0.8 * free_b) / per));
-          for (size_t s0 = 0; s0 < all.size(); s0 += bmax) {
+          for (size_t s0 = 0; s0 < all.size();) {
             std::vector<int> ids(all.begin() + s0, all.begin() + std::min(all.size(), s0 + bmax));
             const ProblemSetup &sg = W.setups[ids[0]];
             const size_t pb = (size_t)6 * sg.nx * sg.ny * sg.num_modes * (prob[i0 + ids[0]].precision == 1 ? 8 : 16);
             unsigned char *region = ob.p + cursor;
             if (cursor + pb * ids.size() > ob.cap) throw std::runtime_error("output buffer accounting error");
-            dispatch_group(kv.first.kind, h->opt.mg_precision == 1, h, ids, W, prob, res, region, copies);
+            try {
+              dispatch_group(kv.first.kind, h->opt.mg_precision == 1, h, ids, W, prob, res, region, copies);
+            } catch (const DeviceOutOfMemory &) {
+              // bytes_per_problem is an estimate (other processes, fragmentation): the arena is reserved before anything else
+              // of the batch happens, so the same problems are simply solved in smaller device batches
+              if (ids.size() == 1) throw;
+              bmax = std::max<int>(1, (int)ids.size() / 2);
+              h->arena.release();
+              if (h->opt.verbose) fprintf(stderr, "[b200ms] solver arena does not fit: device batch reduced to %d problems\n", bmax);
+              continue;
+            }
+            s0 += ids.size();
             post_batch(h, ids, W, prob, res, region, pb);  // gauge / flux / normalisation in HBM, before delivery
             for (size_t b = 0; b < ids.size(); ++b) {
               const int id = ids[b];

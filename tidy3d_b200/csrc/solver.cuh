@@ -31,6 +31,12 @@ namespace b200ms {
                                std::to_string(__LINE__));                                             \
   } while (0)
 
+// the solver arena of a device batch does not fit: the caller retries with fewer problems per batch (api.cu)
+struct DeviceOutOfMemory : std::runtime_error {
+  size_t bytes;
+  explicit DeviceOutOfMemory(size_t n) : std::runtime_error("CUDA error: out of memory reserving " + std::to_string(n) + " bytes for the solver arena"), bytes(n) {}
+};
+
 // ---- simple device arena ---------------------------------------------------------------------------
 struct Arena {
   unsigned char *base = nullptr;
@@ -43,7 +49,13 @@ struct Arena {
     if (base) cudaFree(base);
     base = nullptr;
     cap = 0;
-    CUDA_CHECK(cudaMalloc(&base, bytes));
+    const cudaError_t e = cudaMalloc(&base, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();  // clear the sticky-free allocation error: the context is intact
+      base = nullptr;
+      throw DeviceOutOfMemory(bytes);
+    }
+    CUDA_CHECK(e);
     cap = bytes;
     used = 0;
   }
