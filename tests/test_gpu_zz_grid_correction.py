@@ -72,3 +72,30 @@ def test_te_fraction_of_an_angled_plane_is_taken_in_the_propagation_axes(name):
     tol = 1e-5 if raw.dtype == np.complex64 else 1e-10
     assert np.abs(info[0]["te_fraction"] - want).max() < tol
     assert np.abs(want - OP.pol_fraction(raw.astype(complex), wl.coords)).max() > 1e-4  # the rotation matters
+
+
+def test_flux_and_overlaps_of_a_finite_plane():
+    """b200ms_problem.plane_bounds (ABI v203): the plane ends inside the second / second-to-last cell on every side; flux,
+    normalisation, TE fraction and overlaps on the device use the truncated integration cells of the reference's _diff_area
+    (monitor_data.py:437-455; the restatement is pinned to it by tests/golden/post_finite_plane.npz)."""
+    wl = W.c1()
+    x, y = (np.asarray(c, float) for c in wl.coords)
+    pb = (x[1] + 0.37 * (x[2] - x[1]), x[-2] - 0.61 * (x[-2] - x[-3]), y[1] + 0.2 * (y[2] - y[1]), y[-2] - 0.45 * (y[-2] - y[-3]))
+    freqs = [wl.freqs[0] * s for s in (1.0, 1.01)]
+    probs = [dict(eps_cross=wl.eps_cross, coords=wl.coords, freq=f, mode_spec=wl.mode_spec) for f in freqs]
+    h = get_handle(tolerance="tight")
+    raw = compute_modes_batch(probs, handle=h)
+    out, info = compute_modes_batch([dict(p, plane_bounds=pb) for p in probs], handle=h, post=("gauge", "normalize", "flux", "overlaps"), return_info=True)
+    prev = None
+    for i, ((f_raw, n_raw, _), (f_post, _, _)) in enumerate(zip(raw, out)):
+        g, _ = OP.gauge(f_raw.astype(complex))
+        fn, fl = OP.normalize(g, wl.coords, plane_bounds=pb)
+        assert np.abs(info[i]["flux"] - fl).max() < 1e-9 * np.abs(fl).max()
+        assert np.abs(f_post - fn).max() < 1e-9 * np.abs(fn).max()
+        assert np.abs(info[i]["te_fraction"] - OP.pol_fraction(g, wl.coords, plane_bounds=pb)).max() < 1e-9
+        if prev is not None:
+            assert np.abs(info[i]["overlap_prev"] - OP.dot(prev, fn, wl.coords, plane_bounds=pb)).max() < 1e-9
+        prev = fn
+    # the truncation reaches the result: a mode that fills the plane loses the half cells at the rim
+    da_full, da_cut = OP.diff_area(wl.coords), OP.diff_area(wl.coords, plane_bounds=pb)
+    assert da_cut.sum() < da_full.sum() - 1e-6
