@@ -199,3 +199,20 @@ def test_plane_bounds_of_reads_the_plane_of_the_mode_solver():
         bounds = (tuple(center - np.array(size) / 2), tuple(center + np.array(size) / 2))
         ms = types.SimpleNamespace(normal_axis=normal, plane=types.SimpleNamespace(bounds=bounds))
         assert np.allclose(plugin.plane_bounds_of(ms), want)
+
+
+@pytest.mark.parametrize("name", ["plain", "sym_pmc_x", "sym_pec_y", "sym_both", "one_cell_y"])
+def test_product_colocate_reproduces_the_reference_colocated_data(built_lib, name):
+    """``tidy3d_b200.postprocess.colocate`` (library tables) on the reference's normalised Yee-grid data == the data the
+    reference's ``ModeSolver(colocate=True)`` delivers (``_colocate_data`` before ``_normalize_modes``: the two commute up to
+    the flux the normalisation divides by, which is the same number), symmetry planes and a one-cell axis included."""
+    from tidy3d_b200 import postprocess as PP
+
+    z = np.load(os.path.join(GOLDEN, f"post_{name}.npz"))
+    c = PC.from_arrays(name, {k: z[f"in_{k}"] for k in PC.ARRAYS})
+    for i in range(c["nf"]):
+        yee = z["ref_normalized_yee"][:, :, :, :, i, :][:, :, :, :, None, :]
+        got, (px, py) = PP.colocate(yee, c["coords"], c["symmetry"])
+        want = z["ref_colocated"][:, :, :, :, i, :]
+        assert got.shape[2:4] == want.shape[2:4] == (px.size, py.size)
+        assert np.abs(got[:, :, :, :, 0, :] - want).max() < 1e-12 * np.abs(want).max()

@@ -130,3 +130,45 @@ def grid_correction_factors(n_complex, freq: float, table, angle_theta: float = 
     primal = t[1] * np.exp(1j * k * t[0]) + t[3] * np.exp(1j * k * t[2])
     dual = t[5] * np.exp(1j * k * t[4]) + t[7] * np.exp(1j * k * t[6])
     return primal, dual
+
+
+# Yee sites of the six components in the solver plane (components/grid/grid.py Grid.yee): c = cell centre, b = lower boundary
+_SITES = (("c", "b"), ("b", "c"), ("b", "b"), ("b", "c"), ("c", "b"), ("c", "c"))  # Ex Ey Ez Hx Hy Hz
+
+
+def colocate(fields: np.ndarray, coords, symmetry=(0, 0)):
+    """``ModeSolver._colocate_data`` (mode_solver.py:490-515) for delivered Yee-grid fields: every component linearly
+    interpolated to the interior cell boundaries (plus the symmetry plane itself where the plane has a symmetry wall, the
+    half-domain data being mirrored first as ``symmetry_expanded`` does, monitor_data.py:237-282) -- the format of
+    ``ModeSolver(colocate=True)``, the reference's default.  ``fields``: (2,3,Nx,Ny,1,M) as ``compute_modes`` returns them
+    (after ``post=("gauge", "normalize")`` they are the normalised modes, and colocating commutes with both).  Returns
+    ``(colocated (2,3,Px,Py,1,M), (x_points, y_points))``.
+
+    The interpolation tables are the library's own (the ones its flux / overlap kernels use on the device, host code of
+    ``csrc/api.cu``), so the colocated fields integrate to the flux the device reports."""
+    import ctypes as C
+
+    from . import _cabi
+
+    f = np.asarray(fields)
+    tabs, pts = [], []
+    for c, s in zip(coords, symmetry):
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        n = c.size - 1
+        idx, wgt, area = np.zeros(4 * (n + 1), np.int32), np.zeros(4 * (n + 1)), np.zeros(n + 1)
+        npt = _cabi.lib().b200ms_debug_post_tables(_cabi._ptr(c), n, int(s), n + 1, idx.ctypes.data_as(_cabi._ip), _cabi._ptr(wgt), _cabi._ptr(area))
+        if npt < 1:
+            raise ValueError("bad coordinates")
+        tabs.append((idx[: 4 * npt].reshape(npt, 4), wgt[: 4 * npt].reshape(npt, 4)))
+        pts.append((c[1:-1] if s == 0 else c[:-1]) if n > 1 else 0.5 * (c[:1] + c[1:]))
+    out = np.empty(f.shape[:2] + (tabs[0][0].shape[0], tabs[1][0].shape[0]) + f.shape[4:], dtype=f.dtype)
+    for k, kinds in enumerate(_SITES):
+        g = f[k // 3, k % 3]
+        for ax, kind in enumerate(kinds):
+            idx, wgt = tabs[ax]
+            o = 0 if kind == "c" else 2
+            shape = [1] * g.ndim
+            shape[ax] = -1
+            g = np.take(g, idx[:, o], axis=ax) * wgt[:, o].reshape(shape) + np.take(g, idx[:, o + 1], axis=ax) * wgt[:, o + 1].reshape(shape)
+        out[k // 3, k % 3] = g
+    return out, tuple(pts)
