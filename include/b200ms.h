@@ -146,7 +146,11 @@ typedef struct {
   double *te_fraction;   /* NULL, or caller-allocated num_modes doubles: TE polarisation fraction int|E1|^2 / int(|E1|^2+|E2|^2) of the
                             colocated field (ModeData.pol_fraction, monitor_data.py:1625-1652), the input of the filter_pol re-ordering
                             (mode_solver.py:523-549); for angle_theta / angle_phi != 0 the field is first rotated to the propagation
-                            axes like the reference does (monitor_data.py:1603-1607) */
+                            axes like the reference does (monitor_data.py:1603-1607).  Known deviation: for an angled plane that
+                            ALSO has a symmetry wall the reference integrates over the symmetry-expanded plane, where the products
+                            of field components of opposite parity that the rotation creates cancel between the two halves; the
+                            device integrates the half domain and keeps them (an angled mode breaks the mirror symmetry, so such a
+                            plane is unphysical to begin with; restated and pinned in oracle/postprocess.py pol_fraction) */
   double *overlap_prev;  /* NULL, or caller-allocated num_modes^2 complex128 (re,im), row-major [m_prev][m]: modal overlap
                             dot(mode m_prev of the PREVIOUS problem of this call, mode m of this one) (monitor_data.py:640-697,
                             after gauge/normalisation), the input of overlap_sort (monitor_data.py:1295-1375).  Zeros when

@@ -191,12 +191,32 @@ def rotation_matrix(axis, angle):
     return rot
 
 
+def _expand_colocated(c, da, symmetry):
+    """The colocated half-domain data ``c`` (name -> (Px, Py, M)) and its cell sizes ``da`` on the FULL, mirrored plane, as the
+    reference's methods see them (``_colocated_fields`` works on ``symmetry_expanded`` data, monitor_data.py:527-542): the
+    points right of a symmetry plane are mirrored with the factor ``sym_val * symmetry_eigenvalue``; the point ON the plane
+    (the first one) is not duplicated and its cell is twice the half-domain one."""
+    c = dict(c)
+    for ax, s0 in enumerate(symmetry):
+        if s0 == 0:
+            continue
+        for name in c:
+            f = c[name]
+            mirrored = np.flip(np.delete(f, 0, axis=ax), axis=ax) * (s0 * symmetry_eigenvalue(name, ax))
+            c[name] = np.concatenate([mirrored, f], axis=ax)
+        first = np.take(da, [0], axis=ax)
+        da = np.concatenate([np.flip(np.delete(da, 0, axis=ax), axis=ax), 2 * first, np.delete(da, 0, axis=ax)], axis=ax)
+    return c, da
+
+
 def pol_fraction(fields, coords, symmetry=(0, 0), angle_theta=0.0, angle_phi=0.0, plane_bounds=None):
     """monitor_data.py:1625-1652: TE fraction = int |E1|^2 dS / int (|E1|^2 + |E2|^2) dS of the colocated field, E1 / E2 its
-    first two components in the propagation axes (:1584-1614: [tangential 1, tangential 2, normal] rotated by -phi around
-    the normal and then by -theta around the second axis)."""
-    c = colocate(fields, coords, symmetry)
-    da = diff_area(coords, symmetry, plane_bounds)
+    first two components in the propagation axes (:1584-1614: [tangential 1, tangential 2, normal] rotated by -phi around the
+    normal and then by -theta around the second axis).  The integrals run over the symmetry-EXPANDED plane: for an angled
+    plane with a symmetry wall the rotation mixes components of opposite parity, whose products cancel between the two halves
+    (pinned by the fuzzed comparison with the reference, tests/golden/post_angled_sym.npz) -- the half-domain integral times
+    two is NOT the same number there."""
+    c, da = _expand_colocated(colocate(fields, coords, symmetry), diff_area(coords, symmetry, plane_bounds), symmetry)
     field = np.array([c["Ex"], c["Ey"], c["Ez"]])
     if angle_phi != 0:
         field = np.tensordot(rotation_matrix([0, 0, 1], -angle_phi), field, axes=1)

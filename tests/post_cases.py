@@ -28,6 +28,9 @@ CASES = {
     "filter_te": dict(nx=8, ny=8, m=4, nf=2, filter_pol="te", seed=11),
     "filter_tm_track": dict(nx=8, ny=7, m=4, nf=3, filter_pol="tm", track="central", coherent=True, swaps=(2,), seed=12),
     "finite_plane": dict(nx=9, ny=8, m=2, nf=2, plane_cut=(0.37, 0.61, 0.2, 0.45), seed=13),
+    # an angled plane WITH symmetry walls (unphysical, but the reference computes something definite: found by fuzzing)
+    "angled_sym": dict(nx=6, ny=7, m=3, nf=2, symmetry=(1, -1), theta=0.19, phi=-0.53, direction="-", seed=14),
+    "angled_sym_x": dict(nx=5, ny=6, m=2, nf=2, symmetry=(-1, 0), theta=-0.22, phi=0.31, filter_pol="te", seed=15),
 }
 
 
@@ -154,7 +157,7 @@ def reference_results(c):
         b = norm._isel(f=[i + 1])._assign_coords(f=[c["freqs"][i]])
         dots.append(a.dot(b).values.ravel())
         outers.append(a.outer_dot(b).to_numpy()[0])
-    out["dot_next"], out["outer_next"] = np.array(dots), np.array(outers)
+    out["dot_next"], out["outer_next"] = np.array(dots).reshape(nf - 1, c["m"]), np.array(outers).reshape(nf - 1, c["m"], c["m"])
     ms = make(False, c["track"], c["filter_pol"])
     final = ms.data_raw  # the whole of data_raw: + polarisation filter (:523-549) + mode tracking (monitor_data.py:1295-1505)
     rec = RP.last_reorder()
