@@ -216,3 +216,30 @@ def oracle_results(c):
     out["final_yee"] = pack([(cur[i][..., sorting[i]] * np.exp(-1j * phase[i]))[:, :, :, :, 0, :] for i in range(nf)])
     out["final_n_complex"] = np.array([n_c[i][sorting[i]] for i in range(nf)])
     return out
+
+
+def random_case(rng):
+    """A random case description (for ``CASES``-style use) covering the option space: sizes incl. one-cell axes, both symmetry
+    kinds, angles, one- / two-point normal grids, direction, tracking, polarisation filters, finite planes.  Excluded, because the
+    reference itself cannot do them: a two-cell axis (its ``_diff_area`` and its colocation disagree about the number of points)
+    and mode tracking on a one-cell axis (``outer_dot`` interpolates along the one-point axis, see ``skipped_keys``)."""
+    nx, ny = (int(rng.choice([1, 3, 4, 5, 6, 7, 8])) for _ in range(2))
+    if nx == 1 and ny == 1:
+        nx = 3
+    sym = (int(rng.choice([0, 0, 1, -1])) if nx > 1 else 0, int(rng.choice([0, 0, 1, -1])) if ny > 1 else 0)
+    m, nf = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+    case = dict(nx=nx, ny=ny, m=m, nf=nf, symmetry=sym, direction=str(rng.choice(["+", "-"])), seed=int(rng.integers(1 << 30)))
+    if rng.random() < 0.5:
+        case.update(theta=float(rng.uniform(-0.4, 0.4)), phi=float(rng.uniform(-1, 1)))
+    r = rng.random()
+    if r < 0.3:
+        case["normal"] = ([-0.04, 0.05], [-0.09, 0.01], float(rng.uniform(-0.03, 0.0)))
+    elif r < 0.5:
+        case["normal"] = ([0.013], [0.04], 0.013)
+    if rng.random() < 0.5 and nf > 1 and min(nx, ny) > 1:
+        case.update(track=str(rng.choice(["central", "lowest", "highest"])), coherent=bool(rng.random() < 0.7), swaps=(1,) if rng.random() < 0.5 else ())
+    if rng.random() < 0.3 and m > 1:
+        case["filter_pol"] = str(rng.choice(["te", "tm"]))
+    if sym == (0, 0) and nx >= 4 and ny >= 4 and rng.random() < 0.3:
+        case["plane_cut"] = tuple(float(v) for v in rng.uniform(0.05, 0.95, 4))
+    return case

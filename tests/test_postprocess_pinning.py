@@ -61,6 +61,27 @@ def test_restatement_against_the_live_reference(name):
 
 
 @pytest.mark.reference
+def test_restatement_fuzzed_against_the_live_reference():
+    """40 random cases over the whole option space (tests/post_cases.random_case; 240 were run when the fixtures were made:
+    tools/fuzz_reference.py): restatement == the reference's own code."""
+    if not _live():
+        pytest.skip("no reference tree here")
+    rng = np.random.default_rng(20260924)
+    for _ in range(40):
+        case = PC.random_case(rng)
+        PC.CASES["_fuzz"] = case
+        try:
+            c = PC.inputs("_fuzz")
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                ref = PC.reference_results(c)
+            err = PC.compare(ref, PC.oracle_results(c), skip=PC.skipped_keys(c))
+        finally:
+            PC.CASES.pop("_fuzz")
+        assert max(err.values()) < 1e-10, (case, err)
+
+
+@pytest.mark.reference
 def test_fixtures_are_current():
     """The committed fixtures are what the reference tree in this container produces."""
     if not _live():
