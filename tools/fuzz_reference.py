@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Fuzz the f-1 / f-2 restatements (oracle/postprocess.py, oracle/sections.py + plugin.section_of + the library's host mirror
+"""Fuzz the restatements of oracle/ -- the numerics (oracle/restatement.py), f-1 and f-2 (oracle/postprocess.py, oracle/sections.py + plugin.section_of + the library's host mirror
 of the device rasteriser) against the UNMODIFIED reference's own code (oracle/ref_post.py, oracle/ref_sections.py).  Build
 container only.     python tools/fuzz_reference.py [seed] [cases]"""
 import ctypes as C
@@ -90,6 +90,57 @@ def fuzz_sections(rng, n):
     return bad
 
 
+def fuzz_numerics(rng, n):
+    """oracle/restatement.py against the unmodified reference's compute_modes (oracle/ref_shim.py) on random small problems:
+    n_eff to 1e-9 (double) / 2e-6 (single: float32 matrices), fields by separate E / H overlaps with a common phase."""
+    from oracle import ref_shim
+    from oracle import restatement as R
+    from tests.helpers import mode_overlaps, well_separated
+    from tidy3d_b200 import workloads as W
+
+    ref = ref_shim.load()
+    bad = 0
+    for t in range(n):
+        nx, ny = int(rng.choice([1, 12, 17, 24])), int(rng.choice([1, 10, 16, 21]))
+        if nx == 1 and ny == 1:
+            nx = 15
+        x = np.cumsum(np.r_[rng.uniform(-1, 0), rng.uniform(0.04, 0.08, nx)])
+        y = np.cumsum(np.r_[rng.uniform(-1, 0), rng.uniform(0.04, 0.08, ny)])
+        xm, ym = 0.5 * (x[:-1] + x[1:]), 0.5 * (y[:-1] + y[1:])
+        blob = np.exp(-((xm[:, None] - xm.mean()) / 0.25) ** 2 - ((ym[None, :] - ym.mean()) / 0.2) ** 2)
+        base = 2.1 + 9 * blob + 0.1 * rng.random((nx, ny))
+        kind = int(rng.integers(0, 3))
+        eps = [np.zeros((nx, ny), complex) for _ in range(9)]
+        for k, s in zip((0, 4, 8), (1.0, 1.05, 0.95)):
+            eps[k] = base * s + 0j
+        if kind == 1:
+            for k in (0, 4, 8):
+                eps[k] = eps[k] + 1j * 0.05 * blob
+        if kind == 2:
+            eps[1] = eps[3] = 0.05 * base + 0j
+        npml = (int(rng.choice([0, 0, 3])) if nx > 12 else 0, int(rng.choice([0, 0, 3])) if ny > 12 else 0)
+        sym = (int(rng.choice([0, 0, 1, -1])) if nx > 1 else 0, int(rng.choice([0, 0, 1, -1])) if ny > 1 else 0)
+        spec = W.ModeSpecLike(num_modes=int(rng.integers(1, 3)), num_pml=npml, target_neff=None if rng.random() < 0.4 else float(rng.uniform(2.0, 3.0)),
+                              precision=str(rng.choice(["single", "double"])))
+        r = rng.random()
+        if r < 0.25 and nx > 1 and ny > 1:
+            spec.bend_radius, spec.bend_axis = float(rng.choice([-1, 1]) * rng.uniform(4, 10)), int(rng.integers(0, 2))
+        elif r < 0.5:
+            spec.angle_theta, spec.angle_phi = float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-1, 1))
+        direction, freq = str(rng.choice(["+", "-"])), W.C_0 / float(rng.uniform(1.3, 1.6))
+        try:
+            f0, n0, s0 = ref.compute_modes(eps_cross=eps, coords=[x, y], freq=freq, mode_spec=spec, symmetry=sym, direction=direction)
+        except Exception:  # noqa: BLE001  (ARPACK did not converge on this random problem: nothing to compare)
+            continue
+        f1, n1, s1 = R.compute_modes(eps, [x, y], freq, spec, symmetry=sym, direction=direction)
+        ok = well_separated(n0, 1e-3)
+        ov = mode_overlaps(f1.astype(complex), f0.astype(complex))[ok]
+        if s0 != s1 or f0.dtype != f1.dtype or np.abs(n0 - n1).max() > (1e-9 if spec.precision == "double" else 2e-6) or (ov.size and ov.min() < 1 - 1e-4):
+            bad += 1
+            print("numerics MISMATCH", t, nx, ny, kind, npml, sym, vars(spec), direction)
+    return bad
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore")
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
@@ -97,4 +148,5 @@ if __name__ == "__main__":
     rng = np.random.default_rng(seed)
     b1 = fuzz_post(rng, n)
     b2 = fuzz_sections(rng, n)
-    print(f"seed {seed}: {n} post-processing cases, {b1} mismatches; {n} scenes, {b2} mismatches")
+    b3 = fuzz_numerics(rng, n)
+    print(f"seed {seed}: {n} post-processing cases, {b1} mismatches; {n} scenes, {b2} mismatches; {n} eigenproblems, {b3} mismatches")
