@@ -146,11 +146,9 @@ typedef struct {
   double *te_fraction;   /* NULL, or caller-allocated num_modes doubles: TE polarisation fraction int|E1|^2 / int(|E1|^2+|E2|^2) of the
                             colocated field (ModeData.pol_fraction, monitor_data.py:1625-1652), the input of the filter_pol re-ordering
                             (mode_solver.py:523-549); for angle_theta / angle_phi != 0 the field is first rotated to the propagation
-                            axes like the reference does (monitor_data.py:1603-1607).  Known deviation: for an angled plane that
-                            ALSO has a symmetry wall the reference integrates over the symmetry-expanded plane, where the products
-                            of field components of opposite parity that the rotation creates cancel between the two halves; the
-                            device integrates the half domain and keeps them (an angled mode breaks the mirror symmetry, so such a
-                            plane is unphysical to begin with; restated and pinned in oracle/postprocess.py pol_fraction) */
+                            axes like the reference does (monitor_data.py:1603-1607) and, with a symmetry wall, the integral is
+                            that over the symmetry-expanded plane: products of components of opposite parity, which the rotation
+                            creates, cancel between a point and its mirror image and are left out (except on the wall itself) */
   double *overlap_prev;  /* NULL, or caller-allocated num_modes^2 complex128 (re,im), row-major [m_prev][m]: modal overlap
                             dot(mode m_prev of the PREVIOUS problem of this call, mode m of this one) (monitor_data.py:640-697,
                             after gauge/normalisation), the input of overlap_sort (monitor_data.py:1295-1375).  Zeros when
@@ -304,6 +302,10 @@ int b200ms_debug_grid_factors(const b200ms_problem *prob, const double *n_comple
  * symmetry-expanded data, and its trapezoid weight.  idx / wgt: 4 per point {centre i0, centre i1, boundary i0, boundary i1};
  * returns the number of points, -1 on bad arguments or when max_points is too small */
 int b200ms_debug_post_tables(const double *coords, int n, int sym, int max_points, int *idx, double *wgt, double *area);
+/* |E1|^2 and |E2|^2 (the integrands of te_fraction) at the px x py colocation points of an angled plane, evaluated by the very
+ * functions the device kernel calls: e = px x py x {Ex, Ey, Ez} complex (re,im), symx / symy the problem's symmetry values (the
+ * first point along an axis with a symmetry wall is the wall itself), out = px x py x {te, tm} */
+int b200ms_debug_te_terms(const double *e, int px, int py, double angle_theta, double angle_phi, int symx, int symy, double *out);
 /* the same with the extent [lo, hi] of a finite mode plane along this axis (b200ms_problem.plane_bounds) */
 int b200ms_debug_post_tables_bounded(const double *coords, int n, int sym, double lo, double hi, int max_points, int *idx, double *wgt,
                                      double *area);

@@ -237,3 +237,36 @@ def test_product_colocate_reproduces_the_reference_colocated_data(built_lib, nam
         want = z["ref_colocated"][:, :, :, :, i, :]
         assert got.shape[2:4] == want.shape[2:4] == (px.size, py.size)
         assert np.abs(got[:, :, :, :, 0, :] - want).max() < 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("name", ["angled", "angled_sym", "angled_sym_x", "sym_both", "plain"])
+def test_device_te_fraction_arithmetic_on_the_reference_fixtures(built_lib, name):
+    """The TE fraction exactly as csrc/post.cuh post_scan_kernel forms it -- colocation by the library's tables, |E1|^2 / |E2|^2
+    per point by ``te_tm_terms`` (the host+device function the kernel calls, reached here through b200ms_debug_te_terms with the
+    same symmetry -> cross-term rule), half-domain trapezoid weights -- on the gauge-fixed fields of the reference fixtures
+    equals the reference's ``pol_fraction``, also for an angled plane WITH symmetry walls, where the reference integrates the
+    symmetry-expanded plane and the products of opposite-parity components cancel."""
+    from oracle import postprocess as OP
+    from tidy3d_b200 import postprocess as PP
+
+    z = np.load(os.path.join(GOLDEN, f"post_{name}.npz"))
+    c = PC.from_arrays(name, {k: z[f"in_{k}"] for k in PC.ARRAYS})
+    areas = []
+    for co, n, s in zip(c["coords"], (c["nx"], c["ny"]), c["symmetry"]):
+        idx, wgt, area = np.zeros(4 * (n + 1), np.int32), np.zeros(4 * (n + 1)), np.zeros(n + 1)
+        P = built_lib.lib().b200ms_debug_post_tables(built_lib._ptr(np.ascontiguousarray(co)), n, int(s), n + 1, idx.ctypes.data_as(built_lib._ip),
+                                                     built_lib._ptr(wgt), built_lib._ptr(area))
+        areas.append(area[:P].copy())
+    da = np.outer(*areas)
+    for i in range(c["nf"]):
+        g, _ = OP.gauge(c["fields"][i])
+        col, _ = PP.colocate(g, c["coords"], c["symmetry"])
+        te, tm = np.zeros(c["m"]), np.zeros(c["m"])
+        for m in range(c["m"]):
+            e = np.ascontiguousarray(np.moveaxis(col[0, :, :, :, 0, m], 0, -1))  # (Px, Py, 3)
+            out = np.zeros(e.shape[:2] + (2,))
+            rc = built_lib.lib().b200ms_debug_te_terms(built_lib._ptr(e.view(np.float64)), e.shape[0], e.shape[1], c["theta"], c["phi"],
+                                                       int(c["symmetry"][0]), int(c["symmetry"][1]), built_lib._ptr(out))
+            assert rc == 0
+            te[m], tm[m] = (out[..., 0] * da).sum(), (out[..., 1] * da).sum()
+        assert np.abs(te / (te + tm) - z["ref_te_fraction"][i]).max() < 1e-12, name

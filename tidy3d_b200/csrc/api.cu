@@ -497,6 +497,7 @@ void post_batch(b200ms_handle *h, const std::vector<int> &ids, const Window &W, 
     pp[b].flags = p.post;
     pp[b].ct = std::cos(p.angle_theta); pp[b].st = std::sin(p.angle_theta);
     pp[b].cp = std::cos(p.angle_phi); pp[b].sp = std::sin(p.angle_phi);
+    pp[b].symx = p.symmetry[0]; pp[b].symy = p.symmetry[1];
     do_gauge |= p.post & 1;
     do_norm |= p.post & 2;
   }
@@ -604,6 +605,7 @@ void post_overlaps(b200ms_handle *h, const b200ms_problem *prob, b200ms_result *
       pp[q].flags = 0;
       pp[q].ct = pp[q].cp = 1.0;
       pp[q].st = pp[q].sp = 0.0;
+      pp[q].symx = pp[q].symy = 0;
       pairs[q].a = dev_fields[i - 1];
       pairs[q].b = dev_fields[i];
       pairs[q].prob = q;
@@ -1188,6 +1190,22 @@ extern "C" int b200ms_debug_grid_factors(const b200ms_problem *prob, const doubl
     dual[2 * m] = gd[m].real(); dual[2 * m + 1] = gd[m].imag();
   }
   return B200MS_OK;
+}
+
+// |E1|^2, |E2|^2 at the px x py colocation points of an angled plane exactly as post_scan_kernel evaluates them (same functions):
+// e = px x py x {Ex, Ey, Ez} complex (re,im), point (p, q) at e + 6 (p py + q); out = px x py x {te, tm}
+extern "C" int b200ms_debug_te_terms(const double *e, int px, int py, double angle_theta, double angle_phi, int symx, int symy, double *out) {
+  if (!e || !out || px < 0 || py < 0) return -1;
+  const double ct = std::cos(angle_theta), st = std::sin(angle_theta), cp = std::cos(angle_phi), sp = std::sin(angle_phi);
+  for (int p = 0; p < px; ++p)
+    for (int q = 0; q < py; ++q) {
+      const size_t i = (size_t)p * py + q;
+      const double *v = e + 6 * i;
+      double kxy, kxz, kyz;
+      te_point_flags(symx, symy, p, q, kxy, kxz, kyz);
+      te_tm_terms(mk(v[0], v[1]), mk(v[2], v[3]), mk(v[4], v[5]), ct, st, cp, sp, kxy, kxz, kyz, out[2 * i], out[2 * i + 1]);
+    }
+  return 0;
 }
 
 extern "C" int b200ms_debug_post_tables_bounded(const double *coords, int n, int sym, double lo, double hi, int max_points, int *idx,

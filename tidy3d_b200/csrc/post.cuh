@@ -29,7 +29,30 @@ struct PostProblem {
   double mult;   // 2^(number of symmetry planes)
   int flags;     // b200ms_problem.post: bit 0 gauge, bit 1 flux normalisation
   double ct, st, cp, sp;  // cos / sin of mode_spec.angle_theta, angle_phi: the TE fraction is taken in the propagation axes
+  int symx, symy;         // the problem's symmetry values: which products of E components survive in the TE fraction (te_point_flags)
 };
+
+// Which products of E components the rotation to propagation axes creates survive in the reference's TE fraction: it integrates
+// |E1|^2, |E2|^2 over the symmetry-EXPANDED plane (monitor_data.py:527-542, 1625-1652), where the product of two components of
+// opposite parity under an active mirror cancels between a point and its mirror image.  Under the x mirror Ex is opposite to Ey and
+// Ez, under the y mirror Ey is opposite to Ex and Ez (components/data/dataset.py:210-220).  A colocation point ON a symmetry
+// plane (the first point along that axis, mode_solver.py:499-502) is its own image: nothing cancels there.
+HD void te_point_flags(int symx, int symy, int p, int q, double &kxy, double &kxz, double &kyz) {
+  kxz = (symx == 0 || p == 0) ? 1.0 : 0.0;
+  kyz = (symy == 0 || q == 0) ? 1.0 : 0.0;
+  kxy = kxz * kyz;
+}
+// |E1|^2 and |E2|^2 at one colocation point, E1 = ct (cp Ex + sp Ey) - st Ez, E2 = cp Ey - sp Ex (monitor_data.py:1603-1607 with
+// the rotation matrices of components/transformation.py:112-131), written out so that the cross products can be switched off.
+// Shared by post_scan_kernel and the host hook b200ms_debug_te_terms (tests/test_postprocess_pinning.py).
+HD void te_tm_terms(cplx ex, cplx ey, cplx ez, double ct, double st, double cp, double sp, double kxy, double kxz, double kyz, double &te,
+                    double &tm) {
+  const double axx = ex.re * ex.re + ex.im * ex.im, ayy = ey.re * ey.re + ey.im * ey.im, azz = ez.re * ez.re + ez.im * ez.im;
+  const double xy = ex.re * ey.re + ex.im * ey.im, xz = ex.re * ez.re + ex.im * ez.im, yz = ey.re * ez.re + ey.im * ez.im;  // Re(a b*)
+  const double inplane = cp * cp * axx + sp * sp * ayy + kxy * 2.0 * cp * sp * xy;  // |cp Ex + sp Ey|^2
+  te = ct * ct * inplane + st * st * azz - 2.0 * ct * st * (kxz * cp * xz + kyz * sp * yz);
+  tm = cp * cp * ayy + sp * sp * axx - kxy * 2.0 * cp * sp * xy;
+}
 
 template <typename F> __device__ __forceinline__ cplx ldf(const F *p);
 template <> __device__ __forceinline__ cplx ldf<cplx>(const cplx *p) { return *p; }
@@ -80,10 +103,12 @@ __global__ void __launch_bounds__(256) post_scan_kernel(const PostProblem *pp, i
         // angled plane: the colocated E field is rotated by -phi around the normal, then by -theta around the second tangential
         // axis (monitor_data.py:1603-1607, rotation matrices components/transformation.py:112-131) before |E1|^2, |E2|^2
         const cplx ez = colocated(f, 2, false, false, P.ax, P.ay, nx, ny, M, p, q, m);
-        const cplx e1 = P.ct * (P.cp * ex + P.sp * ey) - P.st * ez;
-        const cplx e2 = P.cp * ey - P.sp * ex;
-        te += abs2(e1) * da;
-        tm += abs2(e2) * da;
+        double t1, t2;
+        double kxy, kxz, kyz;
+        te_point_flags(P.symx, P.symy, p, q, kxy, kxz, kyz);
+        te_tm_terms(ex, ey, ez, P.ct, P.st, P.cp, P.sp, kxy, kxz, kyz, t1, t2);
+        te += t1 * da;
+        tm += t2 * da;
       } else {
         te += abs2(ex) * da;
         tm += abs2(ey) * da;

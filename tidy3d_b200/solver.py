@@ -115,12 +115,6 @@ def compute_modes_batch(
             target_override = float(np.sqrt(np.max(np.abs(ec[np.abs(ec) < abs(PEC_VAL)]))))
         if split is not None and p.get("solver_basis_fields") is not None:
             raise RuntimeError("Split curl not yet implemented for relative mode solver.")  # solver.py:938
-        if "flux" in post and any(p.get("symmetry", (0, 0))) and (getattr(p["mode_spec"], "angle_theta", 0.0) or getattr(p["mode_spec"], "angle_phi", 0.0)):
-            import warnings
-
-            warnings.warn("te_fraction of an angled mode plane with a symmetry wall: the device integrates the half domain, the reference "
-                          "the symmetry-expanded plane, where products of components of opposite parity cancel (include/b200ms.h, "
-                          "b200ms_result.te_fraction); flux and overlaps are not affected", stacklevel=2)
         section = p.get("section")
         if section is not None and (split is not None or p.get("eps_cross") is not None):
             raise ValueError("give either 'eps_cross' or 'section' (a section cannot be combined with split_curl_scaling)")
