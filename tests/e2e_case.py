@@ -13,37 +13,40 @@ import os
 import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "e2e_strip.npz")
+GOLDEN_SYM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "e2e_strip_sym.npz")  # half domain, PMC wall at x = 0 (CPU twin only)
 C0 = 2.99792458e14
 NUM_MODES, NF = 2, 4
 NORMAL_PRIMAL, NORMAL_DUAL = (-0.045, 0.055), (-0.095, 0.005)  # the plane (z = 0) sits between grid points of a coarse normal grid
 
 
-def reference_solver(track):
-    """The reference-made ModeSolver of the case (build container only)."""
+def reference_solver(track, symmetric=False):
+    """The reference-made ModeSolver of the case (build container only).  ``symmetric``: the right half of a mirror-symmetric
+    variant of the scene with a symmetry wall (PMC, +1) at x = 0."""
     from oracle import ref_sections as RS
     from oracle import ref_solver as RSV
 
     rng = np.random.default_rng(3)
-    x = np.cumsum(np.r_[-1.0, rng.uniform(0.045, 0.055, 40)])  # slightly non-uniform
+    x = np.cumsum(np.r_[0.0 if symmetric else -1.0, rng.uniform(0.045, 0.055, 20 if symmetric else 40)])  # slightly non-uniform
     y = np.cumsum(np.r_[-0.8, rng.uniform(0.045, 0.055, 32)])
     edges = [x, y, np.array([-0.02, 0.02])]
     structures = [
-        (RS.geometry("Box", center=(0.02, 0.01, 0.0), size=(0.5, 0.22, 10.0)), RS.TensorMedium(3.48**2 * np.eye(3), 0.02)),  # dispersive core
+        (RS.geometry("Box", center=(0.0 if symmetric else 0.02, 0.01, 0.0), size=(0.5, 0.22, 10.0)), RS.TensorMedium(3.48**2 * np.eye(3), 0.02)),  # dispersive core
         (RS.geometry("Box", center=(0.0, -0.3, 0.0), size=(10.0, 0.36, 10.0)), RS.TensorMedium(np.diag([2.1, 2.15, 2.05]), -0.01)),  # anisotropic substrate
-        (RS.geometry("Sphere", center=(0.5, 0.2, 0.05), radius=0.17), RS.TensorMedium(2.0**2 * np.eye(3))),  # breaks every symmetry
     ]
+    if not symmetric:
+        structures.append((RS.geometry("Sphere", center=(0.5, 0.2, 0.05), radius=0.17), RS.TensorMedium(2.0**2 * np.eye(3))))  # breaks every symmetry
     spec = RSV.ModeSpec(num_modes=NUM_MODES, track_freq=track, group_index_step=0, precision="double")
     freqs = C0 / np.linspace(1.5, 1.6, NF)
     return RSV.mode_solver(edges, 2, structures, RS.TensorMedium(1.44**2 * np.eye(3)), freqs, spec, colocate=False,
-                           normal_primal=NORMAL_PRIMAL, normal_dual=NORMAL_DUAL)
+                           symmetry=(1, 0, 0) if symmetric else (0, 0, 0), normal_primal=NORMAL_PRIMAL, normal_dual=NORMAL_DUAL)
 
 
-def check(solve, tol_n=1e-6, tol_field=2e-4, tol_overlap=2e-4):
+def check(solve, tol_n=1e-6, tol_field=2e-4, tol_overlap=2e-4, symmetric=False):
     """``solve(problems, post) -> (results, info)`` like ``compute_modes_batch(problems, post=post, return_info=True)``."""
     from tidy3d_b200 import postprocess as PP
     from tidy3d_b200.sections import Medium, Section
 
-    z = np.load(GOLDEN)
+    z = np.load(GOLDEN_SYM if symmetric else GOLDEN)
     freqs = list(z["freqs"])
     tables = z["media"]  # (F, nmedia, 3, 3)
 
@@ -55,7 +58,7 @@ def check(solve, tol_n=1e-6, tol_field=2e-4, tol_overlap=2e-4):
     spec = PP_mode_spec()
     gc = PP.grid_correction_table(NORMAL_PRIMAL, NORMAL_DUAL, 0.0)
     coords = [z["x"], z["y"]]
-    problems = [dict(section=sec, coords=coords, freq=float(f), mode_spec=spec, grid_correction=gc) for f in freqs]
+    problems = [dict(section=sec, coords=coords, freq=float(f), mode_spec=spec, grid_correction=gc, symmetry=(1, 0) if symmetric else (0, 0)) for f in freqs]
     results, info = solve(problems, ("gauge", "normalize", "flux", "overlaps"))
     worst = dict(n=0.0, field=0.0, overlap=0.0)
     fields, n_c = [], []

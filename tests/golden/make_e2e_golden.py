@@ -17,20 +17,25 @@ from tests import e2e_case as E  # noqa: E402
 
 
 def main():
+    for symmetric in (False, True):
+        one(symmetric)
+
+
+def one(symmetric):
     from oracle import ref_post as RP
     from oracle import ref_solver as RSV
 
     import tidy3d_b200.plugin as plugin
 
     warnings.simplefilter("ignore")
-    ms = E.reference_solver(track=None)
+    ms = E.reference_solver(track=None, symmetric=symmetric)
     sec = plugin.section_of(ms)
     freqs = np.array(ms.freqs)
     out = dict(x=ms.simulation.edges[0], y=ms.simulation.edges[1], freqs=freqs, site_medium=sec.site_medium,
                media=np.array([[m.tensor(f) for m in sec.media] for f in freqs]))
     yee = ms._data_on_yee_grid()
     out["n_raw"] = yee.n_complex.values
-    norm = E.reference_solver(track=None).data_raw  # gauge + flux normalisation with the grid-correction factors, no tracking
+    norm = E.reference_solver(track=None, symmetric=symmetric).data_raw  # gauge + flux normalisation with the grid-correction factors, no tracking
     out["normalized_yee"] = RP.packed(norm)
     outers = []
     for i in range(len(freqs) - 1):
@@ -48,12 +53,13 @@ def main():
 
     mod.ModeSolverData._reorder_modes = spy
     try:
-        final = E.reference_solver(track="central").data_raw
+        final = E.reference_solver(track="central", symmetric=symmetric).data_raw
     finally:
         mod.ModeSolverData._reorder_modes = orig
     out.update(sorting=rec["sorting"], phase=rec["phase"], final_yee=RP.packed(final), final_n_complex=final.n_complex.values)
-    np.savez_compressed(E.GOLDEN, **out)
-    print(E.GOLDEN, f"{os.path.getsize(E.GOLDEN) / 1024:.0f} KB", "n_raw", out["n_raw"][0], "sorting", out["sorting"].tolist())
+    path = E.GOLDEN_SYM if symmetric else E.GOLDEN
+    np.savez_compressed(path, **out)
+    print(path, f"{os.path.getsize(path) / 1024:.0f} KB", "n_raw", out["n_raw"][0], "sorting", out["sorting"].tolist())
 
 
 if __name__ == "__main__":

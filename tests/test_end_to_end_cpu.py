@@ -18,8 +18,8 @@ from tests import e2e_case as E
 class EmulatedHandle:
     """``_cabi.Handle`` without a device: same ``solve_batch`` contract, results from oracle/."""
 
-    def __init__(self, cabi, problems):
-        self.cabi, self.problems, self.lock = cabi, problems, threading.Lock()
+    def __init__(self, cabi, problems, nmedia=4):
+        self.cabi, self.problems, self.lock, self.nmedia = cabi, problems, threading.Lock(), nmedia
         self.last_flux, self.last_te, self.last_overlaps = [], [], []
         self.setups = 0
 
@@ -38,12 +38,13 @@ class EmulatedHandle:
         self.last_flux, self.last_te, self.last_overlaps = [], [], []
         for i, (pk, p) in enumerate(zip(packed, self.problems)):
             st = pk.struct
-            assert st.post == 3 and not st.eps and st.section and st.section.contents.nrect == 0 and st.section.contents.nmedia == 4
+            assert st.post == 3 and not st.eps and st.section and st.section.contents.nrect == 0 and st.section.contents.nmedia == self.nmedia
+            assert (st.symmetry[0], st.symmetry[1]) == tuple(p["symmetry"])
             assert [st.grid_correction[k] for k in range(8)] == list(p["grid_correction"]) and not st.plane_bounds
             eps = OS.eps_on_grid(p["section"], p["coords"], p["freq"])
             # the library's host mirror of the device rasteriser sets this very struct up like the sampled array
             outs = []
-            for q in (pk, self.cabi.PackedProblem(eps, p["coords"], p["freq"], p["mode_spec"])):
+            for q in (pk, self.cabi.PackedProblem(eps, p["coords"], p["freq"], p["mode_spec"], p["symmetry"])):
                 f = np.zeros((6, q.nx * q.ny), complex)
                 flags, sigma = (C.c_int * 4)(), np.zeros(2)
                 assert self.cabi.lib().b200ms_debug_setup(C.byref(q.struct), self.cabi._ptr(sigma), flags, None, None, None, None, self.cabi._ptr(f.view(float))) == 0
@@ -52,13 +53,14 @@ class EmulatedHandle:
             self.setups += 1
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                f, n, spec = R.compute_modes(eps, p["coords"], p["freq"], p["mode_spec"], tol=1e-12)
+                f, n, spec = R.compute_modes(eps, p["coords"], p["freq"], p["mode_spec"], symmetry=p["symmetry"], tol=1e-12)
             corr = PP.grid_correction_factors(n, p["freq"], p["grid_correction"], 0.0, "+")
             g, _ = OP.gauge(f)
-            fn, fl = OP.normalize(g, p["coords"], correction=corr)
+            fn, fl = OP.normalize(g, p["coords"], p["symmetry"], correction=corr)
             self.last_flux.append(fl)
-            self.last_te.append(OP.pol_fraction(g, p["coords"]))
-            self.last_overlaps.append(OP.dot(prev[0], fn, p["coords"], correction_a=prev[1], correction_b=corr) if prev else np.zeros((n.size, n.size), complex))
+            self.last_te.append(OP.pol_fraction(g, p["coords"], p["symmetry"]))
+            self.last_overlaps.append(OP.dot(prev[0], fn, p["coords"], p["symmetry"], correction_a=prev[1], correction_b=corr) if prev
+                                      else np.zeros((n.size, n.size), complex))
             prev = (fn, corr)
             fields.append(fn)
             ncs.append(n)
@@ -77,4 +79,19 @@ def test_restated_chain_reproduces_the_reference_mode_solver_data(built_lib):
 
     worst = E.check(emulated_device)
     assert state["h"].setups == E.NF
+    assert worst["n"] < 1e-7 and worst["field"] < 1e-4 and worst["overlap"] < 1e-4, worst
+
+
+def test_restated_chain_with_a_symmetry_wall(built_lib):
+    """The same for the right half of a mirror-symmetric scene with a PMC wall at x = 0 (CPU twin only): half-domain solve,
+    symmetry-expanded colocation, doubled integrals, tracking -- against the reference's own ModeSolver.data_raw."""
+    from tidy3d_b200 import compute_modes_batch
+
+    state = {}
+
+    def emulated_device(problems, post):
+        state["h"] = EmulatedHandle(built_lib, problems, nmedia=3)
+        return compute_modes_batch(problems, handle=state["h"], post=post, return_info=True)
+
+    worst = E.check(emulated_device, symmetric=True)
     assert worst["n"] < 1e-7 and worst["field"] < 1e-4 and worst["overlap"] < 1e-4, worst
