@@ -175,3 +175,24 @@ def test_run_batch_one_device_call_for_many_solvers(seam):
     n3 = np.array([r[1] for r in dev.batch([dict(eps_cross=ms._solver_eps(f), coords=dev.calls[0][0]["coords"], freq=f, mode_spec=ms.mode_spec) for f in f3])])
     f0, n0, ng, disp = plugin.group_index(n3, f3, 0.005)
     assert np.allclose(ng, got[0].n_group_raw.values, rtol=1e-12) and np.allclose(disp, got[0].dispersion_raw.values, rtol=1e-9)
+
+
+def test_grid_correction_and_plane_bounds_helpers_on_the_reference_solver(seam):
+    """``plugin.grid_correction_of`` / ``plane_bounds_of`` read a ModeSolver made of the reference's methods; the factors the host
+    helper forms from the table equal ``ModeSolverData.grid_primal_correction / grid_dual_correction`` as the reference's own
+    ``_grid_correction`` computed them (mode_solver.py:847-904), for every plane normal and for backward modes."""
+    plugin, mod, dev = seam
+    from tidy3d_b200 import postprocess as PP
+
+    for normal, direction in ((0, "+"), (1, "-"), (2, "+")):
+        ms = _make(normal, direction=direction)
+        data = ms._data_on_yee_grid()
+        table = plugin.grid_correction_of(ms)
+        for i, f in enumerate(ms.freqs):
+            primal, dual = PP.grid_correction_factors(data.n_complex.values[i], f, table, 0.0, direction)
+            assert np.allclose(primal, data.grid_primal_correction.values[i], rtol=1e-13, atol=1e-15)
+            assert np.allclose(dual, data.grid_dual_correction.values[i], rtol=1e-13, atol=1e-15)
+        assert np.abs(np.abs(data.grid_dual_correction.values) - 1).max() > 1e-4  # not a no-op in this set-up
+        lo, hi = ms.plane.bounds
+        axes = [a for a in range(3) if a != normal]
+        assert list(plugin.plane_bounds_of(ms)) == [lo[axes[0]], hi[axes[0]], lo[axes[1]], hi[axes[1]]]
