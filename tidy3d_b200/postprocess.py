@@ -146,8 +146,6 @@ def colocate(fields: np.ndarray, coords, symmetry=(0, 0)):
 
     The interpolation tables are the library's own (the ones its flux / overlap kernels use on the device, host code of
     ``csrc/api.cu``), so the colocated fields integrate to the flux the device reports."""
-    import ctypes as C
-
     from . import _cabi
 
     f = np.asarray(fields)
