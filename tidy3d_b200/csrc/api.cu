@@ -12,11 +12,23 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler (ncu / nsys) injects itself
+
 #include "../../include/b200ms.h"
 #include "post.cuh"
 #include "solver.cuh"
 
 using namespace b200ms;
+
+// Named ranges for profilers (the phases of one b200ms_solve_batch call on the timeline, one range stack per thread:
+// the upload and delivery helpers run on their own threads).  `ncu --nvtx --nvtx-include "b200ms:eigen-iteration/"` restricts a
+// capture to the kernels of one phase.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // grow-only device buffer
 struct DevBuf {
@@ -680,7 +692,10 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W,
   auto wall0 = std::chrono::steady_clock::now();
   S.single_out_ = prob[W.i0 + ids[0]].precision == 1;
   const MediumRef *d_refs = upload_refs(h, refs, h->stream);
-  S.build(ps, share, d_refs);
+  {
+    NvtxRange r("b200ms:build (hierarchy, coefficient fields, graph capture)");
+    S.build(ps, share, d_refs);
+  }
   S.set_output(reinterpret_cast<cplx *>(out_region));
   h->stats.setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));  // inputs are resident in HBM from here on
@@ -704,6 +719,7 @@ void solve_group(b200ms_handle *h, const std::vector<int> &ids, const Window &W,
                       h->warm_tsize == (int)sizeof(T) && std::memcmp(key, h->warm_key, sizeof(key)) == 0;
     if (warm) S.init_start_from(reinterpret_cast<const T *>(h->warm.p), h->warm_B);
     else S.init_start_vector(0);
+    NvtxRange r("b200ms:eigen-iteration");
     eig = S.krylov_schur(real_arith);
   }
   // eigenvalues of A: lambda = sigma + 1/theta; n = sqrt(-lambda) (principal root, solver.py:884)
@@ -861,12 +877,14 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
     auto upload = [h, prob, nprob, wsize, dev](int wi, Window *W) {
       if (cudaSetDevice(dev) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed in the upload thread");
       const auto t0 = std::chrono::steady_clock::now();
+      NvtxRange r("b200ms:upload + set-up of a window");
       prepare_window(h, prob, wi * wsize, std::min(nprob, (wi + 1) * wsize), h->raw[wi & 1], h->io_stream, *W);
       return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
     auto download = [h, dev](std::vector<FieldCopy> copies) {
       if (cudaSetDevice(dev) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed in the download thread");
       const auto t0 = std::chrono::steady_clock::now();
+      NvtxRange r("b200ms:delivery of a window's fields");
       for (const FieldCopy &c : copies) CUDA_CHECK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDefault, h->dl_stream));
       CUDA_CHECK(cudaStreamSynchronize(h->dl_stream));
       return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -933,7 +951,10 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
               continue;
             }
             s0 += ids.size();
-            post_batch(h, ids, W, prob, res, region, pb);  // gauge / flux / normalisation in HBM, before delivery
+            {
+              NvtxRange r("b200ms:post-processing in HBM");
+              post_batch(h, ids, W, prob, res, region, pb);  // gauge / flux / normalisation in HBM, before delivery
+            }
             for (size_t b = 0; b < ids.size(); ++b) {
               const int id = ids[b];
               dev_fields[i0 + id] = region + b * pb;
@@ -945,7 +966,10 @@ extern "C" int b200ms_solve_batch(b200ms_handle *h, int nprob, const b200ms_prob
             cursor += align256(pb * ids.size());
           }
         }
-        post_overlaps(h, prob, res, i0, i1, dev_fields);  // modal overlaps between consecutive problems (fields still in HBM)
+        {
+          NvtxRange r("b200ms:modal overlaps");
+          post_overlaps(h, prob, res, i0, i1, dev_fields);  // modal overlaps between consecutive problems (fields still in HBM)
+        }
         // deliver the fields of this window (destination may be host or device memory) while the next window is solved;
         // at most one delivery is in flight, so out[wi & 1] is free again by the time window wi + 2 writes it
         if (dl_f.valid()) h->stats.download_ms += dl_f.get();
@@ -1115,6 +1139,7 @@ extern "C" int b200ms_debug_schur(int n, const double *a, double *t, double *q) 
 extern "C" int b200ms_debug_setup(const b200ms_problem *prob, double *sigma, int *flags, double *target, double *knorm,
                                   double *coef_x, double *coef_y, double *fields) {
   if (!prob) return B200MS_ERR_ARG;
+  NvtxRange r("b200ms:debug set-up (host mirror)");  // also keeps the NVTX path exercised where there is no GPU
   ProblemSetup s;
   setup_problem(*prob, s);
   if (s.status != B200MS_OK && s.status != B200MS_ERR_UNSUPPORTED) return s.status;
